@@ -1,0 +1,366 @@
+"""B200-native data-parallel core of ChanJoon/3D-Astar-Path-Planners — Python face of the C-ABI.
+
+Everything here is a thin ctypes binding of `libb200planner.so` (include/b200_planner.h).  The classes mirror
+the reference's two C++ seams — `GridMap` (include/plan_env/grid_map.h:139-196) and the
+`AlgorithmBase` family (include/Planners/AlgorithmBase.hpp:28-53) — with the reference's own method names
+where a Python spelling exists.  There is NO CPU fallback: importing works without a GPU (so symbol/ABI
+tests can run), but every compute call raises `B200Error` unless an sm_100 device executes it, and loading
+fails loudly when the shared library is missing.
+
+The directory name is not a valid Python identifier; import it through the repo-root shim
+`astar_planners_b200.py`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200planner.so")
+
+ALGORITHMS = ("astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar")
+STATUS_NAMES = {0: "solved", 1: "open_set_empty", 2: "pool_exhausted", 3: "tier_overflow"}
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class MapParams(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("size", C.c_double * 3), ("resolution", C.c_double),
+                ("obstacles_inflation", C.c_double), ("local_update_range", C.c_double * 3),
+                ("ground_height", C.c_double), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PlannerParams(C.Structure):
+    _fields_ = [("resolution", C.c_double), ("lambda_heuristic", C.c_double), ("allocate_num", C.c_int32),
+                ("reserved", C.c_int32), ("cost_weight", C.c_double), ("max_los", C.c_double)]
+
+
+RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("pad", "i4"), ("path_offset", "i8"),
+                         ("g_final", "f8"), ("path_length", "f8"), ("explored_nodes", "i8"), ("iter_num", "i8"),
+                         ("los_checks", "i8"), ("los_samples", "i8"), ("goal_coords", "f8", 3),
+                         ("start_coords", "f8", 3), ("time_us", "f8")])
+assert RESULT_DTYPE.itemsize == 128
+
+# every symbol include/b200_planner.h declares: (name, restype, argtypes)
+_vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+_pp = C.POINTER(C.c_void_p)
+ABI = [
+    ("b200_map_create", C.c_int, [C.POINTER(MapParams), _pp]),
+    ("b200_map_destroy", C.c_int, [_vp]),
+    ("b200_map_set_stream", C.c_int, [_vp, _vp]),
+    ("b200_map_sync", C.c_int, [_vp]),
+    ("b200_map_dims", C.c_int, [_vp, C.POINTER(_i32)]),
+    ("b200_map_get_region", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    ("b200_map_get_resolution", _dbl, [_vp]),
+    ("b200_map_update_cloud", C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, C.POINTER(_dbl), _i32]),
+    ("b200_map_clear_box", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    ("b200_map_reset", C.c_int, [_vp]),
+    ("b200_map_local_bounds", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    ("b200_map_get_inflate_occupancy", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
+    ("b200_map_is_in_map", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
+    ("b200_map_pos_to_index", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
+    ("b200_map_download_inflate", C.c_int, [_vp, _vp]),
+    ("b200_map_upload_inflate", C.c_int, [_vp, _vp]),
+    ("b200_map_device_bits", C.c_int, [_vp, _pp, C.POINTER(_i64)]),
+    ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
+    ("b200_map_download_dist2", C.c_int, [_vp, _vp]),
+    ("b200_map_download_costq", C.c_int, [_vp, _vp]),
+    ("b200_map_download_cost", C.c_int, [_vp, _vp]),
+    ("b200_los_batch", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
+    ("b200_map_set_profiling", C.c_int, [_vp, _i32]),
+    ("b200_map_get_stage_ms", C.c_int, [_vp, C.POINTER(_dbl)]),
+    ("b200_planner_create", C.c_int, [C.c_char_p, C.POINTER(PlannerParams), _pp]),
+    ("b200_planner_destroy", C.c_int, [_vp]),
+    ("b200_planner_set_map", C.c_int, [_vp, _vp]),
+    ("b200_planner_set_cost_factor", C.c_int, [_vp, _dbl]),
+    ("b200_planner_detect_collision", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i32)]),
+    ("b200_planner_find_path", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _i64]),
+    ("b200_planner_find_paths", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32]),
+    ("b200_planner_last_launches", C.c_int, [_vp, C.POINTER(_i32)]),
+    ("b200_last_error", C.c_char_p, []),
+    ("b200_version", C.c_char_p, []),
+    ("b200_host_alloc", C.c_int, [_pp, _i64]),
+    ("b200_host_free", C.c_int, [_vp]),
+]
+
+_LIB = None
+
+
+def build(verbose=False):
+    """Compile libb200planner.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-j4"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    """Load the C-ABI library; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: run `make -C {_HERE}` (or __graft_entry__.build()). "
+                            "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in ABI:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _ck(rc):
+    if rc != 0:
+        raise B200Error(f"b200 error {rc}: {lib().b200_last_error().decode()}")
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _ptr(a):
+    """host numpy array or device pointer carrier (anything with data_ptr(), e.g. a torch CUDA tensor)."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _is_dev(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+class GridMap:
+    """Mirror of the reference `GridMap`'s cloud path (src/plan_env/grid_map.cpp:6-171,711-804).
+
+    `origin=None` reproduces initMap's origin (-sx/2, -sy/2, ground_height) (grid_map.cpp:53).
+    """
+
+    def __init__(self, size, resolution, origin=None, obstacles_inflation=0.099, local_update_range=(5.0, 5.0, 5.0),
+                 ground_height=-0.01, device=0):
+        if origin is None:
+            origin = (-size[0] / 2.0, -size[1] / 2.0, ground_height)
+        p = MapParams()
+        p.origin[:] = [float(x) for x in origin]
+        p.size[:] = [float(x) for x in size]
+        p.resolution = float(resolution)
+        p.obstacles_inflation = float(obstacles_inflation)
+        p.local_update_range[:] = [float(x) for x in local_update_range]
+        p.ground_height = float(ground_height)
+        p.device = int(device)
+        self.params = p
+        self.h = C.c_void_p()
+        _ck(lib().b200_map_create(C.byref(p), C.byref(self.h)))
+        d = (C.c_int32 * 3)()
+        _ck(lib().b200_map_dims(self.h, d))
+        self.dims = tuple(d)
+        self.origin, self.size, self.resolution = tuple(p.origin), tuple(p.size), p.resolution
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_map_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # --- GridMap API (reference names in comments) -------------------------------------------------
+    def cloudCallback(self, cloud, camera_pos, point_step=None, offsets=(0, 4, 8)):
+        """cloudCallback (grid_map.cpp:711-804). `cloud`: float32 array (n, step/4) or a CUDA tensor."""
+        if _is_dev(cloud):
+            step = point_step or cloud.stride(0) * cloud.element_size()
+            n = cloud.shape[0]
+            dev = 1
+        else:
+            cloud = np.ascontiguousarray(cloud)
+            step = point_step or (cloud.strides[0] if cloud.ndim == 2 else 16)
+            n = cloud.nbytes // step
+            dev = 0
+        self._keep = cloud
+        _ck(lib().b200_map_update_cloud(self.h, _ptr(cloud), n, step, *offsets, _d3(camera_pos), dev))
+
+    update_cloud = cloudCallback
+
+    def resetBuffer(self, min_pos=None, max_pos=None):
+        """resetBuffer() / resetBuffer(min,max) (grid_map.cpp:144-171)."""
+        if min_pos is None:
+            _ck(lib().b200_map_reset(self.h))
+        else:
+            _ck(lib().b200_map_clear_box(self.h, _d3(min_pos), _d3(max_pos)))
+
+    def getInflateOccupancy(self, pos, out=None):
+        """getInflateOccupancy (grid_map.h:350-359) for an (n,3) batch -> int8 {-1,0,1}."""
+        if _is_dev(pos):
+            _ck(lib().b200_map_get_inflate_occupancy(self.h, _ptr(pos), pos.shape[0], _ptr(out), 1))
+            return out
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        _ck(lib().b200_map_get_inflate_occupancy(self.h, _ptr(pos), len(pos), _ptr(out), 0))
+        return out
+
+    def isInMap(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.uint8)
+        _ck(lib().b200_map_is_in_map(self.h, _ptr(pos), len(pos), _ptr(out), 0))
+        return out.astype(bool)
+
+    def posToIndex(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((len(pos), 3), dtype=np.int32)
+        _ck(lib().b200_map_pos_to_index(self.h, _ptr(pos), len(pos), _ptr(out), 0))
+        return out
+
+    def getRegion(self):
+        o, s = (C.c_double * 3)(), (C.c_double * 3)()
+        _ck(lib().b200_map_get_region(self.h, o, s))
+        return tuple(o), tuple(s)
+
+    def getResolution(self):
+        return lib().b200_map_get_resolution(self.h)
+
+    def local_bounds(self):
+        a, b = (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        _ck(lib().b200_map_local_bounds(self.h, a, b))
+        return tuple(a), tuple(b)
+
+    def inflate(self):
+        """occupancy_buffer_inflate_ as uint8 [Nx,Ny,Nz] (reference byte layout)."""
+        out = np.empty(self.dims, dtype=np.uint8)
+        _ck(lib().b200_map_download_inflate(self.h, _ptr(out)))
+        return out
+
+    def set_inflate(self, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert grid.shape == self.dims
+        _ck(lib().b200_map_upload_inflate(self.h, _ptr(grid)))
+
+    # --- new functionality ------------------------------------------------------------------------
+    def build_edt(self, d_safe=0.0):
+        _ck(lib().b200_map_build_edt(self.h, float(d_safe)))
+
+    def dist2(self):
+        out = np.empty(self.dims, dtype=np.int32)
+        _ck(lib().b200_map_download_dist2(self.h, _ptr(out)))
+        return out
+
+    def costq(self):
+        out = np.empty(self.dims, dtype=np.uint16)
+        _ck(lib().b200_map_download_costq(self.h, _ptr(out)))
+        return out
+
+    def cost(self):
+        out = np.empty(self.dims, dtype=np.float32)
+        _ck(lib().b200_map_download_cost(self.h, _ptr(out)))
+        return out
+
+    def los_batch(self, starts, ends, return_samples=False, vis_out=None, samples_out=None):
+        """LineOfSight::fastLOS (LineOfSight.cpp:9-27) for n segments."""
+        if _is_dev(starts):
+            _ck(lib().b200_los_batch(self.h, _ptr(starts), _ptr(ends), starts.shape[0], _ptr(vis_out), _ptr(samples_out), 1))
+            return vis_out
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        e = np.ascontiguousarray(ends, dtype=np.float64).reshape(-1, 3)
+        vis = np.empty(len(s), dtype=np.uint8)
+        ns = np.empty(len(s), dtype=np.int32)
+        _ck(lib().b200_los_batch(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(ns), 0))
+        return (vis, ns) if return_samples else vis
+
+    def set_stream(self, cuda_stream_ptr):
+        _ck(lib().b200_map_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        _ck(lib().b200_map_sync(self.h))
+
+    def set_profiling(self, on=True):
+        _ck(lib().b200_map_set_profiling(self.h, 1 if on else 0))
+
+    def stage_ms(self):
+        out = (C.c_double * 8)()
+        _ck(lib().b200_map_get_stage_ms(self.h, out))
+        return list(out)
+
+
+class Planner:
+    """Mirror of `Planners::AlgorithmBase` (AlgorithmBase.hpp:28-53): setGridMap / setCostFactor /
+    detectCollision / findPath / getPath, plus the batched `findPaths`."""
+
+    def __init__(self, algorithm="astar", resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0,
+                 max_los=0.0):
+        p = PlannerParams(float(resolution), float(lambda_heuristic), int(allocate_num), 0, float(cost_weight), float(max_los))
+        self.h = C.c_void_p()
+        _ck(lib().b200_planner_create(algorithm.encode(), C.byref(p), C.byref(self.h)))
+        self.algorithm = algorithm if algorithm in ALGORITHMS else "astar"
+        self._path = np.zeros((0, 3))
+        self.map = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def setGridMap(self, grid_map):
+        self.map = grid_map
+        _ck(lib().b200_planner_set_map(self.h, grid_map.h))
+
+    def setCostFactor(self, w):
+        _ck(lib().b200_planner_set_cost_factor(self.h, float(w)))
+
+    def detectCollision(self, pos):
+        out = C.c_int32()
+        _ck(lib().b200_planner_detect_collision(self.h, _d3(pos), C.byref(out)))
+        return bool(out.value)
+
+    def findPath(self, source, target, path_cap=65536):
+        """reset() + findPath(src,tgt) (AStar.cpp:80-179). Returns the PathData-like dict of
+        createResultDataObject (AlgorithmBase.cpp:123-175)."""
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        path = np.empty((path_cap, 3), dtype=np.float64)
+        _ck(lib().b200_planner_find_path(self.h, _d3(source), _d3(target), _ptr(res), _ptr(path), path_cap))
+        r = res[0]
+        self._path = path[: min(int(r["n_path"]), path_cap)].copy()
+        return {
+            "solved": bool(r["solved"]), "goal_coords": r["goal_coords"].copy(), "g_final_node": float(r["g_final"]),
+            "algorithm": self.algorithm, "path": self._path, "time_spent": float(r["time_us"]),
+            "explored_nodes": int(r["explored_nodes"]), "start_coords": r["start_coords"].copy(),
+            "path_length": float(r["path_length"]), "total_cost1": 0, "total_cost2": 0, "h_cost": 0, "g_cost1": 0,
+            "g_cost2": 0, "c_cost": 0, "grid_cost1": 0, "grid_cost2": 0, "line_of_sight_checks": int(r["los_checks"]),
+            "status": STATUS_NAMES.get(int(r["status"]), "?"), "iter_num": int(r["iter_num"]),
+            "los_samples": int(r["los_samples"]),
+        }
+
+    def getPath(self):
+        return self._path
+
+    def findPaths(self, starts, goals, path_cap=None, results=None, path_buf=None):
+        """nq independent reset()+findPath() pairs. Host numpy in/out, or CUDA tensors for all of
+        starts/goals/results(/path_buf) (results: uint8 tensor of nq*128 bytes)."""
+        if _is_dev(starts):
+            nq = starts.shape[0]
+            cap = 0 if path_buf is None else path_buf.shape[0]
+            _ck(lib().b200_planner_find_paths(self.h, _ptr(starts), _ptr(goals), nq, _ptr(results), _ptr(path_buf), cap, 1))
+            return results, path_buf
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        g = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, 3)
+        nq = len(s)
+        res = np.zeros(nq, dtype=RESULT_DTYPE) if results is None else results
+        cap = int(path_cap) if path_cap is not None else 0
+        path = (np.empty((cap, 3), dtype=np.float64) if path_buf is None else path_buf) if cap else None
+        _ck(lib().b200_planner_find_paths(self.h, _ptr(s), _ptr(g), nq, _ptr(res), _ptr(path), cap, 0))
+        return res, path
+
+    def last_launches(self):
+        out = C.c_int32()
+        _ck(lib().b200_planner_last_launches(self.h, C.byref(out)))
+        return out.value
+
+
+def path_of(results, path, i):
+    r = results[i]
+    if r["path_offset"] < 0:
+        return None
+    return path[r["path_offset"]: r["path_offset"] + r["n_path"]]

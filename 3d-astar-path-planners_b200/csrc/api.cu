@@ -1,0 +1,696 @@
+// api.cu — the C-ABI of include/b200_planner.h: handles, device buffers, streams and launch sequencing.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof buf, "%s", what);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(B200_ERR_CUDA, #call, e__);     \
+  } while (0)
+#define REQUIRE(cond, msg)                               \
+  do {                                                   \
+    if (!(cond)) return fail(B200_ERR_INVALID, msg);     \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct b200_map {
+  b200_map_params_t prm;
+  MapDev d;
+  int N[3];
+  double minb[3], maxb[3];
+  int sm_count;
+  cudaStream_t stream;
+  long long* d_bounds;  // 6 order-preserving keys
+  bool bounds_pending;
+  double cam[3];
+  int lb_min[3], lb_max[3];
+  DevBuf cloud, stage_in, stage_out, stage_aux;
+  int32_t* d_tmp;
+  double* d_dk;
+  double d_safe;
+  bool has_edt;
+  bool profiling;
+  cudaEvent_t ev[6];
+  double stage_ms[8];
+  long long launches;
+};
+
+static inline int host_floor_idx(double pos, double origin, double inv, int n) {
+  // grid_map.h:400-404 then :267-274 (boundIndex); the clamp is applied in double so huge ranges stay defined
+  double v = std::floor((pos - origin) * inv);
+  if (!(v >= 0.0)) return 0;
+  if (v > (double)(n - 1)) return n - 1;
+  return (int)v;
+}
+
+// shared shape of the three per-position readers
+template <class T, class F>
+static int per_position(b200_map_t* m, const double* pos, int64_t n, T* out, size_t out_elems_per_pos, int on_device, F launch) {
+  REQUIRE(m && (n == 0 || (pos && out)) && n >= 0, "bad argument");
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  if (on_device) {
+    launch(pos, out);
+    m->launches++;
+    CK(cudaGetLastError());
+    return B200_OK;
+  }
+  if (m->stage_in.ensure((size_t)n * 24) || m->stage_out.ensure((size_t)n * out_elems_per_pos * sizeof(T)))
+    return fail(B200_ERR_NOMEM, "position staging");
+  CK(cudaMemcpyAsync(m->stage_in.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  launch((const double*)m->stage_in.p, (T*)m->stage_out.p);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, m->stage_out.p, (size_t)n * out_elems_per_pos * sizeof(T), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+const char* b200_version(void) { return "b200-planner 0.1 (sm_100a)"; }
+
+int b200_host_alloc(void** ptr, int64_t bytes) {
+  REQUIRE(ptr && bytes >= 0, "b200_host_alloc: bad args");
+  CK(cudaMallocHost(ptr, (size_t)bytes));
+  return B200_OK;
+}
+int b200_host_free(void* ptr) {
+  CK(cudaFreeHost(ptr));
+  return B200_OK;
+}
+
+int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
+  REQUIRE(p && out, "b200_map_create: NULL argument");
+  REQUIRE(p->resolution > 0 && p->size[0] > 0 && p->size[1] > 0 && p->size[2] > 0, "b200_map_create: bad geometry");
+  CK(cudaSetDevice(p->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major != 10) return fail(B200_ERR_UNSUPPORTED, "b200_map_create: device is not sm_100 (B200); no fallback path exists");
+  b200_map* m = new b200_map();
+  memset(&m->d, 0, sizeof m->d);
+  m->prm = *p;
+  m->sm_count = prop.multiProcessorCount;
+  m->stream = cudaStreamLegacy;
+  const double res = p->resolution;
+  MapDev& d = m->d;
+  d.res = res;
+  d.inv_res = 1 / res;  // grid_map.cpp:52
+  d.ox = p->origin[0]; d.oy = p->origin[1]; d.oz = p->origin[2];
+  for (int i = 0; i < 3; ++i) {
+    m->N[i] = (int)std::ceil(p->size[i] / res);  // grid_map.cpp:69-70
+    m->minb[i] = p->origin[i];                   // :72
+    m->maxb[i] = p->origin[i] + p->size[i];      // :73
+    d.lo[i] = m->minb[i] + 1e-4;                 // grid_map.h:372
+    d.hi[i] = m->maxb[i] - 1e-4;                 // grid_map.h:378
+    m->lb_min[i] = 0;
+    m->lb_max[i] = m->N[i] - 1;
+  }
+  if (m->N[0] > 16384 || m->N[1] > 16384 || m->N[2] > 16384) {
+    delete m;
+    return fail(B200_ERR_UNSUPPORTED, "b200_map_create: more than 16384 voxels along one axis");
+  }
+  d.Nx = m->N[0]; d.Ny = m->N[1]; d.Nz = m->N[2];
+  d.wz = (d.Nz + 31) / 32;
+  const size_t words = (size_t)d.Nx * d.Ny * d.wz;
+  cudaError_t e = cudaMalloc(&d.occ, words * 4);
+  if (e != cudaSuccess) { delete m; return fail(B200_ERR_NOMEM, "b200_map_create: occupancy grid", e); }
+  cudaMemset(d.occ, 0, words * 4);  // grid_map.cpp:80
+  // d_k table of fastLOS (LineOfSight.cpp:19): d += 0.05 by repeated addition, long enough for the map diagonal
+  const double diag = std::sqrt(p->size[0] * p->size[0] + p->size[1] * p->size[1] + p->size[2] * p->size[2]);
+  const int len = (int)std::ceil(diag / kLosStep) + 64;
+  std::vector<double> dk(len);
+  double acc = 0;
+  for (int i = 0; i < len; ++i) { dk[i] = acc; acc += kLosStep; }
+  e = cudaMalloc(&m->d_dk, (size_t)len * 8);
+  if (e != cudaSuccess) { cudaFree(d.occ); delete m; return fail(B200_ERR_NOMEM, "b200_map_create: dk table", e); }
+  cudaMemcpy(m->d_dk, dk.data(), (size_t)len * 8, cudaMemcpyHostToDevice);
+  d.dk = m->d_dk;
+  d.dk_len = len;
+  e = cudaMalloc(&m->d_bounds, 6 * 8);
+  if (e != cudaSuccess) { cudaFree(d.occ); cudaFree(m->d_dk); delete m; return fail(B200_ERR_NOMEM, "b200_map_create: bounds", e); }
+  m->bounds_pending = false;
+  m->d_tmp = nullptr;
+  m->has_edt = false;
+  m->d_safe = 0;
+  m->profiling = false;
+  for (auto& ev : m->ev) cudaEventCreate(&ev);
+  memset(m->stage_ms, 0, sizeof m->stage_ms);
+  m->launches = 0;
+  CK(cudaDeviceSynchronize());
+  *out = m;
+  return B200_OK;
+}
+
+int b200_map_destroy(b200_map_t* m) {
+  if (!m) return B200_OK;
+  cudaSetDevice(m->prm.device);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(m->d.occ);
+  if (m->d.dist2) cudaFree(m->d.dist2);
+  if (m->d.costq) cudaFree(m->d.costq);
+  if (m->d_tmp) cudaFree(m->d_tmp);
+  cudaFree(m->d_dk);
+  cudaFree(m->d_bounds);
+  m->cloud.release(); m->stage_in.release(); m->stage_out.release(); m->stage_aux.release();
+  for (auto& ev : m->ev) cudaEventDestroy(ev);
+  delete m;
+  return B200_OK;
+}
+
+int b200_map_set_stream(b200_map_t* m, void* st) {
+  REQUIRE(m, "NULL map");
+  m->stream = st ? (cudaStream_t)st : cudaStreamLegacy;
+  return B200_OK;
+}
+int b200_map_sync(b200_map_t* m) {
+  REQUIRE(m, "NULL map");
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_dims(const b200_map_t* m, int32_t n[3]) {
+  REQUIRE(m && n, "NULL argument");
+  for (int i = 0; i < 3; ++i) n[i] = m->N[i];
+  return B200_OK;
+}
+int b200_map_get_region(const b200_map_t* m, double origin[3], double size[3]) {
+  REQUIRE(m && origin && size, "NULL argument");
+  for (int i = 0; i < 3; ++i) { origin[i] = m->prm.origin[i]; size[i] = m->prm.size[i]; }
+  return B200_OK;
+}
+double b200_map_get_resolution(const b200_map_t* m) { return m ? m->prm.resolution : 0.0; }
+
+int b200_map_clear_box(b200_map_t* m, const double mn[3], const double mx[3]) {
+  REQUIRE(m && mn && mx, "NULL argument");
+  CK(cudaSetDevice(m->prm.device));
+  int a[3], b[3];
+  const double o[3] = {m->d.ox, m->d.oy, m->d.oz};
+  for (int i = 0; i < 3; ++i) {
+    a[i] = host_floor_idx(mn[i], o[i], m->d.inv_res, m->N[i]);
+    b[i] = host_floor_idx(mx[i], o[i], m->d.inv_res, m->N[i]);
+  }
+  launch_clear_box(m->d, a, b, m->sm_count, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+int b200_map_reset(b200_map_t* m) {  // grid_map.cpp:144-153
+  REQUIRE(m, "NULL map");
+  int rc = b200_map_clear_box(m, m->minb, m->maxb);
+  if (rc) return rc;
+  m->bounds_pending = false;
+  for (int i = 0; i < 3; ++i) { m->lb_min[i] = 0; m->lb_max[i] = m->N[i] - 1; }
+  return B200_OK;
+}
+
+int b200_map_update_cloud(b200_map_t* m, const void* pts, int64_t n, int32_t step, int32_t ox, int32_t oy, int32_t oz,
+                          const double cam[3], int32_t on_device) {
+  REQUIRE(m && cam, "NULL argument");
+  REQUIRE(n >= 0 && (n == 0 || pts), "b200_map_update_cloud: bad cloud");
+  REQUIRE(step >= 12 && ox >= 0 && oy >= 0 && oz >= 0 && ox + 4 <= step && oy + 4 <= step && oz + 4 <= step && (ox | oy | oz | step) % 4 == 0,
+          "b200_map_update_cloud: bad point layout");
+  if (n == 0) return B200_OK;                                                  // grid_map.cpp:724-725
+  if (std::isnan(cam[0]) || std::isnan(cam[1]) || std::isnan(cam[2])) return B200_OK;  // :727-728
+  CK(cudaSetDevice(m->prm.device));
+  const int s = (int)std::ceil(m->prm.obstacles_inflation / m->prm.resolution);  // :735
+  if (s < 0 || s > 4) return fail(B200_ERR_UNSUPPORTED, "b200_map_update_cloud: inflation step > 4 voxels");
+  const uint8_t* dpts = (const uint8_t*)pts;
+  if (!on_device) {
+    if (m->cloud.ensure((size_t)n * step)) return fail(B200_ERR_NOMEM, "cloud staging");
+    CK(cudaMemcpyAsync(m->cloud.p, pts, (size_t)n * step, cudaMemcpyHostToDevice, m->stream));
+    dpts = (const uint8_t*)m->cloud.p;
+  }
+  if (m->profiling) cudaEventRecord(m->ev[0], m->stream);
+  double mn[3], mx[3];
+  for (int i = 0; i < 3; ++i) { mn[i] = cam[i] - m->prm.local_update_range[i]; mx[i] = cam[i] + m->prm.local_update_range[i]; }
+  int rc = b200_map_clear_box(m, mn, mx);  // :730
+  if (rc) return rc;
+  if (m->profiling) cudaEventRecord(m->ev[1], m->stream);
+  // running min starts at map max, running max at map min (:740-746), as order-preserving keys
+  long long keys[6];
+  for (int i = 0; i < 3; ++i) {
+    long long b;
+    memcpy(&b, &m->maxb[i], 8); keys[i] = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+    memcpy(&b, &m->minb[i], 8); keys[3 + i] = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+  }
+  CK(cudaMemcpyAsync(m->d_bounds, keys, sizeof keys, cudaMemcpyHostToDevice, m->stream));
+  if (launch_scatter(m->d, dpts, n, step, ox, oy, oz, cam, m->prm.local_update_range, s, m->d_bounds, m->stream))
+    return fail(B200_ERR_UNSUPPORTED, "scatter: inflation step");
+  m->launches++;
+  if (m->profiling) cudaEventRecord(m->ev[2], m->stream);
+  CK(cudaGetLastError());
+  m->bounds_pending = true;
+  for (int i = 0; i < 3; ++i) m->cam[i] = cam[i];
+  return B200_OK;
+}
+
+int b200_map_local_bounds(b200_map_t* m, int32_t mn[3], int32_t mx[3]) {
+  REQUIRE(m && mn && mx, "NULL argument");
+  if (m->bounds_pending) {
+    CK(cudaSetDevice(m->prm.device));
+    long long keys[6];
+    CK(cudaMemcpyAsync(keys, m->d_bounds, sizeof keys, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    double lo[3], hi[3];
+    for (int i = 0; i < 6; ++i) {
+      long long b = keys[i] >= 0 ? keys[i] : (keys[i] ^ 0x7fffffffffffffffLL);
+      double v;
+      memcpy(&v, &b, 8);
+      if (i < 3) lo[i] = v; else hi[i - 3] = v;
+    }
+    for (int i = 0; i < 3; ++i) {  // grid_map.cpp:789-795
+      lo[i] = std::min(lo[i], m->cam[i]);
+      hi[i] = std::max(hi[i], m->cam[i]);
+    }
+    hi[2] = std::max(hi[2], m->prm.ground_height);  // :797
+    const double o[3] = {m->d.ox, m->d.oy, m->d.oz};
+    for (int i = 0; i < 3; ++i) {  // :799-803
+      m->lb_max[i] = host_floor_idx(hi[i], o[i], m->d.inv_res, m->N[i]);
+      m->lb_min[i] = host_floor_idx(lo[i], o[i], m->d.inv_res, m->N[i]);
+    }
+    m->bounds_pending = false;
+  }
+  for (int i = 0; i < 3; ++i) { mn[i] = m->lb_min[i]; mx[i] = m->lb_max[i]; }
+  return B200_OK;
+}
+
+int b200_map_get_inflate_occupancy(b200_map_t* m, const double* pos, int64_t n, int8_t* out, int32_t on_device) {
+  return per_position<int8_t>(m, pos, n, out, 1, on_device,
+                              [&](const double* p, int8_t* o) { launch_occupancy(m->d, p, n, o, m->stream); });
+}
+int b200_map_is_in_map(b200_map_t* m, const double* pos, int64_t n, uint8_t* out, int32_t on_device) {
+  return per_position<uint8_t>(m, pos, n, out, 1, on_device,
+                               [&](const double* p, uint8_t* o) { launch_in_map(m->d, p, n, o, m->stream); });
+}
+int b200_map_pos_to_index(b200_map_t* m, const double* pos, int64_t n, int32_t* out, int32_t on_device) {
+  return per_position<int32_t>(m, pos, n, out, 3, on_device,
+                               [&](const double* p, int32_t* o) { launch_pos_to_index(m->d, p, n, o, m->stream); });
+}
+
+int b200_map_download_inflate(b200_map_t* m, uint8_t* dst) {
+  REQUIRE(m && dst, "NULL argument");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
+  if (m->stage_out.ensure(nv)) return fail(B200_ERR_NOMEM, "download staging");
+  launch_unpack(m->d, (uint8_t*)m->stage_out.p, m->sm_count, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, m->stage_out.p, nv, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_upload_inflate(b200_map_t* m, const uint8_t* src) {
+  REQUIRE(m && src, "NULL argument");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
+  if (m->stage_in.ensure(nv)) return fail(B200_ERR_NOMEM, "upload staging");
+  CK(cudaMemcpyAsync(m->stage_in.p, src, nv, cudaMemcpyHostToDevice, m->stream));
+  launch_pack(m->d, (const uint8_t*)m->stage_in.p, m->sm_count, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_device_bits(b200_map_t* m, void** p, int64_t* n_words) {
+  REQUIRE(m && p && n_words, "NULL argument");
+  *p = m->d.occ;
+  *n_words = (int64_t)m->N[0] * m->N[1] * m->d.wz;
+  return B200_OK;
+}
+
+int b200_map_build_edt(b200_map_t* m, double d_safe) {
+  REQUIRE(m, "NULL map");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
+  if (!m->d_tmp) {
+    if (cudaMalloc(&m->d_tmp, nv * 4) != cudaSuccess) { cudaGetLastError(); m->d_tmp = nullptr; return fail(B200_ERR_NOMEM, "edt scratch"); }
+  }
+  if (!m->d.dist2) {
+    if (cudaMalloc(&m->d.dist2, nv * 4) != cudaSuccess) { cudaGetLastError(); m->d.dist2 = nullptr; return fail(B200_ERR_NOMEM, "dist2 field"); }
+  }
+  if (d_safe > 0 && !m->d.costq) {
+    if (cudaMalloc(&m->d.costq, nv * 2) != cudaSuccess) { cudaGetLastError(); m->d.costq = nullptr; return fail(B200_ERR_NOMEM, "cost field"); }
+  }
+  if (m->profiling) cudaEventRecord(m->ev[3], m->stream);
+  launch_edt(m->d, m->d_tmp, m->d.dist2, m->d.costq, nullptr, d_safe, m->stream, m->profiling ? m->ev[4] : nullptr);
+  m->launches += 2;
+  if (m->profiling) cudaEventRecord(m->ev[5], m->stream);
+  CK(cudaGetLastError());
+  m->has_edt = true;
+  m->d_safe = d_safe;
+  return B200_OK;
+}
+
+static int download_field(b200_map_t* m, const void* src, void* dst, size_t bytes) {
+  CK(cudaSetDevice(m->prm.device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_download_dist2(b200_map_t* m, int32_t* dst) {
+  REQUIRE(m && dst && m->has_edt, "no distance field (call b200_map_build_edt)");
+  return download_field(m, m->d.dist2, dst, (size_t)m->N[0] * m->N[1] * m->N[2] * 4);
+}
+int b200_map_download_costq(b200_map_t* m, uint16_t* dst) {
+  REQUIRE(m && dst && m->has_edt && m->d_safe > 0 && m->d.costq, "no cost field (build_edt with d_safe > 0)");
+  return download_field(m, m->d.costq, dst, (size_t)m->N[0] * m->N[1] * m->N[2] * 2);
+}
+
+int b200_los_batch(b200_map_t* m, const double* s, const double* e, int64_t n, uint8_t* vis, int32_t* ns, int32_t on_device) {
+  REQUIRE(m && n >= 0 && (n == 0 || (s && e && vis)), "bad argument");
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  if (on_device) {
+    launch_los_batch(m->d, s, e, n, vis, ns, m->sm_count, m->stream);
+    m->launches++;
+    CK(cudaGetLastError());
+    return B200_OK;
+  }
+  if (m->stage_in.ensure((size_t)n * 48) || m->stage_out.ensure((size_t)n) || m->stage_aux.ensure((size_t)n * 4))
+    return fail(B200_ERR_NOMEM, "los staging");
+  double* ds = (double*)m->stage_in.p;
+  double* de = ds + 3 * n;
+  CK(cudaMemcpyAsync(ds, s, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  CK(cudaMemcpyAsync(de, e, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  launch_los_batch(m->d, ds, de, n, (uint8_t*)m->stage_out.p, (int32_t*)m->stage_aux.p, m->sm_count, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vis, m->stage_out.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+  if (ns) CK(cudaMemcpyAsync(ns, m->stage_aux.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+
+int b200_map_set_profiling(b200_map_t* m, int32_t enable) {
+  REQUIRE(m, "NULL map");
+  m->profiling = enable != 0;
+  return B200_OK;
+}
+int b200_map_get_stage_ms(b200_map_t* m, double out[8]) {
+  REQUIRE(m && out, "NULL argument");
+  CK(cudaSetDevice(m->prm.device));
+  CK(cudaStreamSynchronize(m->stream));
+  memset(out, 0, 8 * sizeof(double));
+  float t;
+  if (cudaEventElapsedTime(&t, m->ev[0], m->ev[1]) == cudaSuccess) out[0] = t;
+  if (cudaEventElapsedTime(&t, m->ev[1], m->ev[2]) == cudaSuccess) out[1] = t;
+  if (cudaEventElapsedTime(&t, m->ev[3], m->ev[4]) == cudaSuccess) out[2] = t;
+  if (cudaEventElapsedTime(&t, m->ev[4], m->ev[5]) == cudaSuccess) out[3] = t;
+  cudaGetLastError();
+  return B200_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------------
+// cost (float32) download: derived from dist2 on the fly with the same formula the EDT pass quantises
+// --------------------------------------------------------------------------------------------------
+namespace b200 {
+__global__ void __launch_bounds__(256) cost_f32_kernel(const int32_t* __restrict__ d2, float* __restrict__ out, long long n, float res, float d_safe) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t v = d2[i];
+    float c = 0.0f;
+    if (v < kDistInf) {
+      const float d = __fmul_rn(__fsqrt_rn((float)v), res);
+      if (d < d_safe) c = __fsub_rn(1.0f, __fdiv_rn(d, d_safe));
+    }
+    out[i] = c;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_map_download_cost(b200_map_t* m, float* dst) {
+  REQUIRE(m && dst && m->has_edt && m->d_safe > 0, "no cost field (build_edt with d_safe > 0)");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
+  if (m->stage_out.ensure(nv * 4)) return fail(B200_ERR_NOMEM, "cost staging");
+  cost_f32_kernel<<<m->sm_count * 8, 256, 0, m->stream>>>(m->d.dist2, (float*)m->stage_out.p, (long long)nv, (float)m->prm.resolution,
+                                                           (float)m->d_safe);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, m->stage_out.p, nv * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// planners
+// --------------------------------------------------------------------------------------------------
+struct Tier {
+  int cap = 0;
+  int slots = 0;
+  uint32_t hcap = 0;
+  void* base = nullptr;
+  NodeRec* nodes = nullptr;
+  uint32_t* hash = nullptr;
+  HeapEnt* heap = nullptr;
+};
+
+struct b200_planner {
+  int algo;
+  std::string name;
+  b200_planner_params_t prm;
+  b200_map* map;
+  double dv[3];
+  Tier tier[2];
+  DevBuf q_in, q_res, q_path, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
+  int last_launches;
+};
+
+static void tier_free(Tier& t) {
+  if (t.base) cudaFree(t.base);
+  t = Tier();
+}
+static int tier_alloc(Tier& t, int cap, int slots) {
+  if (t.base && t.cap == cap && t.slots == slots) return 0;
+  tier_free(t);
+  uint32_t hcap;
+  search_slot_bytes(cap, &hcap);
+  const size_t nb = (size_t)slots * cap * sizeof(NodeRec);
+  const size_t hb = (size_t)slots * hcap * 4;
+  const size_t pb = (size_t)slots * ((size_t)cap + 32) * sizeof(HeapEnt);
+  if (cudaMalloc(&t.base, nb + hb + pb) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return -1; }
+  t.nodes = (NodeRec*)t.base;
+  t.heap = (HeapEnt*)((char*)t.base + nb);
+  t.hash = (uint32_t*)((char*)t.base + nb + pb);
+  cudaMemset(t.hash, 0, hb);
+  t.cap = cap; t.slots = slots; t.hcap = hcap;
+  return 0;
+}
+
+extern "C" {
+
+int b200_planner_create(const char* algorithm, const b200_planner_params_t* p, b200_planner_t** out) {
+  REQUIRE(algorithm && p && out, "NULL argument");
+  REQUIRE(p->resolution > 1e-3 && p->allocate_num >= 2, "b200_planner_create: resolution must exceed 1e-3 and allocate_num >= 2");
+  b200_planner* pl = new b200_planner();
+  const std::string a(algorithm);
+  // planner_ros_node.cpp:261-285: unknown names fall back to A*
+  if (a == "thetastar") pl->algo = ALGO_THETASTAR;
+  else if (a == "lazythetastar") pl->algo = ALGO_LAZYTHETASTAR;
+  else if (a == "costastar") pl->algo = ALGO_COSTASTAR;
+  else if (a == "costlazythetastar") pl->algo = ALGO_COSTLAZYTHETASTAR;
+  else pl->algo = ALGO_ASTAR;
+  pl->name = pl->algo == ALGO_ASTAR ? "astar" : a;
+  pl->prm = *p;
+  pl->map = nullptr;
+  pl->last_launches = 0;
+  // the neighbour offsets exactly as `for (double dx = -r; dx <= r + 1e-3; dx += r)` produces them (AStar.cpp:131)
+  int nd = 0;
+  double dv[8];
+  for (double dx = -p->resolution; dx <= p->resolution + 1e-3 && nd < 8; dx += p->resolution) dv[nd++] = dx;
+  if (nd != 3) { delete pl; return fail(B200_ERR_UNSUPPORTED, "b200_planner_create: resolution yields a neighbour stencil other than 3x3x3"); }
+  for (int i = 0; i < 3; ++i) pl->dv[i] = dv[i];
+  *out = pl;
+  return B200_OK;
+}
+
+int b200_planner_destroy(b200_planner_t* pl) {
+  if (!pl) return B200_OK;
+  if (pl->map) cudaSetDevice(pl->map->prm.device);
+  tier_free(pl->tier[0]);
+  tier_free(pl->tier[1]);
+  pl->q_in.release(); pl->q_res.release(); pl->q_path.release(); pl->ctl.release();
+  delete pl;
+  return B200_OK;
+}
+int b200_planner_set_map(b200_planner_t* pl, b200_map_t* m) {
+  REQUIRE(pl && m, "NULL argument");
+  pl->map = m;
+  return B200_OK;
+}
+int b200_planner_set_cost_factor(b200_planner_t* pl, double w) {
+  REQUIRE(pl, "NULL planner");
+  pl->prm.cost_weight = w;
+  return B200_OK;
+}
+int b200_planner_detect_collision(b200_planner_t* pl, const double pos[3], int32_t* collides) {
+  REQUIRE(pl && pos && collides, "NULL argument");
+  if (!pl->map) return fail(B200_ERR_NO_MAP, "planner has no map");
+  int8_t v = 0;
+  int rc = b200_map_get_inflate_occupancy(pl->map, pos, 1, &v, 0);
+  if (rc) return rc;
+  *collides = v != 0;  // AlgorithmBase.cpp:43: bool(int) — -1 (outside) counts as a collision
+  return B200_OK;
+}
+int b200_planner_last_launches(b200_planner_t* pl, int32_t* n) {
+  REQUIRE(pl && n, "NULL argument");
+  *n = pl->last_launches;
+  return B200_OK;
+}
+
+int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const double* goals, int64_t nq, b200_path_result_t* results,
+                            double* path_xyz, int64_t path_cap, int32_t on_device) {
+  REQUIRE(pl && nq >= 0 && (nq == 0 || (starts && goals && results)), "bad argument");
+  REQUIRE(nq < (1LL << 31), "too many queries in one call");
+  if (!pl->map) return fail(B200_ERR_NO_MAP, "planner has no map");
+  pl->last_launches = 0;
+  if (nq == 0) return B200_OK;
+  b200_map* m = pl->map;
+  const bool cost_algo = pl->algo == ALGO_COSTASTAR || pl->algo == ALGO_COSTLAZYTHETASTAR;
+  if (cost_algo && !(m->has_edt && m->d_safe > 0 && m->d.costq))
+    return fail(B200_ERR_INVALID, "cost-aware planner needs b200_map_build_edt(map, d_safe > 0) first");
+  CK(cudaSetDevice(m->prm.device));
+  cudaStream_t st = m->stream;
+  if (!path_xyz) path_cap = 0;
+
+  // workspace tiers: a small one for the common query, the full allocate_num one for the rare big query
+  const int tpb = search_threads_per_block(pl->algo);
+  const int per_sm = tpb == 32 ? 16 : 4;
+  int slots0 = m->sm_count * per_sm;
+  if ((int64_t)slots0 > nq) slots0 = (int)nq;
+  const int cap0 = std::min(pl->prm.allocate_num, 16384);
+  if (tier_alloc(pl->tier[0], cap0, std::max(slots0, pl->tier[0].cap == cap0 ? pl->tier[0].slots : 0)))
+    return fail(B200_ERR_NOMEM, "search workspace (tier 0)");
+
+  const double* d_starts = starts;
+  const double* d_goals = goals;
+  b200_path_result_t* d_res = results;
+  double* d_path = path_xyz;
+  if (!on_device) {
+    if (pl->q_in.ensure((size_t)nq * 48) || pl->q_res.ensure((size_t)nq * sizeof(b200_path_result_t)) ||
+        (path_cap > 0 && pl->q_path.ensure((size_t)path_cap * 24)))
+      return fail(B200_ERR_NOMEM, "query staging");
+    double* ds = (double*)pl->q_in.p;
+    CK(cudaMemcpyAsync(ds, starts, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ds + 3 * nq, goals, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+    d_starts = ds;
+    d_goals = ds + 3 * nq;
+    d_res = (b200_path_result_t*)pl->q_res.p;
+    d_path = path_cap > 0 ? (double*)pl->q_path.p : nullptr;
+  }
+  if (pl->ctl.ensure(64 + (size_t)nq * 4)) return fail(B200_ERR_NOMEM, "control block");
+  CK(cudaMemsetAsync(pl->ctl.p, 0, 64, st));
+  unsigned long long* q_counter = (unsigned long long*)pl->ctl.p;
+  unsigned long long* path_cursor = q_counter + 1;
+  int* overflow_count = (int*)(q_counter + 2);
+  int* overflow_list = (int*)((char*)pl->ctl.p + 64);
+
+  SearchParams P;
+  memset(&P, 0, sizeof P);
+  P.map = m->d;
+  P.r = pl->prm.resolution;
+  P.lambda = pl->prm.lambda_heuristic;
+  P.tie = 1.0 + 1.0 / 10000;  // AStar.cpp:40
+  P.cost_weight = pl->prm.cost_weight;
+  P.max_los = pl->prm.max_los;
+  for (int i = 0; i < 3; ++i) P.dv[i] = pl->dv[i];
+  P.allocate_num = pl->prm.allocate_num;
+  P.algo = pl->algo;
+  P.starts = d_starts; P.goals = d_goals; P.qlist = nullptr; P.nq = nq;
+  P.results = d_res; P.path_pool = d_path; P.path_cap = path_cap; P.path_cursor = path_cursor;
+  P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;
+  const Tier& t0 = pl->tier[0];
+  P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap;
+  launch_search(P, std::min<int64_t>(t0.slots, nq), st);
+  pl->last_launches++;
+  CK(cudaGetLastError());
+
+  if (t0.cap < pl->prm.allocate_num) {
+    int n_over = 0;
+    CK(cudaMemcpyAsync(&n_over, overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_over > 0) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      uint32_t hc;
+      const size_t slot_b = search_slot_bytes(pl->prm.allocate_num, &hc);
+      size_t budget = pl->tier[1].base ? (size_t)pl->tier[1].slots * slot_b : free_b / 2;
+      int slots1 = (int)std::min<size_t>({(size_t)n_over, (size_t)m->sm_count * (tpb == 32 ? 4 : 2), std::max<size_t>(1, budget / slot_b)});
+      if (pl->tier[1].base && pl->tier[1].cap == pl->prm.allocate_num && pl->tier[1].slots >= slots1) slots1 = pl->tier[1].slots;
+      if (tier_alloc(pl->tier[1], pl->prm.allocate_num, slots1)) return fail(B200_ERR_NOMEM, "search workspace (tier 1)");
+      CK(cudaMemsetAsync(q_counter, 0, 8, st));
+      const Tier& t1 = pl->tier[1];
+      P.qlist = overflow_list; P.nq = n_over;
+      P.overflow_list = nullptr; P.overflow_count = overflow_count;
+      P.nodes = t1.nodes; P.hash = t1.hash; P.heap = t1.heap; P.cap = t1.cap; P.hcap = t1.hcap;
+      launch_search(P, std::min(t1.slots, n_over), st);
+      pl->last_launches++;
+      CK(cudaGetLastError());
+    }
+  }
+  if (!on_device) {
+    CK(cudaMemcpyAsync(results, d_res, (size_t)nq * sizeof(b200_path_result_t), cudaMemcpyDeviceToHost, st));
+    unsigned long long used = 0;
+    CK(cudaMemcpyAsync(&used, path_cursor, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (path_cap > 0) {
+      const size_t npts = (size_t)std::min<unsigned long long>(used, (unsigned long long)path_cap);
+      if (npts) CK(cudaMemcpyAsync(path_xyz, d_path, npts * 24, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  m->launches += pl->last_launches;
+  return B200_OK;
+}
+
+int b200_planner_find_path(b200_planner_t* pl, const double start[3], const double goal[3], b200_path_result_t* result,
+                           double* path_xyz, int64_t path_cap) {
+  REQUIRE(pl && start && goal && result, "NULL argument");
+  int rc = b200_planner_find_paths(pl, start, goal, 1, result, path_xyz, path_cap, 0);
+  if (rc) return rc;
+  if (result->path_offset < 0 && result->solved && path_xyz && path_cap > 0) {
+    // path longer than the caller's buffer: rerun into a staging buffer of the right size and copy the prefix
+    std::vector<double> tmp((size_t)result->n_path * 3);
+    rc = b200_planner_find_paths(pl, start, goal, 1, result, tmp.data(), result->n_path, 0);
+    if (rc) return rc;
+    memcpy(path_xyz, tmp.data(), (size_t)std::min<int64_t>(path_cap, result->n_path) * 24);
+  }
+  if (result->path_offset > 0) result->path_offset = 0;
+  return B200_OK;
+}
+
+}  // extern "C"

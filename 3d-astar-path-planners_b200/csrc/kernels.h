@@ -1,0 +1,77 @@
+// kernels.h — launchers shared between the .cu translation units and the C-ABI layer (api.cu).
+#pragma once
+#include "common.cuh"
+#include "../../include/b200_planner.h"
+
+namespace b200 {
+
+// ---- map_kernels.cu
+void launch_clear_box(const MapDev& m, const int a[3], const int b[3], int sm_count, cudaStream_t st);
+int launch_scatter(const MapDev& m, const uint8_t* pts, long long n, int step, int offx, int offy, int offz, const double cam[3],
+                   const double range[3], int s, long long* bounds, cudaStream_t st);
+void launch_unpack(const MapDev& m, uint8_t* dst, int sm_count, cudaStream_t st);
+void launch_pack(const MapDev& m, const uint8_t* src, int sm_count, cudaStream_t st);
+void launch_occupancy(const MapDev& m, const double* pos, long long n, int8_t* out, cudaStream_t st);
+void launch_in_map(const MapDev& m, const double* pos, long long n, uint8_t* out, cudaStream_t st);
+void launch_pos_to_index(const MapDev& m, const double* pos, long long n, int32_t* out, cudaStream_t st);
+void launch_los_batch(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* nsamples, int sm_count,
+                      cudaStream_t st);
+
+// ---- edt_kernels.cu
+void launch_edt(const MapDev& m, int32_t* tmp, int32_t* dist2, uint16_t* costq, float* cost, double d_safe, cudaStream_t st,
+                cudaEvent_t mid);
+
+// ---- search_kernels.cu
+enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4 };
+enum { ST_SOLVED = 0, ST_OPEN_EMPTY = 1, ST_POOL_EXHAUSTED = 2, ST_TIER_OVERFLOW = 3 };
+
+// Per-slot search workspace in HBM (one slot per resident thread block; SoA of slots, AoS inside):
+//   nodes  NodeRec [cap]      64 B records, index = creation order (the reference's pool index / tie-break)
+//   hash   uint32  [hcap]     open addressing on the exact 3xFP64 key -> node index + 1
+//   heap   HeapEnt [cap+32]   32-ary min-heap on (f, creation index); children of k are one aligned 512 B row
+struct __align__(16) NodeRec {
+  double px, py, pz;
+  double g, f;
+  int parent;     // node index or -1
+  int hpos;       // heap position, -1 when not in the open list
+  uint32_t slot;  // hash slot (for O(used) clearing)
+  int via;        // lazy variants: expanded node that last relaxed this one
+  int state;      // low byte: NODE_*; next byte: via direction code (0..26)
+  int pad;
+};
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte record");
+struct __align__(16) HeapEnt {
+  unsigned long long key;  // order-preserving image of f
+  uint32_t idx;
+  uint32_t pad;
+};
+
+struct SearchParams {
+  MapDev map;
+  double r, lambda, tie, cost_weight, max_los;
+  double dv[3];
+  int allocate_num;
+  int algo;
+  const double* starts;
+  const double* goals;
+  const int* qlist;  // optional indirection (second-tier pass)
+  long long nq;
+  b200_path_result_t* results;
+  double* path_pool;
+  long long path_cap;
+  unsigned long long* path_cursor;
+  unsigned long long* q_counter;
+  int* overflow_list;
+  int* overflow_count;
+  NodeRec* nodes;
+  uint32_t* hash;
+  HeapEnt* heap;
+  int cap;        // physical nodes per slot
+  uint32_t hcap;  // hash entries per slot (power of two >= 2*cap)
+};
+
+size_t search_slot_bytes(int cap, uint32_t* hcap_out);
+int search_threads_per_block(int algo);
+void launch_search(const SearchParams& p, int slots, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,266 @@
+// map_kernels.cu — GridMap cloud path on B200: clear box, voxelise+inflate scatter, occupancy reads,
+// byte<->bit (un)packing for parity, and the batched fastLOS kernel.
+//
+// Reference behaviour restated (not ported): src/plan_env/grid_map.cpp:155-171 (resetBuffer),
+// :711-804 (cloudCallback), include/plan_env/grid_map.h:350-404 (occupancy inlines),
+// src/utils/LineOfSight.cpp:9-27 (fastLOS).
+#include "kernels.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------
+// clear box: one thread per 32-bit word of the box's columns.  Whole words get a plain store; edge words
+// a masked read-modify-write (each word is owned by exactly one thread, so no atomics).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clear_box_kernel(MapDev m, int ax, int ay, int az, int bx, int by, int bz) {
+  const int w0 = az >> 5, w1 = bz >> 5, nw = w1 - w0 + 1;
+  const int ny = by - ay + 1;
+  const long long total = (long long)(bx - ax + 1) * ny * nw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = w0 + (int)(i % nw);
+    const long long c = i / nw;
+    const int y = ay + (int)(c % ny), x = ax + (int)(c / ny);
+    const int zlo = max(az, w << 5), zhi = min(bz, (w << 5) + 31);
+    const int nb = zhi - zlo + 1;
+    const uint32_t mask = (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u)) << (zlo & 31);
+    uint32_t* p = m.occ + ((size_t)x * m.Ny + y) * m.wz + w;
+    if (mask == 0xffffffffu) *p = 0u;
+    else *p &= ~mask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cloud scatter: one thread per point.  Each point produces (2s+1)^2 columns x 3 z-cells in POSITION
+// space (pt + k*res, then floor — grid_map.cpp:765-777), which is not the same as voxelise-then-dilate
+// for lattice-aligned points.  The three z cells of a column almost always share a
+// 32-bit word, so a column costs one OR.  A word that already holds the bits is skipped after a plain
+// load; the remaining ORs are warp-aggregated (__match_any_sync on the word address, __reduce_or_sync on
+// the masks, one atomicOr per distinct word per warp).
+// bounds[0..2] = running min, bounds[3..5] = running max of every generated position (:769-775), kept
+// as order-preserving int64 keys so atomicMin/atomicMax apply.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long dkey(double v) {
+  long long b = __double_as_longlong(v);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+
+__device__ __forceinline__ void or_aggregated(uint32_t* addr, uint32_t mask, bool need) {
+  const unsigned todo = __ballot_sync(0xffffffffu, need);
+  if (!need) return;
+  const unsigned peers = __match_any_sync(todo, (unsigned long long)addr);
+  const uint32_t merged = __reduce_or_sync(peers, mask);
+  if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicOr(addr, merged);
+}
+
+template <int MAXS>
+__global__ void __launch_bounds__(256)
+scatter_kernel(MapDev m, const uint8_t* __restrict__ pts, long long n, int step, int offx, int offy, int offz, double camx,
+               double camy, double camz, double rx, double ry, double rz, int s, long long* __restrict__ bounds) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  bool accept = false;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  if (i < n) {
+    const uint8_t* p = pts + i * step;
+    if (step == 16 && offx == 0 && offy == 4 && offz == 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p));  // coalesced 128-bit loads (PointXYZ stride)
+      fx = v.x; fy = v.y; fz = v.z;
+    } else {
+      fx = __ldg(reinterpret_cast<const float*>(p + offx));
+      fy = __ldg(reinterpret_cast<const float*>(p + offy));
+      fz = __ldg(reinterpret_cast<const float*>(p + offz));
+    }
+    // :754-758  |pt - cam| < range per axis (NaN/Inf fail the compare)
+    accept = fabs(dsub((double)fx, camx)) < rx && fabs(dsub((double)fy, camy)) < ry && fabs(dsub((double)fz, camz)) < rz;
+  }
+  constexpr int SIDE = 2 * MAXS + 1;
+  int ixs[SIDE], iys[SIDE];
+  uint32_t zmask[2] = {0u, 0u};
+  int zw[2] = {-1, -1};
+  if (accept) {
+#pragma unroll
+    for (int k = 0; k < SIDE; ++k) {  // :765-766  pt + k*res (float promoted to double), :777 floor
+      const double off = dmul((double)(k - s), m.res);
+      ixs[k] = pos_to_idx1(dadd((double)fx, off), m.ox, m.inv_res);
+      iys[k] = pos_to_idx1(dadd((double)fy, off), m.oy, m.inv_res);
+    }
+    for (int k = -1; k <= 1; ++k) {  // inf_step_z = 1 (:736)
+      const int iz = pos_to_idx1(dadd((double)fz, dmul((double)k, m.res)), m.oz, m.inv_res);
+      if (iz < 0 || iz > m.Nz - 1) continue;  // isInMap(Vector3i) :779
+      const int w = iz >> 5;
+      const int slot = (zw[0] == w || zw[0] < 0) ? 0 : 1;
+      zw[slot] = w;
+      zmask[slot] |= 1u << (iz & 31);
+    }
+  }
+  const int side = 2 * s + 1;
+#pragma unroll
+  for (int a = 0; a < SIDE; ++a) {
+    if (a >= side) break;  // warp-uniform
+#pragma unroll
+    for (int b = 0; b < SIDE; ++b) {
+      if (b >= side) break;
+      bool in = false;
+      size_t col = 0;
+      if (accept) {
+        const int ix = ixs[a], iy = iys[b];
+        in = ix >= 0 && ix <= m.Nx - 1 && iy >= 0 && iy <= m.Ny - 1;
+        col = ((size_t)ix * m.Ny + iy) * m.wz;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        bool need = false;
+        uint32_t* addr = m.occ;
+        if (in && zw[q] >= 0) {
+          addr = m.occ + col + zw[q];
+          need = (*addr & zmask[q]) != zmask[q];  // already set by an earlier point: nothing to do
+        }
+        or_aggregated(addr, zmask[q], need);
+      }
+    }
+  }
+  // running min/max of the generated positions; monotone rounding => extremes are at k = -s / +s (z: -1 / +1)
+  double mn[3], mx[3];
+  if (accept) {
+    mn[0] = dadd((double)fx, dmul((double)(-s), m.res)); mx[0] = dadd((double)fx, dmul((double)s, m.res));
+    mn[1] = dadd((double)fy, dmul((double)(-s), m.res)); mx[1] = dadd((double)fy, dmul((double)s, m.res));
+    mn[2] = dadd((double)fz, dmul(-1.0, m.res));         mx[2] = dadd((double)fz, dmul(1.0, m.res));
+  }
+  const unsigned am = __ballot_sync(0xffffffffu, accept);
+  if (am) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      long long lo = accept ? dkey(mn[a]) : 0x7fffffffffffffffLL;
+      long long hi = accept ? dkey(mx[a]) : (long long)0x8000000000000000ULL;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if ((threadIdx.x & 31) == 0) {
+        if (lo < bounds[a]) atomicMin(bounds + a, lo);
+        if (hi > bounds[3 + a]) atomicMax(bounds + 3 + a, hi);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parity helpers: bit grid <-> the reference's byte-per-voxel layout
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_kernel(MapDev m, uint8_t* __restrict__ dst) {
+  const long long total = (long long)m.Nx * m.Ny * m.Nz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % m.Nz);
+    const long long c = i / m.Nz;
+    dst[i] = (uint8_t)((m.occ[c * m.wz + (z >> 5)] >> (z & 31)) & 1u);
+  }
+}
+__global__ void __launch_bounds__(256) pack_kernel(MapDev m, const uint8_t* __restrict__ src) {
+  const long long total = (long long)m.Nx * m.Ny * m.wz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % m.wz);
+    const long long c = i / m.wz;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int z = (w << 5) + b;
+      if (z < m.Nz && src[c * m.Nz + z]) v |= 1u << b;
+    }
+    m.occ[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-position reads
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) occupancy_kernel(MapDev m, const double* __restrict__ pos, long long n, int8_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int8_t)inflate_occ(m, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+}
+__global__ void __launch_bounds__(256) in_map_kernel(MapDev m, const double* __restrict__ pos, long long n, uint8_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = is_in_map(m, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) pos_to_index_kernel(MapDev m, const double* __restrict__ pos, long long n, int32_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) {
+    out[3 * i] = pos_to_idx1(pos[3 * i], m.ox, m.inv_res);
+    out[3 * i + 1] = pos_to_idx1(pos[3 * i + 1], m.oy, m.inv_res);
+    out[3 * i + 2] = pos_to_idx1(pos[3 * i + 2], m.oz, m.inv_res);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batched fastLOS: one warp per segment, grid-stride over segments
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) los_batch_kernel(MapDev m, const double* __restrict__ s, const double* __restrict__ e,
+                                                        long long n, uint8_t* __restrict__ vis, int32_t* __restrict__ nsamples) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp0; i < n; i += nwarps) {
+    int samples = 0;
+    const bool v = los_warp<false>(m, s[3 * i], s[3 * i + 1], s[3 * i + 2], e[3 * i], e[3 * i + 1], e[3 * i + 2], lane, &samples, nullptr);
+    if (lane == 0) {
+      vis[i] = v ? 1 : 0;
+      if (nsamples) nsamples[i] = samples;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------------
+static inline int grid_for(long long n, int block, int cap) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+void launch_clear_box(const MapDev& m, const int a[3], const int b[3], int sm_count, cudaStream_t st) {
+  if (a[0] > b[0] || a[1] > b[1] || a[2] > b[2]) return;
+  if (a[0] == 0 && a[1] == 0 && a[2] == 0 && b[0] == m.Nx - 1 && b[1] == m.Ny - 1 && b[2] == m.Nz - 1) {
+    cudaMemsetAsync(m.occ, 0, (size_t)m.Nx * m.Ny * m.wz * 4, st);
+    return;
+  }
+  const long long total = (long long)(b[0] - a[0] + 1) * (b[1] - a[1] + 1) * ((b[2] >> 5) - (a[2] >> 5) + 1);
+  clear_box_kernel<<<grid_for(total, 256, sm_count * 8), 256, 0, st>>>(m, a[0], a[1], a[2], b[0], b[1], b[2]);
+}
+
+int launch_scatter(const MapDev& m, const uint8_t* pts, long long n, int step, int offx, int offy, int offz, const double cam[3],
+                   const double range[3], int s, long long* bounds, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long long g = (n + 255) / 256;
+  if (s <= 1)
+    scatter_kernel<1><<<(unsigned)g, 256, 0, st>>>(m, pts, n, step, offx, offy, offz, cam[0], cam[1], cam[2], range[0], range[1], range[2], s, bounds);
+  else if (s <= 4)
+    scatter_kernel<4><<<(unsigned)g, 256, 0, st>>>(m, pts, n, step, offx, offy, offz, cam[0], cam[1], cam[2], range[0], range[1], range[2], s, bounds);
+  else
+    return -1;
+  return 0;
+}
+
+void launch_unpack(const MapDev& m, uint8_t* dst, int sm_count, cudaStream_t st) {
+  unpack_kernel<<<grid_for((long long)m.Nx * m.Ny * m.Nz, 256, sm_count * 16), 256, 0, st>>>(m, dst);
+}
+void launch_pack(const MapDev& m, const uint8_t* src, int sm_count, cudaStream_t st) {
+  pack_kernel<<<grid_for((long long)m.Nx * m.Ny * m.wz, 256, sm_count * 16), 256, 0, st>>>(m, src);
+}
+void launch_occupancy(const MapDev& m, const double* pos, long long n, int8_t* out, cudaStream_t st) {
+  if (n > 0) occupancy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n, out);
+}
+void launch_in_map(const MapDev& m, const double* pos, long long n, uint8_t* out, cudaStream_t st) {
+  if (n > 0) in_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n, out);
+}
+void launch_pos_to_index(const MapDev& m, const double* pos, long long n, int32_t* out, cudaStream_t st) {
+  if (n > 0) pos_to_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n, out);
+}
+void launch_los_batch(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* nsamples, int sm_count,
+                      cudaStream_t st) {
+  if (n <= 0) return;
+  const long long warps_needed = n;
+  const int blocks = grid_for(warps_needed * 32, 256, sm_count * 8);
+  los_batch_kernel<<<blocks, 256, 0, st>>>(m, s, e, n, vis, nsamples);
+}
+
+}  // namespace b200

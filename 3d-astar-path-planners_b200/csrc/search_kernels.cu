@@ -1,0 +1,532 @@
+// search_kernels.cu — batched independent path queries, one query per thread block (persistent blocks
+// pull query ids from a global counter).
+//
+// Behaviour restated from the reference (not ported): src/Planners/AStar.cpp:80-179 (findPath),
+// :56-78 (ComputeCost/UpdateVertex), src/Planners/ThetaStar.cpp:37-89, src/utils/LineOfSight.cpp:9-27,
+// src/Planners/AlgorithmBase.cpp:123-212 (result object, retrievePath), src/utils/geometry_utils.cpp:10-20.
+// Semantics are the CANONICAL ones of DESIGN.md §"Search semantics" (SURVEY Appendix B): node index =
+// creation order, open list = exact priority queue on (f, creation index) with true decrease-key, guarded
+// relaxations, hash keyed on the exact FP64 triple.  oracle/oracle.cpp (mode CANONICAL) is the checker.
+//
+// Mapping to the machine:
+//   * warp 0 of the block is the control warp: lane L < 27 owns neighbour offset L of the current
+//     expansion (same dx->dy->dz order as AStar.cpp:131-133), so the 26 isInMap tests, exact-key hash
+//     probes, occupancy bit reads and relaxations of one expansion run in one warp-wide pass; node
+//     creation order is recovered with a ballot prefix so pool indices match the sequential loop.
+//   * open list: 32-ary implicit heap in the slot's HBM workspace (L1/L2 resident).  A pop reads each
+//     level as one aligned 512 B row (one entry per lane) and finds the minimum with three REDUX ops.
+//   * Theta*: the <= 26 fastLOS segments of an expansion are spread over all warps of the block,
+//     warp-per-segment, lanes = consecutive 0.05 m samples, __ballot_sync early-out (common.cuh).
+//   * FP64 everywhere positions are touched (voxel registration is rounding-dependent).
+#include "kernels.h"
+
+namespace b200 {
+
+enum { NODE_NEW = 0, NODE_OPEN = 1, NODE_CLOSED = 2 };
+
+__device__ __forceinline__ unsigned long long fkey(double f) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(f);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ bool key_less(unsigned long long ka, uint32_t ia, unsigned long long kb, uint32_t ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+__device__ __forceinline__ uint32_t hash3(double x, double y, double z) {
+  // -0.0 + 0.0 == +0.0: keys that compare equal under `==` hash equally (utils.hpp:63-92 semantics)
+  unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0);
+  unsigned long long b = (unsigned long long)__double_as_longlong(y + 0.0);
+  unsigned long long c = (unsigned long long)__double_as_longlong(z + 0.0);
+  unsigned long long h = a * 0x9E3779B97F4A7C15ULL;
+  h ^= (b + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2)) * 0xC2B2AE3D27D4EB4FULL;
+  h ^= (c + 0x165667B19E3779F9ULL + (h << 6) + (h >> 2)) * 0xFF51AFD7ED558CCDULL;
+  h ^= h >> 33;
+  h *= 0xC4CEB9FE1A85EC53ULL;
+  h ^= h >> 29;
+  return (uint32_t)h;
+}
+
+struct Slot {
+  NodeRec* nodes;
+  uint32_t* hash;
+  HeapEnt* heap;  // physical index = logical + 31 (children of k: physical 32k+32 .. 32k+63)
+  uint32_t hmask;
+  int heap_n;
+  int use;
+};
+
+// ---- 32-ary heap, all 32 lanes of the control warp call these with warp-uniform arguments ----------
+__device__ __forceinline__ void heap_place(Slot& s, int k, unsigned long long key, uint32_t idx, int lane) {
+  if (lane == 0) {
+    HeapEnt e;
+    e.key = key; e.idx = idx; e.pad = 0;
+    s.heap[k + 31] = e;
+    s.nodes[idx].hpos = k;
+  }
+}
+__device__ __forceinline__ void heap_sift_up(Slot& s, int k, unsigned long long key, uint32_t idx, int lane) {
+  while (k > 0) {
+    const int par = (k - 1) >> 5;
+    const HeapEnt pe = s.heap[par + 31];
+    if (!key_less(key, idx, pe.key, pe.idx)) break;
+    heap_place(s, k, pe.key, pe.idx, lane);
+    k = par;
+  }
+  heap_place(s, k, key, idx, lane);
+  __syncwarp();
+}
+__device__ __forceinline__ void heap_push(Slot& s, unsigned long long key, uint32_t idx, int lane) {
+  const int k = s.heap_n++;
+  heap_sift_up(s, k, key, idx, lane);
+}
+// removes the root; returns its node index
+__device__ __forceinline__ uint32_t heap_pop(Slot& s, int lane) {
+  const HeapEnt top = s.heap[31];
+  const int n = --s.heap_n;
+  if (lane == 0) s.nodes[top.idx].hpos = -1;
+  if (n > 0) {
+    const HeapEnt last = s.heap[n + 31];
+    int k = 0;
+    for (;;) {
+      const int c0 = 32 * k + 1;
+      if (c0 >= n) break;
+      const int ci = c0 + lane;
+      const bool valid = ci < n;
+      HeapEnt ce;
+      ce.key = ~0ULL; ce.idx = 0xffffffffu; ce.pad = 0;
+      if (valid) ce = s.heap[ci + 31];
+      const uint32_t hi = valid ? (uint32_t)(ce.key >> 32) : 0xffffffffu;
+      const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+      const uint32_t lo = (valid && hi == mhi) ? (uint32_t)ce.key : 0xffffffffu;
+      const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+      const uint32_t id = (valid && hi == mhi && lo == mlo) ? ce.idx : 0xffffffffu;
+      const uint32_t mid = __reduce_min_sync(0xffffffffu, id);
+      const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+      if (!key_less(mkey, mid, last.key, last.idx)) break;
+      const int wl = __ffs(__ballot_sync(0xffffffffu, valid && id == mid)) - 1;
+      heap_place(s, k, mkey, mid, lane);
+      k = c0 + wl;
+    }
+    heap_place(s, k, last.key, last.idx, lane);
+  }
+  __syncwarp();
+  return top.idx;
+}
+
+// exact-key probe: returns node index or -1
+__device__ __forceinline__ int hash_find(const Slot& s, double x, double y, double z) {
+  uint32_t h = hash3(x, y, z) & s.hmask;
+  for (;;) {
+    const uint32_t e = s.hash[h];
+    if (e == 0) return -1;
+    const NodeRec* n = s.nodes + (e - 1);
+    if (n->px == x && n->py == y && n->pz == z) return (int)(e - 1);
+    h = (h + 1) & s.hmask;
+  }
+}
+__device__ __forceinline__ uint32_t hash_insert(const Slot& s, double x, double y, double z, int idx) {
+  uint32_t h = hash3(x, y, z) & s.hmask;
+  for (;;) {
+    if (atomicCAS(s.hash + h, 0u, (uint32_t)idx + 1u) == 0u) return h;
+    h = (h + 1) & s.hmask;
+  }
+}
+
+struct Shared {
+  long long q;
+  int state;       // 0 continue, 1 query finished
+  int los_phase;   // this expansion needs the block-wide LoS phase
+  unsigned valid;  // neighbour lanes that reach UpdateVertex
+  double ppx, ppy, ppz;
+  double nbx[27], nby[27], nbz[27];
+  int nsamp[27];
+  unsigned char vis[27];
+};
+
+// cost-aware edge (ours, DESIGN.md "Cost-aware variants"): len + w * (len * ((qa + qb) / 131070))
+__device__ __forceinline__ double costq_at(const MapDev& m, double x, double y, double z) {
+  const int ix = min(max(pos_to_idx1(x, m.ox, m.inv_res), 0), m.Nx - 1);
+  const int iy = min(max(pos_to_idx1(y, m.oy, m.inv_res), 0), m.Ny - 1);
+  const int iz = min(max(pos_to_idx1(z, m.oz, m.inv_res), 0), m.Nz - 1);
+  return (double)m.costq[vox_addr(m, ix, iy, iz)];
+}
+template <bool COST>
+__device__ __forceinline__ double edge_cost(const SearchParams& P, double ax, double ay, double az, double bx, double by, double bz,
+                                            double len) {
+  if (!COST) return len;
+  const double qa = costq_at(P.map, ax, ay, az), qb = costq_at(P.map, bx, by, bz);
+  return dadd(len, dmul(P.cost_weight, dmul(len, __ddiv_rn(dadd(qa, qb), 131070.0))));
+}
+
+template <int ALGO, int NW>
+__global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
+  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR;
+  constexpr bool IS_LAZY = ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
+  constexpr bool IS_COST = ALGO == ALGO_COSTASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
+  __shared__ Shared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MapDev& m = P.map;
+  Slot s;
+  s.nodes = P.nodes + (size_t)blockIdx.x * P.cap;
+  s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
+  s.heap = P.heap + (size_t)blockIdx.x * ((size_t)P.cap + 32);
+  s.hmask = P.hcap - 1;
+
+  // neighbour offset of this lane: L = 9a + 3b + c <-> (dx,dy,dz) = (dv[a],dv[b],dv[c])  (AStar.cpp:131-133)
+  const int la = lane / 9, lb = (lane / 3) % 3, lc = lane % 3;
+  const double ddx = P.dv[la % 3], ddy = P.dv[lb], ddz = P.dv[lc];
+  const double dnorm = norm3(ddx, ddy, ddz);
+  const bool lane_nb = lane < 27 && !(dnorm < 1e-3);  // AStar.cpp:136
+
+  for (;;) {
+    if (tid == 0) sh.q = (long long)atomicAdd(P.q_counter, 1ULL);
+    __syncthreads();
+    const long long qi = sh.q;
+    if (qi >= P.nq) break;
+    const long long q = P.qlist ? (long long)P.qlist[qi] : qi;
+    const double sx = P.starts[3 * q], sy = P.starts[3 * q + 1], sz = P.starts[3 * q + 2];
+    const double gx = P.goals[3 * q], gy = P.goals[3 * q + 1], gz = P.goals[3 * q + 2];
+    unsigned long long t_begin = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
+
+    // ---------------- initialise (AStar.cpp:87-97) ----------------
+    s.heap_n = 0;
+    s.use = 1;
+    long long iter_num = 0, los_checks = 0, los_samples = 0;
+    int status = ST_OPEN_EMPTY, last = 0, term = -1;
+    if (warp == 0) {
+      if (lane == 0) {
+        NodeRec n;
+        n.px = sx; n.py = sy; n.pz = sz;
+        n.g = 0.0;
+        n.f = dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, sx), dsub(gy, sy), dsub(gz, sz))));
+        n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
+        n.slot = hash_insert(s, sx, sy, sz, 0);
+        s.nodes[0] = n;
+      }
+      __syncwarp();
+      heap_push(s, fkey(s.nodes[0].f), 0u, lane);
+      sh.state = 0;
+    }
+
+    // ---------------- search loop (AStar.cpp:103-173) ----------------
+    int cur = 0;
+    double cx = 0, cy = 0, cz = 0, cg = 0;
+    int cpar = -1;
+    // per-lane neighbour state, live between the phases of one expansion
+    int nb_idx = -1;
+    double nx = 0, ny = 0, nz = 0;
+    for (;;) {
+      bool valid = false;
+      if (warp == 0) {
+        bool done = false;
+        if (s.heap_n == 0) {  // AStar.cpp:175-178
+          status = ST_OPEN_EMPTY; last = cur; done = true;
+        } else {
+          cur = (int)heap_pop(s, lane);
+          NodeRec c = s.nodes[cur];
+          if (IS_LAZY && c.parent >= 0 && c.parent != c.via) {
+            // SetVertex: verify the optimistic parent with one fastLOS; fall back to the best closed neighbour
+            const NodeRec pr = s.nodes[c.parent];
+            const double len = norm3(dsub(pr.px, c.px), dsub(pr.py, c.py), dsub(pr.pz, c.pz));
+            ++los_checks;
+            bool vis = false;
+            int ns = 0;
+            unsigned long long sumq = 0;
+            if (!(P.max_los > 0 && len > P.max_los)) vis = los_warp<IS_COST>(m, pr.px, pr.py, pr.pz, c.px, c.py, c.pz, lane, &ns, &sumq);
+            los_samples += ns;
+            bool changed = false;
+            if (vis) {
+              if (IS_COST) {
+                c.g = dadd(pr.g, dadd(len, dmul(P.cost_weight, dmul(kLosStep, __ddiv_rn((double)sumq, 65535.0)))));
+                changed = true;
+              }
+            } else {
+              // candidates: via first, then the 26 exact-key lookups in expansion order; strict < replaces
+              const NodeRec vn = s.nodes[c.via];
+              const int vcode = (c.state >> 8) & 0xff;
+              const double vstep = norm3(P.dv[(vcode / 9) % 3], P.dv[(vcode / 3) % 3], P.dv[vcode % 3]);
+              double best_g = dadd(vn.g, edge_cost<IS_COST>(P, vn.px, vn.py, vn.pz, c.px, c.py, c.pz, vstep));
+              int best = c.via;
+              double cand = __longlong_as_double(0x7ff0000000000000LL);
+              int cand_idx = -1;
+              if (lane_nb) {
+                const double qx = dadd(c.px, ddx), qy = dadd(c.py, ddy), qz = dadd(c.pz, ddz);
+                const int fi = hash_find(s, qx, qy, qz);
+                if (fi >= 0 && (s.nodes[fi].state & 0xff) == NODE_CLOSED) {
+                  const NodeRec fn = s.nodes[fi];
+                  cand = dadd(fn.g, edge_cost<IS_COST>(P, fn.px, fn.py, fn.pz, c.px, c.py, c.pz, dnorm));
+                  cand_idx = fi;
+                }
+              }
+              // sequential-order argmin: smallest value, first lane on ties, and only if strictly below via's
+              const unsigned long long ck = cand_idx >= 0 ? fkey(cand) : ~0ULL;
+              const uint32_t hi = (uint32_t)(ck >> 32);
+              const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+              const uint32_t lo = hi == mhi ? (uint32_t)ck : 0xffffffffu;
+              const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+              const unsigned wm = __ballot_sync(0xffffffffu, cand_idx >= 0 && hi == mhi && lo == mlo);
+              if (wm) {
+                const int wl = __ffs(wm) - 1;
+                const double wg = __shfl_sync(0xffffffffu, cand, wl);
+                const int wi = __shfl_sync(0xffffffffu, cand_idx, wl);
+                if (wg < best_g) { best_g = wg; best = wi; }
+              }
+              c.parent = best;
+              c.g = best_g;
+              changed = true;
+            }
+            if (changed) {
+              c.f = dadd(c.g, dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, c.px), dsub(gy, c.py), dsub(gz, c.pz)))));
+              if (lane == 0) {
+                s.nodes[cur].g = c.g; s.nodes[cur].f = c.f; s.nodes[cur].parent = c.parent;
+              }
+            }
+          }
+          cx = c.px; cy = c.py; cz = c.pz; cg = c.g; cpar = c.parent;
+          // termination (AStar.cpp:110-119)
+          if (fabs(dsub(cx, gx)) <= P.r && fabs(dsub(cy, gy)) <= P.r && fabs(dsub(cz, gz)) <= P.r) {
+            status = ST_SOLVED; last = cur; term = cur; done = true;
+          }
+        }
+        if (!done) {
+          if (lane == 0) s.nodes[cur].state = (s.nodes[cur].state & ~0xff) | NODE_CLOSED;  // AStar.cpp:122
+          ++iter_num;
+          __syncwarp();
+          // ---- neighbour resolution (AStar.cpp:131-169), one lane per offset ----
+          nb_idx = -1;
+          valid = lane_nb;
+          nx = dadd(cx, ddx); ny = dadd(cy, ddy); nz = dadd(cz, ddz);            // :138
+          if (valid && !is_in_map(m, nx, ny, nz)) valid = false;                 // :141
+          if (valid) {
+            nb_idx = hash_find(s, nx, ny, nz);                                   // :146
+            if (nb_idx >= 0 && (s.nodes[nb_idx].state & 0xff) == NODE_CLOSED) valid = false;  // :147
+          }
+          if (valid && inflate_occ(m, nx, ny, nz) == 1) valid = false;          // :151
+          const bool need = valid && nb_idx < 0;
+          const unsigned cm = __ballot_sync(0xffffffffu, need);
+          const int ncreate = __popc(cm);
+          const int rank = __popc(cm & ((1u << lane) - 1u));
+          bool oom = false, overflow = false;
+          int fail_lane = 32;
+          if (ncreate > 0) {
+            if (P.cap < P.allocate_num && s.use + ncreate > P.cap) {
+              overflow = true;  // physical tier too small: the host reruns this query in the big tier
+            } else if (s.use + ncreate >= P.allocate_num) {  // :165-168: the creation that makes use == allocate_num bails out
+              const int fail_rank = P.allocate_num - s.use - 1;
+              const unsigned fm = __ballot_sync(0xffffffffu, need && rank == fail_rank);
+              fail_lane = __ffs(fm) - 1;
+              oom = true;
+            }
+          }
+          if (overflow) {
+            status = ST_TIER_OVERFLOW; last = cur; done = true;
+          } else {
+            if (need && lane <= fail_lane && s.use + rank < P.cap) {
+              const int ni = s.use + rank;
+              NodeRec n;
+              n.px = nx; n.py = ny; n.pz = nz;
+              n.g = __longlong_as_double(0x7ff0000000000000LL);
+              n.f = n.g;
+              n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_NEW; n.pad = 0;
+              n.slot = hash_insert(s, nx, ny, nz, ni);
+              s.nodes[ni] = n;
+              nb_idx = ni;
+            }
+            if (oom) {
+              if (lane >= fail_lane) valid = false;  // the failing neighbour and everything after it never reach UpdateVertex
+              s.use = min(P.allocate_num, P.cap);
+              status = ST_POOL_EXHAUSTED; last = cur;
+            } else {
+              s.use += ncreate;
+            }
+            __syncwarp();
+          }
+          if (!done) {
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (IS_THETA) {
+              const bool lp = cpar >= 0 && vm != 0;
+              if (lp) {
+                los_checks += __popc(vm);  // ThetaStar.cpp:50
+                if (lane < 27) { sh.nbx[lane] = nx; sh.nby[lane] = ny; sh.nbz[lane] = nz; }
+                if (lane == 0) {
+                  const NodeRec pr = s.nodes[cpar];
+                  sh.ppx = pr.px; sh.ppy = pr.py; sh.ppz = pr.pz;
+                  sh.valid = vm;
+                }
+              }
+              if (lane == 0) sh.los_phase = lp ? 1 : 0;
+            }
+          }
+        }
+        if (lane == 0) sh.state = done ? 1 : 0;
+        if (done) valid = false;
+      }
+      if (NW > 1) __syncthreads(); else __syncwarp();
+      if (sh.state == 1) break;
+
+      // ---- Theta*: block-wide line-of-sight phase (ThetaStar.cpp:49-51) ----
+      if (IS_THETA && sh.los_phase) {
+        const unsigned vm = sh.valid;
+        const double ppx = sh.ppx, ppy = sh.ppy, ppz = sh.ppz;
+        for (int seg = warp; seg < 27; seg += NW) {
+          if (!((vm >> seg) & 1u)) continue;
+          const double ex = sh.nbx[seg], ey = sh.nby[seg], ez = sh.nbz[seg];
+          bool vis = false;
+          int ns = 0;
+          if (P.max_los > 0) {
+            const double len = norm3(dsub(ppx, ex), dsub(ppy, ey), dsub(ppz, ez));
+            if (len > P.max_los) { if (lane == 0) { sh.vis[seg] = 0; sh.nsamp[seg] = 0; } continue; }
+          }
+          vis = los_warp<false>(m, ppx, ppy, ppz, ex, ey, ez, lane, &ns, nullptr);
+          if (lane == 0) { sh.vis[seg] = vis ? 1 : 0; sh.nsamp[seg] = ns; }
+        }
+        if (NW > 1) __syncthreads(); else __syncwarp();
+      }
+
+      // ---- UpdateVertex (AStar.cpp:65-78 / ThetaStar.cpp:37-89), control warp ----
+      if (warp == 0) {
+        bool improved = false;
+        double new_g = 0, new_f = 0;
+        if (valid) {
+          const NodeRec nb = s.nodes[nb_idx];
+          int new_parent = cur;
+          bool use_parent = false;
+          if (IS_THETA && cpar >= 0) {
+            los_samples += sh.nsamp[lane];
+            use_parent = sh.vis[lane] != 0;
+          }
+          if (IS_THETA && use_parent) {  // ThetaStar.cpp:51-60
+            const NodeRec pr = s.nodes[cpar];
+            const double dist = norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz));
+            new_g = dadd(pr.g, dist);
+            new_parent = cpar;
+          } else if (IS_LAZY && cpar >= 0) {  // optimistic path 2 (Lazy Theta*)
+            const NodeRec pr = s.nodes[cpar];
+            const double dist = norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz));
+            new_g = dadd(pr.g, edge_cost<IS_COST>(P, pr.px, pr.py, pr.pz, nx, ny, nz, dist));
+            new_parent = cpar;
+          } else {  // AStar.cpp:57 / ThetaStar.cpp:39-47,61-69
+            new_g = dadd(cg, edge_cost<IS_COST>(P, cx, cy, cz, nx, ny, nz, dnorm));
+          }
+          if (new_g < nb.g) {
+            improved = true;
+            new_f = dadd(new_g, dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, nx), dsub(gy, ny), dsub(gz, nz)))));
+            NodeRec* w = s.nodes + nb_idx;
+            w->g = new_g; w->f = new_f; w->parent = new_parent;
+            w->state = NODE_OPEN | (lane << 8);
+            if (IS_LAZY) w->via = cur;
+          }
+        }
+        __syncwarp();
+        // open-list updates in lane (= expansion) order; (f, index) is a total order so the order is immaterial
+        unsigned im = __ballot_sync(0xffffffffu, improved);
+        while (im) {
+          const int b = __ffs(im) - 1;
+          im &= im - 1;
+          const uint32_t bi = (uint32_t)__shfl_sync(0xffffffffu, nb_idx, b);
+          const unsigned long long bk = fkey(__shfl_sync(0xffffffffu, new_f, b));
+          const int hp = s.nodes[bi].hpos;
+          if (hp >= 0) heap_sift_up(s, hp, bk, bi, lane);
+          else heap_push(s, bk, bi, lane);
+        }
+        if (status == ST_POOL_EXHAUSTED) {
+          if (lane == 0) sh.state = 1;
+        }
+      }
+      if (NW > 1) __syncthreads(); else __syncwarp();
+      if (sh.state == 1) break;
+    }
+
+    // ---------------- result (AlgorithmBase.cpp:123-175, :202-212; geometry_utils.cpp:10-20) -------------
+    if (warp == 0) {
+      if (IS_THETA || IS_LAZY) {
+        // los_samples was accumulated per lane; fold it
+        long long v = los_samples;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        los_samples = IS_LAZY ? los_samples : v;
+      }
+      int n_path = 0;
+      long long off = -1;
+      float plen = 0.f;
+      int* chain = reinterpret_cast<int*>(s.heap);  // the open list is dead now: reuse it as scratch
+      float* seglen = reinterpret_cast<float*>(s.heap) + (size_t)P.cap + 8;
+      if (status == ST_SOLVED) {
+        if (lane == 0) {
+          int c = term;
+          while (c >= 0) { chain[n_path++] = c; c = s.nodes[c].parent; }
+          if (P.path_pool) {
+            const unsigned long long o = atomicAdd(P.path_cursor, (unsigned long long)n_path);
+            off = (o + (unsigned long long)n_path <= (unsigned long long)P.path_cap) ? (long long)o : -1;
+          }
+        }
+        n_path = __shfl_sync(0xffffffffu, n_path, 0);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        __syncwarp();
+        for (int i = lane; i < n_path; i += 32) {
+          const NodeRec a = s.nodes[chain[n_path - 1 - i]];
+          if (off >= 0) {
+            P.path_pool[3 * (off + i)] = a.px; P.path_pool[3 * (off + i) + 1] = a.py; P.path_pool[3 * (off + i) + 2] = a.pz;
+          }
+          if (i > 0) {
+            const NodeRec b = s.nodes[chain[n_path - i]];
+            const double ux = dmul(dsub(a.px, b.px), m.res), uy = dmul(dsub(a.py, b.py), m.res), uz = dmul(dsub(a.pz, b.pz), m.res);
+            seglen[i] = __fsqrt_rn((float)dadd(dadd(dmul(ux, ux), dmul(uy, uy)), dmul(uz, uz)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int i = 1; i < n_path; ++i) plen = __fadd_rn(plen, seglen[i]);
+      }
+      if (lane == 0) {
+        b200_path_result_t r;
+        const NodeRec ln = s.nodes[last];
+        r.solved = status == ST_SOLVED ? 1 : 0;
+        r.status = status;
+        r.n_path = n_path;
+        r.pad = 0;
+        r.path_offset = off;
+        r.g_final = ln.g;
+        r.path_length = (double)plen;
+        r.explored_nodes = s.use;
+        r.iter_num = iter_num;
+        r.los_checks = los_checks;
+        r.los_samples = los_samples;
+        r.goal_coords[0] = ln.px; r.goal_coords[1] = ln.py; r.goal_coords[2] = ln.pz;
+        r.start_coords[0] = sx; r.start_coords[1] = sy; r.start_coords[2] = sz;
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        r.time_us = (double)(t_end - t_begin) * 1e-3;
+        P.results[q] = r;
+        if (status == ST_TIER_OVERFLOW && P.overflow_list) P.overflow_list[atomicAdd(P.overflow_count, 1)] = (int)q;
+      }
+      sh.state = s.use;  // broadcast the number of used nodes for the clearing pass
+    }
+    __syncthreads();
+    // reset(): clear only the hash slots this query touched (AlgorithmBase.cpp:17-32 analogue)
+    const int used = min(sh.state, P.cap);
+    for (int i = tid; i < used; i += NW * 32) s.hash[s.nodes[i].slot] = 0u;
+    __syncthreads();
+  }
+}
+
+size_t search_slot_bytes(int cap, uint32_t* hcap_out) {
+  uint32_t h = 1024;
+  while (h < 2u * (uint32_t)cap) h <<= 1;
+  if (hcap_out) *hcap_out = h;
+  return (size_t)cap * sizeof(NodeRec) + (size_t)h * 4 + ((size_t)cap + 32) * sizeof(HeapEnt);
+}
+
+int search_threads_per_block(int algo) { return algo == ALGO_THETASTAR ? 128 : 32; }
+
+void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
+  switch (p.algo) {
+    case ALGO_ASTAR: search_kernel<ALGO_ASTAR, 1><<<slots, 32, 0, st>>>(p); break;
+    case ALGO_THETASTAR: search_kernel<ALGO_THETASTAR, 4><<<slots, 128, 0, st>>>(p); break;
+    case ALGO_LAZYTHETASTAR: search_kernel<ALGO_LAZYTHETASTAR, 1><<<slots, 32, 0, st>>>(p); break;
+    case ALGO_COSTASTAR: search_kernel<ALGO_COSTASTAR, 1><<<slots, 32, 0, st>>>(p); break;
+    default: search_kernel<ALGO_COSTLAZYTHETASTAR, 1><<<slots, 32, 0, st>>>(p); break;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,106 @@
+"""Seeded synthetic worlds, point clouds and query sets.
+
+`forest()` mimics the reference's simulator (`map_generator/random_forest`): uniformly placed axis-aligned
+pillars, width U[0.5,1.2] m, height U[0.8,3.0] m (launch/simulator.xml:26-29, simulator2.xml:28-31 of the
+reference), sampled at voxel centres, stored as float32 xyz with PCL PointXYZ stride 16.
+Pure numpy; no GPU, no oracle.
+"""
+import numpy as np
+
+CONFIGS = {
+    # name: origin, size, resolution (SURVEY.md §8d / BASELINE.md §3)
+    "C1": dict(origin=(-5.0, -5.0, -0.01), size=(50.0, 50.0, 10.0), resolution=0.2, seed=1, n_pillars=120),
+    "C2": dict(origin=(-25.6, -25.6, -0.01), size=(51.2, 51.2, 12.8), resolution=0.1, seed=2, n_pillars=700),
+    "C3": dict(origin=(-12.8, -12.8, -0.01), size=(25.6, 25.6, 6.4), resolution=0.1, seed=4, n_pillars=60),
+    "C4": dict(origin=(-25.6, -25.6, -0.01), size=(51.2, 51.2, 12.8), resolution=0.1, seed=2, n_pillars=700),
+}
+
+
+def pack_cloud(xyz, point_step=16):
+    """float32 (n,3) -> PointCloud2-style byte blob with the given stride (x,y,z at offsets 0,4,8)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = len(xyz)
+    if point_step == 12:
+        return xyz.copy()
+    out = np.zeros((n, point_step // 4), dtype=np.float32)
+    out[:, :3] = xyz
+    return out
+
+
+def forest(seed, origin, size, resolution, n_pillars, ground=False, n_points=None, keep_clear=()):
+    """Returns float32 (n,3) points. keep_clear: list of (xyz, radius) around which no pillar is placed."""
+    rng = np.random.default_rng(seed)
+    o = np.asarray(origin, dtype=np.float64)
+    s = np.asarray(size, dtype=np.float64)
+    r = float(resolution)
+    pts = []
+    placed = 0
+    guard = 0
+    while placed < n_pillars and guard < 50 * n_pillars:
+        guard += 1
+        w = rng.uniform(0.5, 1.2)
+        h = rng.uniform(0.8, 3.0)
+        cx = rng.uniform(o[0] + 1.0, o[0] + s[0] - 1.0)
+        cy = rng.uniform(o[1] + 1.0, o[1] + s[1] - 1.0)
+        if any(np.hypot(cx - c[0], cy - c[1]) < rad + w for c, rad in keep_clear):
+            continue
+        placed += 1
+        i0, i1 = int(np.floor((cx - w / 2 - o[0]) / r)), int(np.ceil((cx + w / 2 - o[0]) / r))
+        j0, j1 = int(np.floor((cy - w / 2 - o[1]) / r)), int(np.ceil((cy + w / 2 - o[1]) / r))
+        k1 = max(1, int(np.ceil(min(h, s[2] - 2 * r) / r)))
+        ii, jj, kk = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), np.arange(0, k1), indexing="ij")
+        p = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], 1).astype(np.float64)
+        pts.append((p + 0.5) * r + o)
+    if ground:
+        nx, ny = int(round(s[0] / r)), int(round(s[1] / r))
+        ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        p = np.stack([ii.ravel(), jj.ravel(), np.zeros(ii.size)], 1).astype(np.float64)
+        pts.append((p + 0.5) * r + o)
+    xyz = np.concatenate(pts, 0) if pts else np.zeros((0, 3))
+    if n_points is not None:
+        if len(xyz) >= n_points:
+            sel = rng.choice(len(xyz), n_points, replace=False)
+            xyz = xyz[sel]
+        else:
+            extra = xyz[rng.integers(0, len(xyz), n_points - len(xyz))]
+            extra = extra + rng.uniform(-0.5 * r, 0.5 * r, extra.shape)
+            xyz = np.concatenate([xyz, extra], 0)
+        xyz = xyz[rng.permutation(len(xyz))]
+    return xyz.astype(np.float32)
+
+
+def uniform_cloud(seed, origin, size, n_points, margin=0.0):
+    rng = np.random.default_rng(seed)
+    o = np.asarray(origin, dtype=np.float64) - margin
+    s = np.asarray(size, dtype=np.float64) + 2 * margin
+    return (o + rng.random((n_points, 3)) * s).astype(np.float32)
+
+
+def config_cloud(name, n_points=None, ground=None):
+    c = CONFIGS[name]
+    ground = (name in ("C2", "C4")) if ground is None else ground
+    return forest(c["seed"], c["origin"], c["size"], c["resolution"], c["n_pillars"], ground=ground, n_points=n_points,
+                  keep_clear=[((0.0, 0.0, 0.0), 1.0), ((40.0, 40.0, 4.0), 1.0)] if name == "C1" else ())
+
+
+def random_queries(seed, occ_fn, origin, size, n, min_dist=5.0, z_range=None, margin=0.5):
+    """n (start, goal) pairs uniform over free inflated space; occ_fn(pos(n,3)) -> int8 {-1,0,1}."""
+    rng = np.random.default_rng(seed)
+    o = np.asarray(origin, dtype=np.float64)
+    s = np.asarray(size, dtype=np.float64)
+    lo = o + margin
+    hi = o + s - margin
+    if z_range is not None:
+        lo[2], hi[2] = z_range
+    starts, goals = [], []
+    need = n
+    while need > 0:
+        m = max(1024, 3 * need)
+        a = lo + rng.random((m, 3)) * (hi - lo)
+        b = lo + rng.random((m, 3)) * (hi - lo)
+        ok = (occ_fn(a) == 0) & (occ_fn(b) == 0) & (np.linalg.norm(a - b, axis=1) >= min_dist)
+        a, b = a[ok][:need], b[ok][:need]
+        starts.append(a)
+        goals.append(b)
+        need -= len(a)
+    return np.concatenate(starts, 0), np.concatenate(goals, 0)

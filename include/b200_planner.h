@@ -1,0 +1,187 @@
+/*
+ * b200_planner.h — C-ABI of libb200planner.so: the B200 (sm_100a) replacement for the data-parallel hot
+ * path of ChanJoon/3D-Astar-Path-Planners (ROS package heuristic_planners).
+ *
+ * The reference has no FFI layer: its seam is two C++ classes, `GridMap` (include/plan_env/grid_map.h:139-196)
+ * and `Planners::AlgorithmBase` (include/Planners/AlgorithmBase.hpp:28-53), consumed by
+ * `HeuristicPlannerROS` (src/planner_ros_node.cpp).  Every entry point below names the reference member it
+ * replaces (file:line relative to the reference root).  The C++ adapter classes that put the reference's
+ * own method names back on top of this ABI live in 3d-astar-path-planners_b200/host/; INTEGRATION.md shows
+ * the binding a maintainer would add to the ROS node.
+ *
+ * Conventions: plain pointers and sizes, opaque handles, `int` status (0 = OK, <0 = error, see
+ * b200_status_t), no exceptions across the boundary, caller-owned output buffers.  A handle is
+ * thread-compatible (not thread-safe).  All work of a handle is issued on one CUDA stream (default: the
+ * legacy default stream, so it orders with a framework's default stream; see b200_map_set_stream); calls
+ * that return data to host memory synchronise that stream before returning.  Calls taking `on_device != 0`
+ * expect device pointers on the handle's device and do not synchronise.
+ *
+ * There is no CPU fallback: every call fails with B200_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef B200_PLANNER_H
+#define B200_PLANNER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,     /* bad argument / NULL handle */
+  B200_ERR_CUDA = -2,        /* CUDA runtime error; text via b200_last_error() */
+  B200_ERR_NOMEM = -3,       /* device or host allocation failed */
+  B200_ERR_UNSUPPORTED = -4, /* parameter combination outside the supported envelope */
+  B200_ERR_NO_MAP = -5       /* planner used before b200_planner_set_map */
+} b200_status_t;
+
+typedef struct b200_map b200_map_t;
+typedef struct b200_planner b200_planner_t;
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* GridMap                                                                                              */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* MappingParameters subset used by the cloud path (include/plan_env/grid_map.h:50-58).  `origin` is explicit;
+ * the reference derives it as (-size_x/2, -size_y/2, ground_height) (src/plan_env/grid_map.cpp:53). */
+typedef struct {
+  double origin[3];             /* map_origin_            grid_map.cpp:53  */
+  double size[3];               /* map_size_              grid_map.cpp:54  */
+  double resolution;            /* grid_map/resolution    grid_map.cpp:12  */
+  double obstacles_inflation;   /* grid_map/obstacles_inflation grid_map.cpp:19 */
+  double local_update_range[3]; /* grid_map/local_update_range_{x,y,z} grid_map.cpp:16-18 */
+  double ground_height;         /* grid_map/ground_height grid_map.cpp:50  */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t reserved;
+} b200_map_params_t;
+
+/* GridMap::initMap — geometry + buffer allocation (grid_map.cpp:52-54,69-80).  Grid starts all-free. */
+int b200_map_create(const b200_map_params_t* params, b200_map_t** out);
+int b200_map_destroy(b200_map_t* map);
+/* Use an existing cudaStream_t (passed as void*) for all work of this map and of planners bound to it. */
+int b200_map_set_stream(b200_map_t* map, void* cuda_stream);
+int b200_map_sync(b200_map_t* map);
+
+/* map_voxel_num_ (grid_map.cpp:69-70) */
+int b200_map_dims(const b200_map_t* map, int32_t n[3]);
+/* GridMap::getRegion (grid_map.cpp:960-963) */
+int b200_map_get_region(const b200_map_t* map, double origin[3], double size[3]);
+/* GridMap::getResolution (grid_map.h:443-446) */
+double b200_map_get_resolution(const b200_map_t* map);
+
+/* GridMap::cloudCallback (grid_map.cpp:711-804): clear the camera-centred box, then voxelise + inflate every
+ * point (float32 x,y,z at byte offsets off_* inside records of `point_step` bytes — the PointCloud2 layout
+ * pcl::fromROSMsg reads, grid_map.cpp:713-714), and update the local bounds.  n == 0 or a NaN camera is a
+ * no-op exactly like :724-728.  `pts` is a host pointer (copied inside) unless on_device != 0. */
+int b200_map_update_cloud(b200_map_t* map, const void* pts, int64_t n, int32_t point_step, int32_t off_x,
+                          int32_t off_y, int32_t off_z, const double cam[3], int32_t on_device);
+/* GridMap::resetBuffer(min,max) (grid_map.cpp:155-171) and resetBuffer() (:144-153). */
+int b200_map_clear_box(b200_map_t* map, const double min_pos[3], const double max_pos[3]);
+int b200_map_reset(b200_map_t* map);
+/* md_.local_bound_min_/max_ after the last cloud update (grid_map.cpp:799-803). */
+int b200_map_local_bounds(b200_map_t* map, int32_t min_idx[3], int32_t max_idx[3]);
+
+/* GridMap::getInflateOccupancy (grid_map.h:350-359): out[i] in {-1 outside map, 0 free, 1 occupied}. */
+int b200_map_get_inflate_occupancy(b200_map_t* map, const double* pos_xyz, int64_t n, int8_t* out,
+                                   int32_t on_device);
+/* GridMap::isInMap(Vector3d) (grid_map.h:370-385): out[i] in {0,1}. */
+int b200_map_is_in_map(b200_map_t* map, const double* pos_xyz, int64_t n, uint8_t* out, int32_t on_device);
+/* GridMap::posToIndex (grid_map.h:400-404): out[3*i..] = floor((pos-origin)*res_inv). */
+int b200_map_pos_to_index(b200_map_t* map, const double* pos_xyz, int64_t n, int32_t* out_idx, int32_t on_device);
+
+/* occupancy_buffer_inflate_ in the reference's own layout: one byte per voxel, address x*Ny*Nz + y*Nz + z
+ * (grid_map.h:257-260).  Download is for parity / publishers; upload replaces the grid (≡ setOccupied loops). */
+int b200_map_download_inflate(b200_map_t* map, uint8_t* dst);
+int b200_map_upload_inflate(b200_map_t* map, const uint8_t* src);
+/* Device pointer + word count of the bit-packed grid (uint32 words, [x][y][ceil(Nz/32)], bit z&31). */
+int b200_map_device_bits(b200_map_t* map, void** dev_ptr, int64_t* n_words);
+
+/* NEW (not in the reference; replaces the commented-out evaluateCoarseEDT hook, AlgorithmBase.cpp:40-42):
+ * exact squared Euclidean distance (voxel units, int32; 1<<29 where no obstacle exists) of every voxel to
+ * the nearest inflated-occupied voxel, plus — when d_safe > 0 — the safety-cost field
+ * c = max(0, 1 - sqrt(d2)*res/d_safe) (float32) and its uint16 quantisation the cost-aware planners read. */
+int b200_map_build_edt(b200_map_t* map, double d_safe);
+int b200_map_download_dist2(b200_map_t* map, int32_t* dst);
+int b200_map_download_costq(b200_map_t* map, uint16_t* dst);
+int b200_map_download_cost(b200_map_t* map, float* dst);
+
+/* LineOfSight::fastLOS (src/utils/LineOfSight.cpp:9-27) for n independent segments:
+ * visible[i] = 1 iff no 0.05 m sample of start→end is occupied or outside the map.
+ * n_samples (optional, may be NULL) = samples the reference loop evaluates. */
+int b200_los_batch(b200_map_t* map, const double* seg_start_xyz, const double* seg_end_xyz, int64_t n,
+                   uint8_t* visible, int32_t* n_samples, int32_t on_device);
+
+/* Per-stage device times (ms, CUDA events on the map's stream) of the last update_cloud / build_edt when
+ * profiling is enabled: [0] clear, [1] scatter, [2] edt z+y pass, [3] edt x pass (+cost), [4..7] reserved. */
+int b200_map_set_profiling(b200_map_t* map, int32_t enable);
+int b200_map_get_stage_ms(b200_map_t* map, double out_ms[8]);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Planners                                                                                             */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* ROS params of AStar::setParam / ThetaStar::setParam (src/Planners/AStar.cpp:31-41, ThetaStar.cpp:25-35)
+ * + AlgorithmBase::setCostFactor (AlgorithmBase.hpp:39) + GetPath.srv:26 max_los. */
+typedef struct {
+  double resolution;        /* <algo>/resolution */
+  double lambda_heuristic;  /* <algo>/lambda_heuristic */
+  int32_t allocate_num;     /* <algo>/allocate_num: node budget per query */
+  int32_t reserved;
+  double cost_weight;       /* cost-aware variants only */
+  double max_los;           /* <= 0: unlimited */
+} b200_planner_params_t;
+
+/* AlgorithmBase::createResultDataObject (src/Planners/AlgorithmBase.cpp:123-175) as a plain struct. */
+typedef struct {
+  int32_t solved;           /* "solved" */
+  int32_t status;           /* 0 solved, 1 open set empty (AStar.cpp:175-178), 2 pool exhausted (:165-168) */
+  int32_t n_path;           /* path.size() */
+  int32_t pad;
+  int64_t path_offset;      /* first point of this path inside the caller's path buffer (in points) */
+  double g_final;           /* "g_final_node" */
+  double path_length;       /* "path_length" (float accumulation, geometry_utils.cpp:10-20) */
+  int64_t explored_nodes;   /* "explored_nodes" = use_node_num_ */
+  int64_t iter_num;         /* iter_num_ (expansions) */
+  int64_t los_checks;       /* "line_of_sight_checks" */
+  int64_t los_samples;      /* fastLOS samples evaluated (extra counter) */
+  double goal_coords[3];    /* "goal_coords" = position of the LAST node (AlgorithmBase.cpp:130) */
+  double start_coords[3];   /* "start_coords" */
+  double time_us;           /* "time_spent": device time of this query (the reference reports 0) */
+} b200_path_result_t;
+
+/* algorithm: "astar", "thetastar" (reference, src/planner_ros_node.cpp:261-285), and the north-star
+ * extensions "lazythetastar", "costastar", "costlazythetastar".  Unknown names fall back to "astar" exactly
+ * like planner_ros_node.cpp:280-284.  ≡ new AStar()/ThetaStar() + setParam() + init(). */
+int b200_planner_create(const char* algorithm, const b200_planner_params_t* params, b200_planner_t** out);
+int b200_planner_destroy(b200_planner_t* planner);
+/* AlgorithmBase::setGridMap (AlgorithmBase.cpp:10-13) */
+int b200_planner_set_map(b200_planner_t* planner, b200_map_t* map);
+/* AlgorithmBase::setCostFactor (AlgorithmBase.hpp:39) */
+int b200_planner_set_cost_factor(b200_planner_t* planner, double cost_weight);
+/* AlgorithmBase::detectCollision (AlgorithmBase.cpp:38-44): *collides = bool(getInflateOccupancy(pos)). */
+int b200_planner_detect_collision(b200_planner_t* planner, const double pos[3], int32_t* collides);
+
+/* AlgorithmBase::reset + findPath(src, tgt) + getPath (AStar.cpp:80-179; AlgorithmBase.cpp:17-32,177-183).
+ * path_xyz receives up to path_cap points (3 doubles each); result->n_path is the full length. */
+int b200_planner_find_path(b200_planner_t* planner, const double start[3], const double goal[3],
+                           b200_path_result_t* result, double* path_xyz, int64_t path_cap);
+/* nq independent queries (one reset+findPath each, one query per thread block).  Paths are packed into
+ * path_xyz (capacity path_cap points) at results[i].path_offset; a path that does not fit keeps n_path but
+ * gets path_offset = -1.  Pointers are host pointers unless on_device != 0. */
+int b200_planner_find_paths(b200_planner_t* planner, const double* starts_xyz, const double* goals_xyz, int64_t nq,
+                            b200_path_result_t* results, double* path_xyz, int64_t path_cap, int32_t on_device);
+/* Kernel launches issued by the last find_paths call (for bench accounting). */
+int b200_planner_last_launches(b200_planner_t* planner, int32_t* n_launches);
+
+/* ---------------------------------------------------------------------------------------------------- */
+const char* b200_last_error(void);
+const char* b200_version(void);
+/* Pinned host memory helpers for callers that want the fast H2D/D2H path. */
+int b200_host_alloc(void** ptr, int64_t bytes);
+int b200_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_PLANNER_H */

@@ -1,0 +1,202 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY (see oracle/oracle.cpp header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ALGOS = {"astar": 0, "thetastar": 1, "lazythetastar": 2, "costastar": 3, "costlazythetastar": 4}
+FAITHFUL, CANONICAL = 0, 1
+
+
+class Result(C.Structure):
+    _fields_ = [("solved", C.c_int32), ("status", C.c_int32), ("n_path", C.c_int32), ("pad", C.c_int32),
+                ("path_offset", C.c_int64), ("g_final", C.c_double), ("path_length", C.c_double),
+                ("explored_nodes", C.c_int64), ("iter_num", C.c_int64), ("los_checks", C.c_int64),
+                ("los_samples", C.c_int64), ("goal_coords", C.c_double * 3), ("start_coords", C.c_double * 3),
+                ("time_us", C.c_double)]
+
+
+RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("pad", "i4"), ("path_offset", "i8"),
+                         ("g_final", "f8"), ("path_length", "f8"), ("explored_nodes", "i8"), ("iter_num", "i8"),
+                         ("los_checks", "i8"), ("los_samples", "i8"), ("goal_coords", "f8", 3),
+                         ("start_coords", "f8", 3), ("time_us", "f8")])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "CXX=g++"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp, dp, i64 = C.c_void_p, C.POINTER(C.c_double), C.c_int64
+        L.orc_map_create.restype = vp
+        L.orc_map_create.argtypes = [dp, dp, C.c_double, C.c_double, dp, C.c_double]
+        L.orc_map_destroy.argtypes = [vp]
+        L.orc_map_dims.argtypes = [vp, C.POINTER(C.c_int)]
+        L.orc_map_update_cloud.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int]
+        L.orc_map_clear_box.argtypes = [vp, dp, dp]
+        L.orc_map_download_inflate.argtypes = [vp, vp]
+        L.orc_map_upload_inflate.argtypes = [vp, vp]
+        L.orc_map_local_bounds.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_map_get_inflate_occupancy.argtypes = [vp, vp, i64, vp]
+        L.orc_map_is_in_map.argtypes = [vp, vp, i64, vp]
+        L.orc_pos_to_index.argtypes = [vp, vp, i64, vp]
+        L.orc_los_batch.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int]
+        L.orc_los_dk.argtypes = [vp, i64]
+        L.orc_edt_brute.argtypes = [vp, vp]
+        L.orc_map_build_edt.argtypes = [vp, C.c_double, vp, vp, vp, C.c_int]
+        L.orc_planner_create.restype = vp
+        L.orc_planner_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.orc_planner_destroy.argtypes = [vp]
+        L.orc_planner_set_map.argtypes = [vp, vp]
+        L.orc_planner_find_path.argtypes = [vp, dp, dp, C.POINTER(Result), vp, i64]
+        L.orc_planner_find_paths.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                             vp, vp, vp, i64, vp, vp, i64, C.c_int]
+        L.orc_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleMap:
+    """Restatement of GridMap's cloud path (grid_map.cpp:52-80,155-171,711-804; grid_map.h:257-404)."""
+
+    def __init__(self, origin, size, resolution, obstacles_inflation=0.099, local_update_range=(1e9, 1e9, 1e9),
+                 ground_height=None):
+        self.origin, self.size, self.res = tuple(origin), tuple(size), float(resolution)
+        gh = origin[2] if ground_height is None else ground_height
+        self.h = lib().orc_map_create(_d3(origin), _d3(size), resolution, obstacles_inflation, _d3(local_update_range), gh)
+        d = (C.c_int * 3)()
+        lib().orc_map_dims(self.h, d)
+        self.dims = tuple(d)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_map_destroy(self.h)
+            self.h = None
+
+    def update_cloud(self, cloud, cam, point_step=None, offsets=(0, 4, 8), nthreads=1):
+        cloud = np.ascontiguousarray(cloud)
+        if point_step is None:
+            point_step = cloud.strides[0] if cloud.ndim == 2 else 16
+        n = cloud.nbytes // point_step
+        lib().orc_map_update_cloud(self.h, _ptr(cloud), n, point_step, *offsets, _d3(cam), nthreads)
+
+    def clear_box(self, mn, mx):
+        lib().orc_map_clear_box(self.h, _d3(mn), _d3(mx))
+
+    def inflate(self):
+        out = np.empty(self.dims, dtype=np.uint8)
+        lib().orc_map_download_inflate(self.h, _ptr(out))
+        return out
+
+    def set_inflate(self, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert grid.shape == self.dims
+        lib().orc_map_upload_inflate(self.h, _ptr(grid))
+
+    def local_bounds(self):
+        a, b = (C.c_int * 3)(), (C.c_int * 3)()
+        lib().orc_map_local_bounds(self.h, a, b)
+        return tuple(a), tuple(b)
+
+    def get_inflate_occupancy(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        lib().orc_map_get_inflate_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
+
+    def is_in_map(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.uint8)
+        lib().orc_map_is_in_map(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out.astype(bool)
+
+    def pos_to_index(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((len(pos), 3), dtype=np.int32)
+        lib().orc_pos_to_index(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
+
+    def los_batch(self, starts, ends, nthreads=1, return_samples=False):
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        e = np.ascontiguousarray(ends, dtype=np.float64).reshape(-1, 3)
+        vis = np.empty(len(s), dtype=np.uint8)
+        ns = np.empty(len(s), dtype=np.int64)
+        lib().orc_los_batch(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(ns), nthreads)
+        return (vis, ns) if return_samples else vis
+
+    def edt_brute(self):
+        out = np.empty(self.dims, dtype=np.int32)
+        lib().orc_edt_brute(self.h, _ptr(out))
+        return out
+
+    def build_edt(self, d_safe=0.0, nthreads=1, want_cost=False):
+        d2 = np.empty(self.dims, dtype=np.int32)
+        cq = np.empty(self.dims, dtype=np.uint16) if d_safe > 0 else None
+        cf = np.empty(self.dims, dtype=np.float32) if (d_safe > 0 and want_cost) else None
+        lib().orc_map_build_edt(self.h, d_safe, _ptr(d2), _ptr(cq) if cq is not None else None,
+                                _ptr(cf) if cf is not None else None, nthreads)
+        return (d2, cq, cf) if want_cost else (d2, cq)
+
+
+def los_dk(n):
+    out = np.empty(n, dtype=np.float64)
+    lib().orc_los_dk(_ptr(out), n)
+    return out
+
+
+class OraclePlanner:
+    """Restatement of AStar/ThetaStar::findPath (AStar.cpp:80-179, ThetaStar.cpp:37-89) + our lazy/cost variants."""
+
+    def __init__(self, algo, omap, resolution, lambda_heuristic=5.0, allocate_num=1000000, mode=CANONICAL,
+                 cost_weight=0.0, max_los=0.0):
+        self.algo, self.mode, self.map = ALGOS[algo], mode, omap
+        self.args = (float(resolution), float(lambda_heuristic), int(allocate_num), float(cost_weight), float(max_los))
+        self.h = lib().orc_planner_create(self.algo, mode, *self.args)
+        lib().orc_planner_set_map(self.h, omap.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_planner_destroy(self.h)
+            self.h = None
+
+    def find_path(self, start, goal, path_cap=100000):
+        r = Result()
+        path = np.empty((path_cap, 3), dtype=np.float64)
+        lib().orc_planner_find_path(self.h, _d3(start), _d3(goal), C.byref(r), _ptr(path), path_cap)
+        res = np.frombuffer(bytes(r), dtype=RESULT_DTYPE)[0]
+        return res, path[: min(r.n_path, path_cap)].copy()
+
+    def find_paths(self, starts, goals, path_stride=0, nthreads=1):
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        g = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, 3)
+        nq = len(s)
+        res = np.zeros(nq, dtype=RESULT_DTYPE)
+        path = np.empty((nq * path_stride, 3), dtype=np.float64) if path_stride else None
+        lib().orc_planner_find_paths(self.algo, self.mode, *self.args, self.map.h, _ptr(s), _ptr(g), nq, _ptr(res),
+                                     _ptr(path) if path is not None else None, path_stride, nthreads)
+        return res, path
+
+
+def max_threads():
+    return lib().orc_max_threads()
