@@ -176,7 +176,7 @@ class GridMap:
             dev = 1
         else:
             cloud = np.ascontiguousarray(cloud)
-            step = point_step or (cloud.strides[0] if cloud.ndim == 2 else 16)
+            step = point_step or (cloud.shape[1] * cloud.itemsize if cloud.ndim == 2 else 16)
             n = cloud.nbytes // step
             dev = 0
         self._keep = cloud

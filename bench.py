@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+Default workload = BASELINE.json configs[1] ("C2"): one *frame* = rebuild the 512x512x128 map from a synthetic
+1M-point PointCloud2: clear + voxelise/inflate scatter + exact squared EDT + quantised safety-cost field.
+  value : ms/frame with the cloud already resident in HBM (CUDA events, L2 flushed between frames)
+  e2e   : ms/frame through the host-facing C-ABI call (pinned host cloud -> H2D inside the timed region,
+          local-bounds read-back D2H)
+  extra : batched path queries/s on the same map (lazythetastar / astar / thetastar) and EDT GB/s
+N > 1 (torchrun): the map is replicated (every rank rebuilds its replica — "replicas only" for the map
+build), the query batch is sharded with no collective; max-over-ranks timing.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_SAFE = 1.0
+QUERY_ALGOS = (("lazythetastar", 16384), ("astar", 16384), ("thetastar", 2048))
+
+
+def build_world(synth):
+    c = synth.CONFIGS["C2"]
+    cloud = synth.config_cloud("C2", n_points=1_000_000)
+    return c, synth.pack_cloud(cloud, 16)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle's restatement of cloudCallback + (our) EDT/cost on all host threads."""
+    if rank != 0:
+        return
+    from astar_planners_b200 import synth
+    from oracle import pyoracle as po
+    c, blob = build_world(synth)
+    nthreads = po.max_threads()
+    om = po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=(60.0, 60.0, 20.0),
+                      ground_height=c["origin"][2])
+    cam = (0.0, 0.0, 1.0)
+
+    def frame():
+        om.update_cloud(blob, cam, point_step=16, nthreads=nthreads)
+        om.build_edt(d_safe=D_SAFE, nthreads=nthreads)
+        om.local_bounds()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        frame()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    line = {"impl": "reference", "metric": "map rebuild ms/frame", "value": ms, "unit": "ms/frame", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "config": {"workload": "C2: 1M-point PointCloud2 -> 512x512x128 inflated occupancy + exact squared EDT + cost field",
+                       "grid": [512, 512, 128], "points": 1000000, "d_safe_m": D_SAFE},
+            "cpu_baseline": {"value": ms, "unit": "ms/frame", "cores": nthreads, "kind": "port",
+                             "sample": f"{args.steps} full C2 frames (cloud update + EDT + cost), oracle/liboracle.so, {nthreads} threads"},
+            "e2e": {"value": ms, "unit": "ms/frame", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the query-throughput extras")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import astar_planners_b200 as b200
+    from astar_planners_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    c, blob = build_world(synth)
+    n_pts = blob.shape[0]
+    cam = (0.0, 0.0, 1.0)
+    gm = b200.GridMap(c["size"], c["resolution"], origin=c["origin"], local_update_range=(60.0, 60.0, 20.0),
+                      ground_height=c["origin"][2], device=local_rank)
+    nvox = int(np.prod(gm.dims))
+    d_cloud = torch.from_numpy(blob).to(dev)
+    h_cloud = torch.from_numpy(blob).pin_memory()
+    h_cloud_np = h_cloud.numpy()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def frame_device():
+        gm.cloudCallback(d_cloud, cam, point_step=16)
+        gm.build_edt(D_SAFE)
+
+    def frame_host():
+        gm.cloudCallback(h_cloud_np, cam, point_step=16)
+        gm.build_edt(D_SAFE)
+        return gm.local_bounds()  # D2H read-back of the frame's result (6 x int64 keys)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gm.set_profiling(True)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        frame_device()
+    torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY `steps` frames, L2 flushed (untimed) before each, CUDA events per frame
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = np.zeros((args.steps, 8))
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        ev[i][0].record()
+        frame_device()
+        ev[i][1].record()
+        stage[i] = gm.stage_ms()  # syncs the stream (outside the event bracket)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
+    per = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(per.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e: host cloud through the C-ABI, H2D inside, bounds read back
+    for _ in range(3):
+        frame_host()
+    barrier()
+    e2e_t = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        frame_host()
+        torch.cuda.synchronize()
+        e2e_t.append((time.perf_counter() - t0) * 1e3)
+    e2e_total = float(np.sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_ms = e2e_total / args.steps
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event durations from the timed region)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    st = stage.mean(axis=0)  # [clear, scatter, edt_zy, edt_x]
+    kernels = {
+        "clear(memset)": (st[0], nvox / 8),
+        "scatter_kernel": (st[1], 16 * n_pts + nvox / 8),
+        "edt_zy_kernel": (st[2], nvox / 8 + 4 * nvox),
+        "edt_x_kernel": (st[3], 4 * nvox + 4 * nvox + 2 * nvox),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                "stage_ms": {k: float(v[0]) for k, v in kernels.items()}}
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        roofline["traffic"] = json.load(open(tr_path)).get(dom)
+    edt_ms = st[2] + st[3]
+    edt_gbs = (nvox / 8 + 4 * nvox) / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0
+
+    # ---- extras: batched query throughput on this map (sharded over ranks, no collective)
+    extra = {"edt_hbm_gbs_survey_def": edt_gbs, "edt_ms": float(edt_ms), "wall_ms_timed_region": wall_ms}
+    if not args.no_extra:
+        occ = lambda p: gm.getInflateOccupancy(p)
+        for algo, nq in QUERY_ALGOS:
+            s, g = synth.random_queries(6 + rank, occ, c["origin"], c["size"], nq, min_dist=5.0, z_range=(0.3, 3.0))
+            pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0)
+            pl.setGridMap(gm)
+            ds, dg = torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
+            dres = torch.empty(nq * 128, dtype=torch.uint8, device=dev)
+            pl.findPaths(ds[:256], dg[:256], results=dres)  # warm-up (workspace allocation)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pl.findPaths(ds, dg, results=dres)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            t0 = time.perf_counter()
+            res, _ = pl.findPaths(s, g)  # host-facing (H2D + D2H inside)
+            ms_h = (time.perf_counter() - t0) * 1e3
+            tot = torch.tensor([ms, ms_h, float(nq), float(res["solved"].sum()), float(res["iter_num"].sum())], device=dev,
+                               dtype=torch.float64)
+            if world > 1:
+                mx = tot.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                ms, ms_h = float(mx[0]), float(mx[1])
+            extra[f"{algo}_queries_per_s"] = float(tot[2]) / (ms * 1e-3)
+            extra[f"{algo}_queries_per_s_e2e"] = float(tot[2]) / (ms_h * 1e-3)
+            extra[f"{algo}_queries"] = int(tot[2])
+            extra[f"{algo}_solved"] = int(tot[3])
+            extra[f"{algo}_expansions_per_query"] = float(tot[4]) / float(tot[2])
+            pl.close()
+
+    # ---- cpu_baseline: the oracle on this box's host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import pyoracle as po
+        nthreads = po.max_threads()
+        om = po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=(60.0, 60.0, 20.0),
+                          ground_height=c["origin"][2])
+        om.update_cloud(blob, cam, point_step=16, nthreads=nthreads)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 20):
+            om.update_cloud(blob, cam, point_step=16, nthreads=nthreads)
+            om.build_edt(d_safe=D_SAFE, nthreads=nthreads)
+            om.local_bounds()
+            reps += 1
+        cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+        t1 = time.perf_counter()
+        om.update_cloud(blob, cam, point_step=16, nthreads=1)
+        om.build_edt(d_safe=D_SAFE, nthreads=1)
+        cpu_ms_1t = (time.perf_counter() - t1) * 1e3
+        cpu = {"value": cpu_ms, "unit": "ms/frame", "cores": nthreads, "kind": "port",
+               "sample": f"{reps} full C2 frames (cloud update + EDT + cost) with {nthreads} threads; single-thread frame: {cpu_ms_1t:.0f} ms",
+               "single_thread_ms": cpu_ms_1t}
+
+    if rank == 0:
+        line = {
+            "metric": "map rebuild ms/frame", "value": ms_per_step / world, "unit": "ms/frame", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "config": {"workload": "C2: 1M-point PointCloud2 -> 512x512x128 inflated occupancy + exact squared EDT + cost field",
+                       "grid": list(gm.dims), "points": int(n_pts), "d_safe_m": D_SAFE, "l2": "flushed (256 MiB write) before every timed frame",
+                       "multi_gpu": "map replicated: every rank rebuilds its replica (value = ms/frame / n_gpus); query batches sharded, no collective"},
+            "e2e": {"value": e2e_ms / world, "unit": "ms/frame", "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": 48,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(args.steps * 3), "kernels_per_step": ["scatter_kernel", "edt_zy_kernel", "edt_x_kernel", "(+1 cudaMemsetAsync clear)"],
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,7 +97,7 @@ class OracleMap:
     def update_cloud(self, cloud, cam, point_step=None, offsets=(0, 4, 8), nthreads=1):
         cloud = np.ascontiguousarray(cloud)
         if point_step is None:
-            point_step = cloud.strides[0] if cloud.ndim == 2 else 16
+            point_step = cloud.shape[1] * cloud.itemsize if cloud.ndim == 2 else 16
         n = cloud.nbytes // point_step
         lib().orc_map_update_cloud(self.h, _ptr(cloud), n, point_step, *offsets, _d3(cam), nthreads)
 

@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 def test_edt_matches_brute_force_small(b200, po):
     rng = np.random.default_rng(0)
     for dims, dens in [((24, 20, 37), 0.01), ((16, 33, 8), 0.2), ((40, 12, 70), 0.002), ((9, 9, 9), 0.0)]:
-        size = tuple(d * 0.1 for d in dims)
+        size = tuple(d * 0.5 for d in dims)   # 0.5 is exact in binary: ceil(size/res) == dims
         grid = (rng.random(dims) < dens).astype(np.uint8)
-        gm = b200.GridMap(size, 0.1, origin=(0, 0, 0)); gm.set_inflate(grid)
-        om = po.OracleMap((0, 0, 0), size, 0.1); om.set_inflate(grid)
+        gm = b200.GridMap(size, 0.5, origin=(0, 0, 0)); gm.set_inflate(grid)
+        om = po.OracleMap((0, 0, 0), size, 0.5); om.set_inflate(grid)
         assert gm.dims == dims
         gm.build_edt()
         assert np.array_equal(gm.dist2(), om.edt_brute())
