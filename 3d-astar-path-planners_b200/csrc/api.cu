@@ -57,11 +57,16 @@ struct b200_map {
   int lb_min[3], lb_max[3];
   DevBuf cloud, stage_in, stage_out, stage_aux;
   int32_t* d_tmp;
+  uint2* d_st;
+  void* d_dz;
+  int* d_counts;
+  uint16_t* d_lut;
+  int lut_cap;
   double* d_dk;
   double d_safe;
   bool has_edt;
   bool profiling;
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[10];
   double stage_ms[8];
   long long launches;
 };
@@ -164,6 +169,11 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   if (e != cudaSuccess) { cudaFree(d.occ); cudaFree(m->d_dk); delete m; return fail(B200_ERR_NOMEM, "b200_map_create: bounds", e); }
   m->bounds_pending = false;
   m->d_tmp = nullptr;
+  m->d_st = nullptr;
+  m->d_dz = nullptr;
+  m->d_counts = nullptr;
+  m->d_lut = nullptr;
+  m->lut_cap = 0;
   m->has_edt = false;
   m->d_safe = 0;
   m->profiling = false;
@@ -183,6 +193,10 @@ int b200_map_destroy(b200_map_t* m) {
   if (m->d.dist2) cudaFree(m->d.dist2);
   if (m->d.costq) cudaFree(m->d.costq);
   if (m->d_tmp) cudaFree(m->d_tmp);
+  if (m->d_st) cudaFree(m->d_st);
+  if (m->d_dz) cudaFree(m->d_dz);
+  if (m->d_counts) cudaFree(m->d_counts);
+  if (m->d_lut) cudaFree(m->d_lut);
   cudaFree(m->d_dk);
   cudaFree(m->d_bounds);
   m->cloud.release(); m->stage_in.release(); m->stage_out.release(); m->stage_aux.release();
@@ -355,19 +369,29 @@ int b200_map_build_edt(b200_map_t* m, double d_safe) {
   REQUIRE(m, "NULL map");
   CK(cudaSetDevice(m->prm.device));
   const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
-  if (!m->d_tmp) {
-    if (cudaMalloc(&m->d_tmp, nv * 4) != cudaSuccess) { cudaGetLastError(); m->d_tmp = nullptr; return fail(B200_ERR_NOMEM, "edt scratch"); }
+  auto need = [&](void** p, size_t bytes) -> bool {
+    if (*p) return true;
+    if (cudaMalloc(p, bytes) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return false; }
+    return true;
+  };
+  const size_t max_lines = (size_t)std::max(m->N[0], m->N[1]) * m->N[2];
+  if (!need((void**)&m->d_tmp, nv * 4) || !need((void**)&m->d_st, nv * 8) || !need((void**)&m->d.dist2, nv * 4) ||
+      !need((void**)&m->d_dz, nv * (m->N[2] > 254 ? 2 : 1)) || !need((void**)&m->d_counts, max_lines * 4))
+    return fail(B200_ERR_NOMEM, "distance-field buffers");
+  int lut_n = 0;
+  if (d_safe > 0) {
+    if (!need((void**)&m->d.costq, nv * 2)) return fail(B200_ERR_NOMEM, "cost field");
+    lut_n = edt_lut_size(m->prm.resolution, d_safe);
+    if (lut_n > m->lut_cap) {
+      if (m->d_lut) cudaFree(m->d_lut);
+      m->d_lut = nullptr;
+      if (!need((void**)&m->d_lut, (size_t)lut_n * 2)) return fail(B200_ERR_NOMEM, "cost table");
+      m->lut_cap = lut_n;
+    }
   }
-  if (!m->d.dist2) {
-    if (cudaMalloc(&m->d.dist2, nv * 4) != cudaSuccess) { cudaGetLastError(); m->d.dist2 = nullptr; return fail(B200_ERR_NOMEM, "dist2 field"); }
-  }
-  if (d_safe > 0 && !m->d.costq) {
-    if (cudaMalloc(&m->d.costq, nv * 2) != cudaSuccess) { cudaGetLastError(); m->d.costq = nullptr; return fail(B200_ERR_NOMEM, "cost field"); }
-  }
-  if (m->profiling) cudaEventRecord(m->ev[3], m->stream);
-  launch_edt(m->d, m->d_tmp, m->d.dist2, m->d.costq, nullptr, d_safe, m->stream, m->profiling ? m->ev[4] : nullptr);
-  m->launches += 2;
-  if (m->profiling) cudaEventRecord(m->ev[5], m->stream);
+  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, m->stream,
+             m->profiling ? &m->ev[3] : nullptr);
+  m->launches += 5 + (lut_n > 0 ? 1 : 0);
   CK(cudaGetLastError());
   m->has_edt = true;
   m->d_safe = d_safe;
@@ -427,8 +451,8 @@ int b200_map_get_stage_ms(b200_map_t* m, double out[8]) {
   float t;
   if (cudaEventElapsedTime(&t, m->ev[0], m->ev[1]) == cudaSuccess) out[0] = t;
   if (cudaEventElapsedTime(&t, m->ev[1], m->ev[2]) == cudaSuccess) out[1] = t;
-  if (cudaEventElapsedTime(&t, m->ev[3], m->ev[4]) == cudaSuccess) out[2] = t;
-  if (cudaEventElapsedTime(&t, m->ev[4], m->ev[5]) == cudaSuccess) out[3] = t;
+  for (int i = 0; i < 5; ++i)
+    if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[2 + i] = t;
   cudaGetLastError();
   return B200_OK;
 }

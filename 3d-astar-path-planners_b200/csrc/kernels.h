@@ -18,8 +18,10 @@ void launch_los_batch(const MapDev& m, const double* s, const double* e, long lo
                       cudaStream_t st);
 
 // ---- edt_kernels.cu
-void launch_edt(const MapDev& m, int32_t* tmp, int32_t* dist2, uint16_t* costq, float* cost, double d_safe, cudaStream_t st,
-                cudaEvent_t mid);
+int edt_lut_size(double res, double d_safe);
+// ev (optional): 6 events recorded before z, scan_y, fill_y, scan_x, fill_x and after fill_x
+void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int32_t* dist2, uint16_t* costq, uint16_t* lut,
+                int lut_n, double d_safe, cudaStream_t stream, cudaEvent_t* ev);
 
 // ---- search_kernels.cu
 enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4 };
