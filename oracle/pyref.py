@@ -1,0 +1,151 @@
+"""ctypes binding of oracle/_ref/libref.so — the reference's OWN unmodified sources (AStar.cpp, ThetaStar.cpp,
+AlgorithmBase.cpp, LineOfSight.cpp, geometry_utils.cpp, grid_map.cpp, ...) compiled against the header shim in
+oracle/shim/.  TEST INFRASTRUCTURE ONLY.  Exists only where /root/reference does (this container); tests that
+need it skip elsewhere and fall back to the golden vectors generated from it (tests/golden/)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .pyoracle import RESULT_DTYPE, Result, _d3, _ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libref.so")
+_LIB = None
+
+
+def available():
+    return os.path.exists(_PATH) or os.path.isdir("/root/reference/src")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_PATH):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "CXX=g++"])
+        L = C.CDLL(_PATH)
+        vp, dp, i64 = C.c_void_p, C.POINTER(C.c_double), C.c_int64
+        L.ref_map_create.restype = vp
+        L.ref_map_create.argtypes = [dp, C.c_double, C.c_double, dp, C.c_double]
+        L.ref_map_destroy.argtypes = [vp]
+        L.ref_map_dims.argtypes = [vp, C.POINTER(C.c_int)]
+        L.ref_map_region.argtypes = [vp, dp, dp]
+        L.ref_map_update_cloud.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.ref_map_clear_box.argtypes = [vp, dp, dp]
+        L.ref_map_download_inflate.argtypes = [vp, vp]
+        L.ref_map_upload_inflate.argtypes = [vp, vp]
+        L.ref_map_local_bounds.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_map_get_inflate_occupancy.argtypes = [vp, vp, i64, vp]
+        L.ref_map_is_in_map.argtypes = [vp, vp, i64, vp]
+        L.ref_pos_to_index.argtypes = [vp, vp, i64, vp]
+        L.ref_los_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.ref_planner_create.restype = vp
+        L.ref_planner_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, vp]
+        L.ref_planner_destroy.argtypes = [vp]
+        L.ref_planner_pool_disorder.argtypes = [vp]
+        L.ref_planner_pool_disorder.restype = C.c_int
+        L.ref_planner_find_path.argtypes = [vp, dp, dp, C.POINTER(Result), vp, i64]
+        _LIB = L
+    return _LIB
+
+
+class RefMap:
+    """The reference's GridMap (initMap + odomCallback + cloudCallback); origin is always (-sx/2,-sy/2,ground_height)."""
+
+    def __init__(self, size, resolution, obstacles_inflation=0.099, local_update_range=(1e9, 1e9, 1e9), ground_height=-0.01):
+        self.h = lib().ref_map_create(_d3(size), resolution, obstacles_inflation, _d3(local_update_range), ground_height)
+        d = (C.c_int * 3)()
+        lib().ref_map_dims(self.h, d)
+        self.dims = tuple(d)
+        o, s = (C.c_double * 3)(), (C.c_double * 3)()
+        lib().ref_map_region(self.h, o, s)
+        self.origin, self.size = tuple(o), tuple(s)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_map_destroy(self.h)
+            self.h = None
+
+    def update_cloud(self, cloud, cam, point_step=None, offsets=(0, 4, 8)):
+        cloud = np.ascontiguousarray(cloud)
+        if point_step is None:
+            point_step = cloud.shape[1] * cloud.itemsize if cloud.ndim == 2 else 16
+        lib().ref_map_update_cloud(self.h, _ptr(cloud), cloud.nbytes // point_step, point_step, *offsets, _d3(cam))
+
+    def clear_box(self, mn, mx):
+        lib().ref_map_clear_box(self.h, _d3(mn), _d3(mx))
+
+    def inflate(self):
+        out = np.empty(self.dims, dtype=np.uint8)
+        lib().ref_map_download_inflate(self.h, _ptr(out))
+        return out
+
+    def set_inflate(self, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        assert grid.shape == self.dims
+        lib().ref_map_upload_inflate(self.h, _ptr(grid))
+
+    def local_bounds(self):
+        a, b = (C.c_int * 3)(), (C.c_int * 3)()
+        lib().ref_map_local_bounds(self.h, a, b)
+        return tuple(a), tuple(b)
+
+    def get_inflate_occupancy(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        lib().ref_map_get_inflate_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
+
+    def is_in_map(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.uint8)
+        lib().ref_map_is_in_map(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out.astype(bool)
+
+    def pos_to_index(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((len(pos), 3), dtype=np.int32)
+        lib().ref_pos_to_index(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
+
+    def los_batch(self, starts, ends):
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        e = np.ascontiguousarray(ends, dtype=np.float64).reshape(-1, 3)
+        vis = np.empty(len(s), dtype=np.uint8)
+        lib().ref_los_batch(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis))
+        return vis
+
+
+class RefPlanner:
+    """The reference's AStar / ThetaStar (setParam + setGridMap + init; reset + findPath per query)."""
+
+    def __init__(self, algo, rmap, resolution, lambda_heuristic=5.0, allocate_num=100000):
+        self.map = rmap
+        self.h = lib().ref_planner_create({"astar": 0, "thetastar": 1}[algo], resolution, lambda_heuristic, allocate_num, rmap.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_planner_destroy(self.h)
+            self.h = None
+
+    def pool_disorder(self):
+        """Adjacent pool nodes not in increasing address order (0 on a fresh heap). The reference's tie-break
+        is the node ADDRESS, so its results equal 'creation order' semantics only when this is 0."""
+        return lib().ref_planner_pool_disorder(self.h)
+
+    def find_path(self, start, goal, path_cap=65536):
+        r = Result()
+        path = np.empty((path_cap, 3), dtype=np.float64)
+        lib().ref_planner_find_path(self.h, _d3(start), _d3(goal), C.byref(r), _ptr(path), path_cap)
+        res = np.frombuffer(bytes(r), dtype=RESULT_DTYPE)[0]
+        return res, path[: min(r.n_path, path_cap)].copy()
+
+    def find_paths(self, starts, goals, path_cap=65536):
+        res = np.zeros(len(starts), dtype=RESULT_DTYPE)
+        paths = []
+        for i, (s, g) in enumerate(zip(starts, goals)):
+            r, p = self.find_path(s, g, path_cap)
+            res[i] = r
+            paths.append(p)
+        return res, paths

@@ -1,0 +1,47 @@
+"""CPU, only where /root/reference exists: randomised diff of the oracle (FAITHFUL) against the reference's own
+compiled sources (oracle/_ref/libref.so) on worlds other than the golden one."""
+import numpy as np
+import pytest
+
+from oracle import pyref as pr
+
+pytestmark = pytest.mark.skipif(not pr.available(), reason="/root/reference not present (GPU box): golden vectors cover this")
+
+
+@pytest.mark.parametrize("seed,size,res,infl", [(101, (25.6, 25.6, 6.4), 0.1, 0.099), (102, (20.0, 16.0, 6.0), 0.2, 0.099),
+                                                  (103, (12.8, 12.8, 3.2), 0.1, 0.25)])
+def test_map_los_and_planners_match_reference(po, synth, seed, size, res, infl):
+    gh = -0.01
+    origin = (-size[0] / 2, -size[1] / 2, gh)
+    cloud = synth.pack_cloud(np.concatenate([synth.forest(seed, origin, size, res, 30),
+                                             synth.uniform_cloud(seed + 1, origin, size, 2000, margin=0.5)]))
+    rm = pr.RefMap(size, res, infl, (1e3, 1e3, 1e3), gh)
+    om = po.OracleMap(origin, size, res, infl, (1e3, 1e3, 1e3), gh)
+    assert rm.dims == om.dims and np.allclose(rm.origin, origin)
+    rm.update_cloud(cloud, (0.3, -0.2, 1.0))
+    om.update_cloud(cloud, (0.3, -0.2, 1.0))
+    assert np.array_equal(rm.inflate(), om.inflate())
+    assert rm.local_bounds() == om.local_bounds()
+    s, g = synth.random_queries(seed + 2, om.get_inflate_occupancy, origin, size, 40, min_dist=3.0)
+    assert np.array_equal(rm.los_batch(s, g), om.los_batch(s, g))
+    for algo in ("astar", "thetastar"):
+        rr, rpaths = pr.RefPlanner(algo, rm, res, 5.0, 100000).find_paths(s, g)
+        ro, pth = po.OraclePlanner(algo, om, res, 5.0, 100000, mode=po.FAITHFUL).find_paths(s, g, path_stride=8192, nthreads=4)
+        for f in ("solved", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length", "goal_coords"):
+            assert np.array_equal(rr[f], ro[f]), (algo, f)
+        for i in range(len(s)):
+            assert np.array_equal(pth[i * 8192: i * 8192 + ro["n_path"][i]], rpaths[i]), (algo, i)
+
+
+def test_clear_box_matches_reference(po, synth):
+    size, res = (12.8, 12.8, 3.2), 0.1
+    origin = (-6.4, -6.4, -0.01)
+    rm = pr.RefMap(size, res)
+    om = po.OracleMap(origin, size, res)
+    grid = (np.random.default_rng(1).random(om.dims) < 0.2).astype(np.uint8)
+    rm.set_inflate(grid)
+    om.set_inflate(grid)
+    for mn, mx in [((-3.05, -2.0, 0.33), (4.0, 1.0, 2.71)), ((-100, -100, -100), (0, 0, 0)), ((5, 5, 2), (4, 4, 1))]:
+        rm.clear_box(mn, mx)
+        om.clear_box(mn, mx)
+        assert np.array_equal(rm.inflate(), om.inflate())
