@@ -20,7 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200planner.so")
 
 ALGORITHMS = ("astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar")
-STATUS_NAMES = {0: "solved", 1: "open_set_empty", 2: "pool_exhausted", 3: "tier_overflow"}
+STATUS_NAMES = {0: "solved", 1: "open_set_empty", 2: "pool_exhausted", 3: "tier_overflow", 4: "open_list_full"}
+SEMANTICS = {"default": 0, "canonical": 1, "faithful": 2}
 
 
 class B200Error(RuntimeError):
@@ -35,10 +36,10 @@ class MapParams(C.Structure):
 
 class PlannerParams(C.Structure):
     _fields_ = [("resolution", C.c_double), ("lambda_heuristic", C.c_double), ("allocate_num", C.c_int32),
-                ("reserved", C.c_int32), ("cost_weight", C.c_double), ("max_los", C.c_double)]
+                ("semantics", C.c_int32), ("cost_weight", C.c_double), ("max_los", C.c_double)]
 
 
-RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("pad", "i4"), ("path_offset", "i8"),
+RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("open_peak", "i4"), ("path_offset", "i8"),
                          ("g_final", "f8"), ("path_length", "f8"), ("explored_nodes", "i8"), ("iter_num", "i8"),
                          ("los_checks", "i8"), ("los_samples", "i8"), ("goal_coords", "f8", 3),
                          ("start_coords", "f8", 3), ("time_us", "f8")])
@@ -288,8 +289,11 @@ class Planner:
     detectCollision / findPath / getPath, plus the batched `findPaths`."""
 
     def __init__(self, algorithm="astar", resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0,
-                 max_los=0.0):
-        p = PlannerParams(float(resolution), float(lambda_heuristic), int(allocate_num), 0, float(cost_weight), float(max_los))
+                 max_los=0.0, semantics="default"):
+        """semantics: "faithful" (bit-identical to the reference's std::set behaviour; astar/thetastar only),
+        "canonical" (exact priority queue, faster), "default" (faithful where the reference has the algorithm)."""
+        p = PlannerParams(float(resolution), float(lambda_heuristic), int(allocate_num), SEMANTICS[semantics],
+                          float(cost_weight), float(max_los))
         self.h = C.c_void_p()
         _ck(lib().b200_planner_create(algorithm.encode(), C.byref(p), C.byref(self.h)))
         self.algorithm = algorithm if algorithm in ALGORITHMS else "astar"

@@ -496,6 +496,8 @@ extern "C" int b200_map_download_cost(b200_map_t* m, float* dst) {
 struct Tier {
   int cap = 0;
   int slots = 0;
+  int factor = 0;
+  uint32_t open_entries = 0;
   uint32_t hcap = 0;
   void* base = nullptr;
   NodeRec* nodes = nullptr;
@@ -505,6 +507,7 @@ struct Tier {
 
 struct b200_planner {
   int algo;
+  int faithful;
   std::string name;
   b200_planner_params_t prm;
   b200_map* map;
@@ -518,20 +521,21 @@ static void tier_free(Tier& t) {
   if (t.base) cudaFree(t.base);
   t = Tier();
 }
-static int tier_alloc(Tier& t, int cap, int slots) {
-  if (t.base && t.cap == cap && t.slots == slots) return 0;
+static int tier_alloc(Tier& t, int cap, int slots, int factor) {
+  if (t.base && t.cap == cap && t.slots == slots && t.factor == factor) return 0;
   tier_free(t);
   uint32_t hcap;
-  search_slot_bytes(cap, &hcap);
+  search_slot_bytes(cap, factor, &hcap);
   const size_t nb = (size_t)slots * cap * sizeof(NodeRec);
   const size_t hb = (size_t)slots * hcap * 4;
-  const size_t pb = (size_t)slots * ((size_t)cap + 32) * sizeof(HeapEnt);
+  const size_t pb = (size_t)slots * open_region_entries(cap, factor) * sizeof(HeapEnt);
   if (cudaMalloc(&t.base, nb + hb + pb) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return -1; }
   t.nodes = (NodeRec*)t.base;
   t.heap = (HeapEnt*)((char*)t.base + nb);
   t.hash = (uint32_t*)((char*)t.base + nb + pb);
   cudaMemset(t.hash, 0, hb);
-  t.cap = cap; t.slots = slots; t.hcap = hcap;
+  t.cap = cap; t.slots = slots; t.hcap = hcap; t.factor = factor;
+  t.open_entries = (uint32_t)open_region_entries(cap, factor);
   return 0;
 }
 
@@ -550,6 +554,18 @@ int b200_planner_create(const char* algorithm, const b200_planner_params_t* p, b
   else pl->algo = ALGO_ASTAR;
   pl->name = pl->algo == ALGO_ASTAR ? "astar" : a;
   pl->prm = *p;
+  // semantics: the two algorithms the reference implements default to its exact (rb-tree) behaviour
+  const bool has_reference = pl->algo == ALGO_ASTAR || pl->algo == ALGO_THETASTAR;
+  if (p->semantics == B200_SEMANTICS_FAITHFUL && !has_reference) {
+    delete pl;
+    return fail(B200_ERR_UNSUPPORTED, "b200_planner_create: faithful semantics exist only for astar / thetastar");
+  }
+  if (p->semantics < 0 || p->semantics > 2) { delete pl; return fail(B200_ERR_INVALID, "b200_planner_create: bad semantics"); }
+  if (p->semantics == B200_SEMANTICS_FAITHFUL && p->max_los > 0) {
+    delete pl;
+    return fail(B200_ERR_UNSUPPORTED, "b200_planner_create: max_los is an extension of the canonical semantics");
+  }
+  pl->faithful = has_reference && p->semantics != B200_SEMANTICS_CANONICAL && !(p->max_los > 0);
   pl->map = nullptr;
   pl->last_launches = 0;
   // the neighbour offsets exactly as `for (double dx = -r; dx <= r + 1e-3; dx += r)` produces them (AStar.cpp:131)
@@ -617,7 +633,8 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   int slots0 = m->sm_count * per_sm;
   if ((int64_t)slots0 > nq) slots0 = (int)nq;
   const int cap0 = std::min(pl->prm.allocate_num, 16384);
-  if (tier_alloc(pl->tier[0], cap0, std::max(slots0, pl->tier[0].cap == cap0 ? pl->tier[0].slots : 0)))
+  const int factor = open_region_factor(pl->algo, pl->faithful);
+  if (tier_alloc(pl->tier[0], cap0, std::max(slots0, pl->tier[0].cap == cap0 ? pl->tier[0].slots : 0), factor))
     return fail(B200_ERR_NOMEM, "search workspace (tier 0)");
 
   const double* d_starts = starts;
@@ -654,11 +671,12 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   for (int i = 0; i < 3; ++i) P.dv[i] = pl->dv[i];
   P.allocate_num = pl->prm.allocate_num;
   P.algo = pl->algo;
+  P.faithful = pl->faithful;
   P.starts = d_starts; P.goals = d_goals; P.qlist = nullptr; P.nq = nq;
   P.results = d_res; P.path_pool = d_path; P.path_cap = path_cap; P.path_cursor = path_cursor;
   P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;
   const Tier& t0 = pl->tier[0];
-  P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap;
+  P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap; P.open_entries = t0.open_entries;
   launch_search(P, std::min<int64_t>(t0.slots, nq), st);
   pl->last_launches++;
   CK(cudaGetLastError());
@@ -671,16 +689,16 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
       size_t free_b = 0, total_b = 0;
       CK(cudaMemGetInfo(&free_b, &total_b));
       uint32_t hc;
-      const size_t slot_b = search_slot_bytes(pl->prm.allocate_num, &hc);
+      const size_t slot_b = search_slot_bytes(pl->prm.allocate_num, factor, &hc);
       size_t budget = pl->tier[1].base ? (size_t)pl->tier[1].slots * slot_b : free_b / 2;
       int slots1 = (int)std::min<size_t>({(size_t)n_over, (size_t)m->sm_count * (tpb == 32 ? 4 : 2), std::max<size_t>(1, budget / slot_b)});
       if (pl->tier[1].base && pl->tier[1].cap == pl->prm.allocate_num && pl->tier[1].slots >= slots1) slots1 = pl->tier[1].slots;
-      if (tier_alloc(pl->tier[1], pl->prm.allocate_num, slots1)) return fail(B200_ERR_NOMEM, "search workspace (tier 1)");
+      if (tier_alloc(pl->tier[1], pl->prm.allocate_num, slots1, factor)) return fail(B200_ERR_NOMEM, "search workspace (tier 1)");
       CK(cudaMemsetAsync(q_counter, 0, 8, st));
       const Tier& t1 = pl->tier[1];
       P.qlist = overflow_list; P.nq = n_over;
       P.overflow_list = nullptr; P.overflow_count = overflow_count;
-      P.nodes = t1.nodes; P.hash = t1.hash; P.heap = t1.heap; P.cap = t1.cap; P.hcap = t1.hcap;
+      P.nodes = t1.nodes; P.hash = t1.hash; P.heap = t1.heap; P.cap = t1.cap; P.hcap = t1.hcap; P.open_entries = t1.open_entries;
       launch_search(P, std::min(t1.slots, n_over), st);
       pl->last_launches++;
       CK(cudaGetLastError());

@@ -25,12 +25,13 @@ void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* coun
 
 // ---- search_kernels.cu
 enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4 };
-enum { ST_SOLVED = 0, ST_OPEN_EMPTY = 1, ST_POOL_EXHAUSTED = 2, ST_TIER_OVERFLOW = 3 };
+enum { ST_SOLVED = 0, ST_OPEN_EMPTY = 1, ST_POOL_EXHAUSTED = 2, ST_TIER_OVERFLOW = 3, ST_OPEN_LIST_FULL = 4 };
 
 // Per-slot search workspace in HBM (one slot per resident thread block; SoA of slots, AoS inside):
 //   nodes  NodeRec [cap]      64 B records, index = creation order (the reference's pool index / tie-break)
 //   hash   uint32  [hcap]     open addressing on the exact 3xFP64 key -> node index + 1
-//   heap   HeapEnt [cap+32]   32-ary min-heap on (f, creation index); children of k are one aligned 512 B row
+//   heap   HeapEnt [2cap+32]  canonical: 32-ary min-heap on (f, creation index), children of k are one aligned 512 B row;
+//                             faithful: the red-black tree nodes of rbtree.cuh (16 B each, duplicates possible)
 struct __align__(16) NodeRec {
   double px, py, pz;
   double g, f;
@@ -54,6 +55,7 @@ struct SearchParams {
   double dv[3];
   int allocate_num;
   int algo;
+  int faithful;  // 1: reference-identical open list (astar / thetastar only)
   const double* starts;
   const double* goals;
   const int* qlist;  // optional indirection (second-tier pass)
@@ -69,10 +71,16 @@ struct SearchParams {
   uint32_t* hash;
   HeapEnt* heap;
   int cap;        // physical nodes per slot
+  uint32_t open_entries;  // 16-byte open-list entries per slot (heap / red-black tree nodes)
   uint32_t hcap;  // hash entries per slot (power of two >= 2*cap)
 };
 
-size_t search_slot_bytes(int cap, uint32_t* hcap_out);
+// Open-list region of a slot, in 16-byte entries.  The canonical heap needs cap + 32.  The faithful red-black
+// tree holds DUPLICATES of a node (AStar.cpp:71-72 inserts without erasing): measured peak |open| / nodes is
+// <= 1.0 for thetastar and up to 4.4 for astar at lambda = 1 (oracle, C3 map), hence 8x for faithful astar.
+inline int open_region_factor(int algo, int faithful) { return (faithful && algo == 0) ? 8 : 2; }
+inline size_t open_region_entries(int cap, int factor) { return (size_t)factor * (size_t)cap + 32; }
+size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out);
 int search_threads_per_block(int algo);
 void launch_search(const SearchParams& p, int slots, cudaStream_t st);
 

@@ -19,6 +19,7 @@
 //     warp-per-segment, lanes = consecutive 0.05 m samples, __ballot_sync early-out (common.cuh).
 //   * FP64 everywhere positions are touched (voxel registration is rounding-dependent).
 #include "kernels.h"
+#include "rbtree.cuh"
 
 namespace b200 {
 
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
   Slot s;
   s.nodes = P.nodes + (size_t)blockIdx.x * P.cap;
   s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
-  s.heap = P.heap + (size_t)blockIdx.x * ((size_t)P.cap + 32);
+  s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
   s.hmask = P.hcap - 1;
 
   // neighbour offset of this lane: L = 9a + 3b + c <-> (dx,dy,dz) = (dv[a],dv[b],dv[c])  (AStar.cpp:131-133)
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
     s.heap_n = 0;
     s.use = 1;
     long long iter_num = 0, los_checks = 0, los_samples = 0;
-    int status = ST_OPEN_EMPTY, last = 0, term = -1;
+    int status = ST_OPEN_EMPTY, last = 0, term = -1, open_peak = 1;
     if (warp == 0) {
       if (lane == 0) {
         NodeRec n;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
         if (s.heap_n == 0) {  // AStar.cpp:175-178
           status = ST_OPEN_EMPTY; last = cur; done = true;
         } else {
+          open_peak = max(open_peak, s.heap_n);
           cur = (int)heap_pop(s, lane);
           NodeRec c = s.nodes[cur];
           if (IS_LAZY && c.parent >= 0 && c.parent != c.via) {
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
         r.solved = status == ST_SOLVED ? 1 : 0;
         r.status = status;
         r.n_path = n_path;
-        r.pad = 0;
+        r.open_peak = open_peak;
         r.path_offset = off;
         r.g_final = ln.g;
         r.path_length = (double)plen;
@@ -510,16 +512,315 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
   }
 }
 
-size_t search_slot_bytes(int cap, uint32_t* hcap_out) {
+// ===================================================================================================
+// FAITHFUL semantics (astar, thetastar): bit-identical to the reference's own code — open list = the same
+// red-black tree std::set builds (rbtree.cuh) with keys mutated in place, A* overwrites parent/g/f
+// unconditionally (AStar.cpp:56-63), Theta* erases by the already-mutated key (ThetaStar.cpp:80-83), pops
+// do not test the closed flag (AStar.cpp:105-122).  The per-neighbour arithmetic (isInMap, hash probe,
+// occupancy, fastLOS, candidate g/f) is still done warp-/block-parallel; only the part whose ORDER the
+// reference's result depends on — node writes interleaved with tree operations — is replayed sequentially
+// by lane 0 in the reference's dx->dy->dz order.
+// ===================================================================================================
+struct FShared {
+  int nb_idx[27];
+  int new_parent[27];
+  int flags[27];  // bit0 reaches UpdateVertex, bit1 write node, bit2 improved (g < old g), bit3 was IN_OPEN_SET
+  double new_g[27], new_f[27];
+};
+
+template <int ALGO, int NW>
+__global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchParams P) {
+  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR;
+  __shared__ Shared sh;
+  __shared__ FShared fs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MapDev& m = P.map;
+  Slot s;
+  s.nodes = P.nodes + (size_t)blockIdx.x * P.cap;
+  s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
+  s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
+  s.hmask = P.hcap - 1;
+  RbSet set;  // lane 0 of warp 0 owns the tree; the other lanes only see what it broadcasts
+
+  const int la = lane / 9, lb = (lane / 3) % 3, lc = lane % 3;
+  const double ddx = P.dv[la % 3], ddy = P.dv[lb], ddz = P.dv[lc];
+  const double dnorm = norm3(ddx, ddy, ddz);
+  const bool lane_nb = lane < 27 && !(dnorm < 1e-3);
+
+  for (;;) {
+    if (tid == 0) sh.q = (long long)atomicAdd(P.q_counter, 1ULL);
+    __syncthreads();
+    const long long qi = sh.q;
+    if (qi >= P.nq) break;
+    const long long q = P.qlist ? (long long)P.qlist[qi] : qi;
+    const double sx = P.starts[3 * q], sy = P.starts[3 * q + 1], sz = P.starts[3 * q + 2];
+    const double gx = P.goals[3 * q], gy = P.goals[3 * q + 1], gz = P.goals[3 * q + 2];
+    unsigned long long t_begin = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
+
+    s.use = 1;
+    long long iter_num = 0, los_checks = 0, los_samples = 0;
+    int status = ST_OPEN_EMPTY, last = 0, term = -1, open_peak = 1;
+    if (warp == 0) {
+      if (lane == 0) {  // AStar.cpp:87-97
+        NodeRec n;
+        n.px = sx; n.py = sy; n.pz = sz;
+        n.g = 0.0;
+        n.f = dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, sx), dsub(gy, sy), dsub(gz, sz))));
+        n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
+        n.slot = hash_insert(s, sx, sy, sz, 0);
+        s.nodes[0] = n;
+        set.init(reinterpret_cast<TreeNode*>(s.heap), s.nodes, P.open_entries);
+        set.insert(0u);
+      }
+      __syncwarp();
+      sh.state = 0;
+    }
+
+    int cur = 0;
+    double cx = 0, cy = 0, cz = 0, cg = 0;
+    int cpar = -1;
+    int nb_idx = -1;
+    double nx = 0, ny = 0, nz = 0;
+    for (;;) {
+      bool valid = false;
+      bool oom = false;
+      if (warp == 0) {
+        bool done = false;
+        int popped = -1;
+        if (lane == 0 && !set.empty()) {
+          open_peak = max(open_peak, (int)set.count);
+          popped = (int)set.pop_begin();  // AStar.cpp:105-106 (no closed test)
+        }
+        popped = __shfl_sync(0xffffffffu, popped, 0);
+        if (popped < 0) {  // AStar.cpp:175-178
+          status = ST_OPEN_EMPTY; last = cur; done = true;
+        } else {
+          cur = popped;
+          const NodeRec c = s.nodes[cur];
+          cx = c.px; cy = c.py; cz = c.pz; cg = c.g; cpar = c.parent;
+          if (fabs(dsub(cx, gx)) <= P.r && fabs(dsub(cy, gy)) <= P.r && fabs(dsub(cz, gz)) <= P.r) {  // :110-119
+            status = ST_SOLVED; last = cur; term = cur; done = true;
+          }
+        }
+        if (!done) {
+          if (lane == 0) s.nodes[cur].state = (s.nodes[cur].state & ~0xff) | NODE_CLOSED;  // :122
+          ++iter_num;
+          __syncwarp();
+          nb_idx = -1;
+          valid = lane_nb;
+          nx = dadd(cx, ddx); ny = dadd(cy, ddy); nz = dadd(cz, ddz);
+          if (valid && !is_in_map(m, nx, ny, nz)) valid = false;
+          if (valid) {
+            nb_idx = hash_find(s, nx, ny, nz);
+            if (nb_idx >= 0 && (s.nodes[nb_idx].state & 0xff) == NODE_CLOSED) valid = false;
+          }
+          if (valid && inflate_occ(m, nx, ny, nz) == 1) valid = false;
+          const bool need = valid && nb_idx < 0;
+          const unsigned cm = __ballot_sync(0xffffffffu, need);
+          const int ncreate = __popc(cm);
+          const int rank = __popc(cm & ((1u << lane) - 1u));
+          bool overflow = false;
+          int fail_lane = 32;
+          if (ncreate > 0) {
+            if (P.cap < P.allocate_num && s.use + ncreate > P.cap) overflow = true;
+            else if (s.use + ncreate >= P.allocate_num) {
+              const int fail_rank = P.allocate_num - s.use - 1;
+              fail_lane = __ffs(__ballot_sync(0xffffffffu, need && rank == fail_rank)) - 1;
+              oom = true;
+            }
+          }
+          if (overflow) {
+            status = ST_TIER_OVERFLOW; last = cur; done = true;
+          } else {
+            if (need && lane <= fail_lane && s.use + rank < P.cap) {
+              const int ni = s.use + rank;
+              NodeRec n;
+              n.px = nx; n.py = ny; n.pz = nz;
+              n.g = __longlong_as_double(0x7ff0000000000000LL);
+              n.f = n.g;  // the reference leaves f stale here; it is always overwritten before its first use as a key
+              n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_NEW; n.pad = 0;
+              n.slot = hash_insert(s, nx, ny, nz, ni);
+              s.nodes[ni] = n;
+              nb_idx = ni;
+            }
+            if (oom) {
+              if (lane >= fail_lane) valid = false;
+              s.use = min(P.allocate_num, P.cap);
+              status = ST_POOL_EXHAUSTED; last = cur;
+            } else s.use += ncreate;
+            __syncwarp();
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (IS_THETA) {
+              const bool lp = cpar >= 0 && vm != 0;
+              if (lp) {
+                los_checks += __popc(vm);
+                if (lane < 27) { sh.nbx[lane] = nx; sh.nby[lane] = ny; sh.nbz[lane] = nz; }
+                if (lane == 0) {
+                  const NodeRec pr = s.nodes[cpar];
+                  sh.ppx = pr.px; sh.ppy = pr.py; sh.ppz = pr.pz;
+                  sh.valid = vm;
+                }
+              }
+              if (lane == 0) sh.los_phase = lp ? 1 : 0;
+            }
+          }
+        }
+        if (lane == 0) sh.state = done ? 1 : 0;
+        if (done) valid = false;
+      }
+      if (NW > 1) __syncthreads(); else __syncwarp();
+      if (sh.state == 1) break;
+
+      if (IS_THETA && sh.los_phase) {
+        const unsigned vm = sh.valid;
+        const double ppx = sh.ppx, ppy = sh.ppy, ppz = sh.ppz;
+        for (int seg = warp; seg < 27; seg += NW) {
+          if (!((vm >> seg) & 1u)) continue;
+          int ns = 0;
+          const bool vis = los_warp<false>(m, ppx, ppy, ppz, sh.nbx[seg], sh.nby[seg], sh.nbz[seg], lane, &ns, nullptr);
+          if (lane == 0) { sh.vis[seg] = vis ? 1 : 0; sh.nsamp[seg] = ns; }
+        }
+        if (NW > 1) __syncthreads(); else __syncwarp();
+      }
+
+      if (warp == 0) {
+        // ---- candidates, one lane per neighbour (pure functions of cur / parent(cur) / the neighbour's own record)
+        int flags = 0, new_parent = cur;
+        double new_g = 0, new_f = 0;
+        if (valid) {
+          const NodeRec nb = s.nodes[nb_idx];
+          flags = 1 | (((nb.state & 0xff) == NODE_OPEN) ? 8 : 0);
+          bool use_parent = false;
+          if (IS_THETA && cpar >= 0) {
+            los_samples += sh.nsamp[lane];
+            use_parent = sh.vis[lane] != 0;
+          }
+          if (IS_THETA && use_parent) {
+            const NodeRec pr = s.nodes[cpar];
+            new_g = dadd(pr.g, norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz)));
+            new_parent = cpar;
+          } else {
+            new_g = dadd(cg, dnorm);
+          }
+          new_f = dadd(new_g, dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, nx), dsub(gy, ny), dsub(gz, nz)))));
+          const bool better = new_g < nb.g;
+          if (IS_THETA) { if (better) flags |= 2 | 4; }   // ThetaStar.cpp: guarded write; improved iff written
+          else { flags |= 2; if (better) flags |= 4; }    // AStar.cpp:60-62: unconditional write; :70 guards the insert
+        }
+        if (lane < 27) {
+          fs.nb_idx[lane] = nb_idx; fs.new_parent[lane] = new_parent; fs.flags[lane] = flags;
+          fs.new_g[lane] = new_g; fs.new_f[lane] = new_f;
+        }
+        __syncwarp();
+        // ---- sequential replay in the reference's neighbour order (lane 0 owns the tree)
+        if (lane == 0) {
+          for (int k = 0; k < 27; ++k) {
+            const int fl = fs.flags[k];
+            if (!(fl & 1)) continue;
+            NodeRec* w = s.nodes + fs.nb_idx[k];
+            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; }
+            if (fl & 4) {
+              if (IS_THETA && (fl & 8)) set.erase_key((uint32_t)fs.nb_idx[k]);  // ThetaStar.cpp:80 (key already mutated)
+              w->state = NODE_OPEN | (k << 8);
+              set.insert((uint32_t)fs.nb_idx[k]);                                 // AStar.cpp:71-76 / ThetaStar.cpp:81-86
+            }
+          }
+        }
+        const int ovf = __shfl_sync(0xffffffffu, set.overflow ? 1 : 0, 0);
+        if (ovf) { status = P.cap < P.allocate_num ? ST_TIER_OVERFLOW : ST_OPEN_LIST_FULL; last = cur; }
+        if (lane == 0 && (ovf || status == ST_POOL_EXHAUSTED)) sh.state = 1;
+      }
+      if (NW > 1) __syncthreads(); else __syncwarp();
+      if (sh.state == 1) break;
+    }
+
+    // ---------------- result (same as the canonical kernel) ----------------
+    if (warp == 0) {
+      if (IS_THETA) {
+        long long v = los_samples;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        los_samples = v;
+      }
+      int n_path = 0;
+      long long off = -1;
+      float plen = 0.f;
+      int* chain = reinterpret_cast<int*>(s.heap);
+      float* seglen = reinterpret_cast<float*>(s.heap) + (size_t)P.cap + 8;
+      if (status == ST_SOLVED) {
+        if (lane == 0) {
+          int c = term;
+          while (c >= 0) { chain[n_path++] = c; c = s.nodes[c].parent; }
+          if (P.path_pool) {
+            const unsigned long long o = atomicAdd(P.path_cursor, (unsigned long long)n_path);
+            off = (o + (unsigned long long)n_path <= (unsigned long long)P.path_cap) ? (long long)o : -1;
+          }
+        }
+        n_path = __shfl_sync(0xffffffffu, n_path, 0);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        __syncwarp();
+        for (int i = lane; i < n_path; i += 32) {
+          const NodeRec a = s.nodes[chain[n_path - 1 - i]];
+          if (off >= 0) {
+            P.path_pool[3 * (off + i)] = a.px; P.path_pool[3 * (off + i) + 1] = a.py; P.path_pool[3 * (off + i) + 2] = a.pz;
+          }
+          if (i > 0) {
+            const NodeRec b = s.nodes[chain[n_path - i]];
+            const double ux = dmul(dsub(a.px, b.px), m.res), uy = dmul(dsub(a.py, b.py), m.res), uz = dmul(dsub(a.pz, b.pz), m.res);
+            seglen[i] = __fsqrt_rn((float)dadd(dadd(dmul(ux, ux), dmul(uy, uy)), dmul(uz, uz)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int i = 1; i < n_path; ++i) plen = __fadd_rn(plen, seglen[i]);
+      }
+      if (lane == 0) {
+        b200_path_result_t r;
+        const NodeRec ln = s.nodes[last];
+        r.solved = status == ST_SOLVED ? 1 : 0;
+        r.status = status;
+        r.n_path = n_path;
+        r.open_peak = open_peak;
+        r.path_offset = off;
+        r.g_final = ln.g;
+        r.path_length = (double)plen;
+        r.explored_nodes = s.use;
+        r.iter_num = iter_num;
+        r.los_checks = los_checks;
+        r.los_samples = los_samples;
+        r.goal_coords[0] = ln.px; r.goal_coords[1] = ln.py; r.goal_coords[2] = ln.pz;
+        r.start_coords[0] = sx; r.start_coords[1] = sy; r.start_coords[2] = sz;
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        r.time_us = (double)(t_end - t_begin) * 1e-3;
+        P.results[q] = r;
+        if (status == ST_TIER_OVERFLOW && P.overflow_list) P.overflow_list[atomicAdd(P.overflow_count, 1)] = (int)q;
+      }
+      sh.state = s.use;
+    }
+    __syncthreads();
+    const int used = min(sh.state, P.cap);
+    for (int i = tid; i < used; i += NW * 32) s.hash[s.nodes[i].slot] = 0u;
+    __syncthreads();
+  }
+}
+
+size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out) {
   uint32_t h = 1024;
   while (h < 2u * (uint32_t)cap) h <<= 1;
   if (hcap_out) *hcap_out = h;
-  return (size_t)cap * sizeof(NodeRec) + (size_t)h * 4 + ((size_t)cap + 32) * sizeof(HeapEnt);
+  return (size_t)cap * sizeof(NodeRec) + (size_t)h * 4 + open_region_entries(cap, open_factor) * sizeof(HeapEnt);
 }
 
 int search_threads_per_block(int algo) { return algo == ALGO_THETASTAR ? 128 : 32; }
 
 void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
+  if (p.faithful) {
+    if (p.algo == ALGO_THETASTAR) search_faithful_kernel<ALGO_THETASTAR, 4><<<slots, 128, 0, st>>>(p);
+    else search_faithful_kernel<ALGO_ASTAR, 1><<<slots, 32, 0, st>>>(p);
+    return;
+  }
   switch (p.algo) {
     case ALGO_ASTAR: search_kernel<ALGO_ASTAR, 1><<<slots, 32, 0, st>>>(p); break;
     case ALGO_THETASTAR: search_kernel<ALGO_THETASTAR, 4><<<slots, 128, 0, st>>>(p); break;

@@ -124,11 +124,20 @@ int b200_map_get_stage_ms(b200_map_t* map, double out_ms[8]);
 
 /* ROS params of AStar::setParam / ThetaStar::setParam (src/Planners/AStar.cpp:31-41, ThetaStar.cpp:25-35)
  * + AlgorithmBase::setCostFactor (AlgorithmBase.hpp:39) + GetPath.srv:26 max_los. */
+/* Open-list semantics (DESIGN.md "Search semantics").
+ *  FAITHFUL : bit-identical to the reference's own code — the open list is the red-black tree std::set builds,
+ *             with keys mutated in place, A*'s unconditional overwrite and Theta*'s erase-by-mutated-key
+ *             (AStar.cpp:56-78, ThetaStar.cpp:72-89, utils.hpp:52-61).  astar / thetastar only.
+ *  CANONICAL: exact priority queue on (f, creation index), true decrease-key, guarded relaxations — the clean
+ *             semantics of SURVEY Appendix B; several times faster; the only one for the extension algorithms.
+ *  DEFAULT  : FAITHFUL for astar / thetastar, CANONICAL otherwise. */
+enum { B200_SEMANTICS_DEFAULT = 0, B200_SEMANTICS_CANONICAL = 1, B200_SEMANTICS_FAITHFUL = 2 };
+
 typedef struct {
   double resolution;        /* <algo>/resolution */
   double lambda_heuristic;  /* <algo>/lambda_heuristic */
   int32_t allocate_num;     /* <algo>/allocate_num: node budget per query */
-  int32_t reserved;
+  int32_t semantics;        /* B200_SEMANTICS_* */
   double cost_weight;       /* cost-aware variants only */
   double max_los;           /* <= 0: unlimited */
 } b200_planner_params_t;
@@ -136,9 +145,10 @@ typedef struct {
 /* AlgorithmBase::createResultDataObject (src/Planners/AlgorithmBase.cpp:123-175) as a plain struct. */
 typedef struct {
   int32_t solved;           /* "solved" */
-  int32_t status;           /* 0 solved, 1 open set empty (AStar.cpp:175-178), 2 pool exhausted (:165-168) */
+  int32_t status;           /* 0 solved, 1 open set empty (AStar.cpp:175-178), 2 pool exhausted (:165-168),
+                               4 open-list workspace exhausted (faithful mode only; never seen in practice) */
   int32_t n_path;           /* path.size() */
-  int32_t pad;
+  int32_t open_peak;        /* largest open-list size at a pop (extra counter) */
   int64_t path_offset;      /* first point of this path inside the caller's path buffer (in points) */
   double g_final;           /* "g_final_node" */
   double path_length;       /* "path_length" (float accumulation, geometry_utils.cpp:10-20) */

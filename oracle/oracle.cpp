@@ -362,7 +362,7 @@ struct Result {  // mirrors b200_path_result_t (include/b200_planner.h)
   int32_t solved;
   int32_t status;  // 0 ok, 1 open set empty, 2 pool exhausted
   int32_t n_path;
-  int32_t pad;
+  int32_t open_peak;  // largest open-list size seen (diagnostic; sizes the GPU workspace)
   int64_t path_offset;
   double g_final;
   double path_length;
@@ -601,9 +601,11 @@ struct Planner {
 
     Node* cur = nullptr;
     Node* last = nullptr;
+    size_t open_peak = 1;
     bool solved = false;
     int status = 1;
     while (!open_empty()) {  // :103
+      open_peak = std::max(open_peak, mode == FAITHFUL ? open_faithful.size() : open_canon.size());
       cur = open_pop();      // :105-106
       if (is_lazy()) set_vertex(cur, target, dvals);
       bool reach_end = std::abs(cur->position.x - target.x) <= res && std::abs(cur->position.y - target.y) <= res &&
@@ -653,6 +655,7 @@ struct Planner {
     // createResultDataObject AlgorithmBase.cpp:123-175
     r->solved = solved;
     r->status = status;
+    r->open_peak = (int32_t)std::min<size_t>(open_peak, 0x7fffffff);
     r->explored_nodes = use_node_num;
     r->iter_num = iter_num;
     r->los_checks = los_checks;

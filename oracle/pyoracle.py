@@ -15,14 +15,14 @@ FAITHFUL, CANONICAL = 0, 1
 
 
 class Result(C.Structure):
-    _fields_ = [("solved", C.c_int32), ("status", C.c_int32), ("n_path", C.c_int32), ("pad", C.c_int32),
+    _fields_ = [("solved", C.c_int32), ("status", C.c_int32), ("n_path", C.c_int32), ("open_peak", C.c_int32),
                 ("path_offset", C.c_int64), ("g_final", C.c_double), ("path_length", C.c_double),
                 ("explored_nodes", C.c_int64), ("iter_num", C.c_int64), ("los_checks", C.c_int64),
                 ("los_samples", C.c_int64), ("goal_coords", C.c_double * 3), ("start_coords", C.c_double * 3),
                 ("time_us", C.c_double)]
 
 
-RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("pad", "i4"), ("path_offset", "i8"),
+RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("open_peak", "i4"), ("path_offset", "i8"),
                          ("g_final", "f8"), ("path_length", "f8"), ("explored_nodes", "i8"), ("iter_num", "i8"),
                          ("los_checks", "i8"), ("los_samples", "i8"), ("goal_coords", "f8", 3),
                          ("start_coords", "f8", 3), ("time_us", "f8")])

@@ -38,7 +38,7 @@
 
 namespace {
 struct Result {  // same layout as oracle.cpp's Result / b200_path_result_t
-  int32_t solved, status, n_path, pad;
+  int32_t solved, status, n_path, open_peak;
   int64_t path_offset;
   double g_final, path_length;
   int64_t explored_nodes, iter_num, los_checks, los_samples;

@@ -14,11 +14,11 @@ def world(b200, po, synth):
     return gm, om, c, s, g
 
 
-def _run_both(b200, po, gm, om, algo, s, g, allocate_num=1000000, lam=5.0, res=0.1, **kw):
-    pl = b200.Planner(algo, resolution=res, lambda_heuristic=lam, allocate_num=allocate_num, **kw)
+def _run_both(b200, po, gm, om, algo, s, g, allocate_num=1000000, lam=5.0, res=0.1, semantics="canonical", **kw):
+    pl = b200.Planner(algo, resolution=res, lambda_heuristic=lam, allocate_num=allocate_num, semantics=semantics, **kw)
     pl.setGridMap(gm)
     rg, pg = pl.findPaths(s, g, path_cap=len(s) * 4096)
-    op = po.OraclePlanner(algo, om, res, lam, allocate_num, mode=po.CANONICAL, **kw)
+    op = po.OraclePlanner(algo, om, res, lam, allocate_num, mode=po.FAITHFUL if semantics == "faithful" else po.CANONICAL, **kw)
     ro, pth = op.find_paths(s, g, path_stride=4096, nthreads=8)
     return pl, rg, pg, ro, pth
 
@@ -47,9 +47,49 @@ def test_batched_queries_match_canonical_oracle(b200, po, world, algo):
 
 
 @pytest.mark.parametrize("algo", ["astar", "thetastar"])
+def test_faithful_semantics_match_the_reference_restatement(b200, po, world, algo):
+    """The default semantics of astar/thetastar: bit-identical to the oracle's FAITHFUL mode, which the CPU
+    suite pins against the reference's own compiled code (tests/test_oracle_golden.py, test_oracle_vs_ref.py)."""
+    gm, om, c, s, g = world
+    n = 300 if algo == "astar" else 120
+    pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s[:n], g[:n], semantics="faithful")
+    assert ro["solved"].all()
+    assert_results_equal(rg, ro)
+    _assert_paths_equal(b200, rg, pg, ro, pth)
+    # and "default" means faithful for these two
+    pl2 = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0)
+    pl2.setGridMap(gm)
+    rd, _ = pl2.findPaths(s[:n], g[:n])
+    assert np.array_equal(rd["g_final"], rg["g_final"]) and np.array_equal(rd["explored_nodes"], rg["explored_nodes"])
+
+
+@pytest.mark.parametrize("algo", ["astar", "thetastar"])
+def test_faithful_hard_queries_lambda_one(b200, po, synth, algo):
+    # lambda = 1: thousands of expansions, many re-keyed open nodes -> the tree-shape-dependent pops matter most here
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    s, g = synth.random_queries(9, om.get_inflate_occupancy, c["origin"], c["size"], 6 if algo == "astar" else 3, min_dist=8.0)
+    pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s, g, lam=1.0, allocate_num=150000, semantics="faithful")
+    assert_results_equal(rg, ro)
+    _assert_paths_equal(b200, rg, pg, ro, pth)
+
+
+def test_faithful_pool_exhaustion_and_sealed_goal(b200, po, world):
+    gm, om, c, s, g = world
+    for algo in ["astar", "thetastar"]:
+        pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s[:40], g[:40], allocate_num=400, semantics="faithful")
+        assert (ro["status"] == 2).any()
+        assert_results_equal(rg, ro)
+
+
+def test_faithful_is_rejected_for_extension_algorithms(b200):
+    with pytest.raises(b200.B200Error):
+        b200.Planner("lazythetastar", resolution=0.1, semantics="faithful")
+
+
+@pytest.mark.parametrize("algo", ["astar", "thetastar"])
 def test_single_query_api_and_result_object(b200, po, world, algo):
     gm, om, c, s, g = world
-    pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0)
+    pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, semantics="canonical")
     pl.setGridMap(gm)
     d = pl.findPath(s[0], g[0])
     op = po.OraclePlanner(algo, om, 0.1, 5.0, 1000000, mode=po.CANONICAL)
@@ -70,6 +110,7 @@ def test_unknown_algorithm_falls_back_to_astar(b200, po, world):
     gm, om, c, s, g = world
     pl = b200.Planner("astarm1", resolution=0.1)
     pl.setGridMap(gm)
+    assert pl.algorithm == "astar"
     ref = b200.Planner("astar", resolution=0.1)
     ref.setGridMap(gm)
     a, _ = pl.findPaths(s[:8], g[:8])

@@ -17,7 +17,7 @@ def make_pair(b200, po, synth, name="C3", n_points=None, cam=(0.0, 0.0, 1.0), rn
     return gm, om, c
 
 
-def assert_results_equal(res_gpu, res_cpu, fields=("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks",
+def assert_results_equal(res_gpu, res_cpu, fields=("solved", "status", "n_path", "open_peak", "explored_nodes", "iter_num", "los_checks",
                                                    "los_samples")):
     for f in fields:
         bad = np.nonzero(res_gpu[f] != res_cpu[f])[0]
