@@ -503,6 +503,7 @@ struct Tier {
   NodeRec* nodes = nullptr;
   uint32_t* hash = nullptr;
   HeapEnt* heap = nullptr;
+  double* fkey = nullptr;
 };
 
 struct b200_planner {
@@ -529,10 +530,12 @@ static int tier_alloc(Tier& t, int cap, int slots, int factor) {
   const size_t nb = (size_t)slots * cap * sizeof(NodeRec);
   const size_t hb = (size_t)slots * hcap * 4;
   const size_t pb = (size_t)slots * open_region_entries(cap, factor) * sizeof(HeapEnt);
-  if (cudaMalloc(&t.base, nb + hb + pb) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return -1; }
+  const size_t fb = (size_t)slots * cap * sizeof(double);
+  if (cudaMalloc(&t.base, nb + hb + pb + fb) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return -1; }
   t.nodes = (NodeRec*)t.base;
   t.heap = (HeapEnt*)((char*)t.base + nb);
   t.hash = (uint32_t*)((char*)t.base + nb + pb);
+  t.fkey = (double*)((char*)t.base + nb + pb + hb);
   cudaMemset(t.hash, 0, hb);
   t.cap = cap; t.slots = slots; t.hcap = hcap; t.factor = factor;
   t.open_entries = (uint32_t)open_region_entries(cap, factor);
@@ -629,7 +632,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
 
   // workspace tiers: a small one for the common query, the full allocate_num one for the rare big query
   const int tpb = search_threads_per_block(pl->algo);
-  const int per_sm = tpb == 32 ? 16 : 4;
+  const int per_sm = pl->faithful ? (tpb == 32 ? 8 : 4) : (tpb == 32 ? 16 : 4);
   int slots0 = m->sm_count * per_sm;
   if ((int64_t)slots0 > nq) slots0 = (int)nq;
   const int cap0 = std::min(pl->prm.allocate_num, 16384);
@@ -676,7 +679,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   P.results = d_res; P.path_pool = d_path; P.path_cap = path_cap; P.path_cursor = path_cursor;
   P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;
   const Tier& t0 = pl->tier[0];
-  P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap; P.open_entries = t0.open_entries;
+  P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap; P.open_entries = t0.open_entries; P.fkey = t0.fkey;
   launch_search(P, std::min<int64_t>(t0.slots, nq), st);
   pl->last_launches++;
   CK(cudaGetLastError());
@@ -698,7 +701,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
       const Tier& t1 = pl->tier[1];
       P.qlist = overflow_list; P.nq = n_over;
       P.overflow_list = nullptr; P.overflow_count = overflow_count;
-      P.nodes = t1.nodes; P.hash = t1.hash; P.heap = t1.heap; P.cap = t1.cap; P.hcap = t1.hcap; P.open_entries = t1.open_entries;
+      P.nodes = t1.nodes; P.hash = t1.hash; P.heap = t1.heap; P.cap = t1.cap; P.hcap = t1.hcap; P.open_entries = t1.open_entries; P.fkey = t1.fkey;
       launch_search(P, std::min(t1.slots, n_over), st);
       pl->last_launches++;
       CK(cudaGetLastError());

@@ -70,6 +70,7 @@ struct SearchParams {
   NodeRec* nodes;
   uint32_t* hash;
   HeapEnt* heap;
+  double* fkey;   // faithful mode: compact copy of the nodes' f (the tree comparator's only input), cap per slot
   int cap;        // physical nodes per slot
   uint32_t open_entries;  // 16-byte open-list entries per slot (heap / red-black tree nodes)
   uint32_t hcap;  // hash entries per slot (power of two >= 2*cap)

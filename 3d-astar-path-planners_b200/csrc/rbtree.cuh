@@ -28,12 +28,12 @@ constexpr uint32_t RB_RED = 0x80000000u;
 
 struct RbSet {
   TreeNode* t;            // t[0] is the header: parent = root, left = leftmost, right = rightmost
-  const NodeRec* nodes;   // keys are compared through the nodes' CURRENT f (that is the point)
+  const double* fk;       // keys are compared through the nodes' CURRENT f (that is the point); compact copy of NodeRec::f
   uint32_t count, top, cap, free_head;
   bool overflow;
 
-  __device__ void init(TreeNode* mem, const NodeRec* n, uint32_t capacity) {
-    t = mem; nodes = n; cap = capacity;
+  __device__ void init(TreeNode* mem, const double* fkeys, uint32_t capacity) {
+    t = mem; fk = fkeys; cap = capacity;
     count = 0; top = 1; free_head = RB_NIL; overflow = false;
     t[RB_HEADER].parent = RB_NIL; t[RB_HEADER].left = RB_HEADER; t[RB_HEADER].right = RB_HEADER; t[RB_HEADER].vc = RB_RED;
   }
@@ -48,7 +48,7 @@ struct RbSet {
   // NodeComparator (utils.hpp:52-61): f ascending, then node address — the pool index here (creation order,
   // what a fresh heap gives the reference's per-node `new`)
   __device__ bool key_less(uint32_t a, uint32_t b) const {
-    const double fa = nodes[a].f, fb = nodes[b].f;
+    const double fa = fk[a], fb = fk[b];
     if (fa != fb) return fa < fb;
     return a < b;
   }
@@ -263,7 +263,7 @@ struct RbSet {
     return v;
   }
 
-  __device__ void clear() { init(t, nodes, cap); }
+  __device__ void clear() { init(t, fk, cap); }
 
   // std::set::erase(const key_type&): equal_range under the current keys, then erase the range
   __device__ void erase_key(uint32_t k) {

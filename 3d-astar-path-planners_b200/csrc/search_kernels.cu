@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
   s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
   s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
   s.hmask = P.hcap - 1;
+  double* fk = P.fkey + (size_t)blockIdx.x * P.cap;
   RbSet set;  // lane 0 of warp 0 owns the tree; the other lanes only see what it broadcasts
 
   const int la = lane / 9, lb = (lane / 3) % 3, lc = lane % 3;
@@ -570,7 +571,8 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
         n.slot = hash_insert(s, sx, sy, sz, 0);
         s.nodes[0] = n;
-        set.init(reinterpret_cast<TreeNode*>(s.heap), s.nodes, P.open_entries);
+        fk[0] = n.f;
+        set.init(reinterpret_cast<TreeNode*>(s.heap), fk, P.open_entries);
         set.insert(0u);
       }
       __syncwarp();
@@ -642,6 +644,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
               n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_NEW; n.pad = 0;
               n.slot = hash_insert(s, nx, ny, nz, ni);
               s.nodes[ni] = n;
+              fk[ni] = n.f;
               nb_idx = ni;
             }
             if (oom) {
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
             const int fl = fs.flags[k];
             if (!(fl & 1)) continue;
             NodeRec* w = s.nodes + fs.nb_idx[k];
-            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; }
+            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; fk[fs.nb_idx[k]] = fs.new_f[k]; }
             if (fl & 4) {
               if (IS_THETA && (fl & 8)) set.erase_key((uint32_t)fs.nb_idx[k]);  // ThetaStar.cpp:80 (key already mutated)
               w->state = NODE_OPEN | (k << 8);
@@ -810,7 +813,7 @@ size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out) {
   uint32_t h = 1024;
   while (h < 2u * (uint32_t)cap) h <<= 1;
   if (hcap_out) *hcap_out = h;
-  return (size_t)cap * sizeof(NodeRec) + (size_t)h * 4 + open_region_entries(cap, open_factor) * sizeof(HeapEnt);
+  return (size_t)cap * (sizeof(NodeRec) + sizeof(double)) + (size_t)h * 4 + open_region_entries(cap, open_factor) * sizeof(HeapEnt);
 }
 
 int search_threads_per_block(int algo) { return algo == ALGO_THETASTAR ? 128 : 32; }

@@ -1,0 +1,209 @@
+// b200_grid_map.hpp — host-side mirror of the reference's `GridMap` public interface
+// (include/plan_env/grid_map.h:139-196 + the inline accessors :257-446) on top of the C-ABI
+// (include/b200_planner.h).  Header-only, no ROS / Eigen / PCL needed: `Vec3d` / `Vec3i` are
+// Eigen::Vector3d / Vector3i when B200_WITH_EIGEN is defined (drop-in for the ROS node), else the two
+// small structs below (self-test, non-ROS hosts).
+//
+// What is mirrored: initMap (geometry + parameters of the cloud path), cloudCallback, odomCallback
+// (camera position), resetBuffer (x2), posToIndex, indexToPos, toAddress, isInMap (x2), boundIndex,
+// getInflateOccupancy, setOccupied, getRegion, getResolution, getOrigin, odomValid, plus the new
+// buildDistanceField / getDistance2.  The depth-image path and the rviz publishers stay in the reference
+// (SURVEY.md §8f).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200_planner.h"
+
+#ifdef B200_WITH_EIGEN
+#include <Eigen/Eigen>
+namespace b200host {
+using Vec3d = Eigen::Vector3d;
+using Vec3i = Eigen::Vector3i;
+}
+#else
+namespace b200host {
+struct Vec3d {
+  double v[3];
+  Vec3d() : v{0, 0, 0} {}
+  Vec3d(double x, double y, double z) : v{x, y, z} {}
+  double& operator()(int i) { return v[i]; }
+  const double& operator()(int i) const { return v[i]; }
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double z() const { return v[2]; }
+  const double* data() const { return v; }
+  double* data() { return v; }
+};
+struct Vec3i {
+  int v[3];
+  Vec3i() : v{0, 0, 0} {}
+  Vec3i(int x, int y, int z) : v{x, y, z} {}
+  int& operator()(int i) { return v[i]; }
+  const int& operator()(int i) const { return v[i]; }
+};
+}  // namespace b200host
+#endif
+
+namespace b200host {
+
+struct B200Error : std::runtime_error {
+  int code;
+  B200Error(int c, const std::string& what) : std::runtime_error(what + ": " + b200_last_error()), code(c) {}
+};
+inline void b200_check(int rc, const char* what) {
+  if (rc != B200_OK) throw B200Error(rc, what);
+}
+
+// ROS-private-parameter stand-in: the same keys the reference reads with node_.param(...)
+// (grid_map.cpp:12-50, AStar.cpp:32-35, ThetaStar.cpp:26-29).  With ROS present, fill it from the
+// NodeHandle (see planner_ros_node_b200.cpp).
+struct ParamMap {
+  std::map<std::string, double> num;
+  std::map<std::string, std::string> str;
+  template <class T> void param(const std::string& key, T& out, const T& def) const {
+    auto it = num.find(key);
+    out = it == num.end() ? def : (T)it->second;
+  }
+};
+
+class GridMap {
+ public:
+  typedef std::shared_ptr<GridMap> Ptr;
+  enum { POSE_STAMPED = 1, ODOMETRY = 2, INVALID_IDX = -10000 };
+
+  GridMap() {}
+  ~GridMap() { if (h_) b200_map_destroy(h_); }
+  GridMap(const GridMap&) = delete;
+  GridMap& operator=(const GridMap&) = delete;
+
+  // GridMap::initMap (grid_map.cpp:6-142): same parameter names and defaults
+  void initMap(const ParamMap& nh, int device = 0) {
+    double x_size, y_size, z_size;
+    nh.param("grid_map/resolution", prm_.resolution, 0.1);
+    nh.param("grid_map/map_size_x", x_size, 40.0);
+    nh.param("grid_map/map_size_y", y_size, 40.0);
+    nh.param("grid_map/map_size_z", z_size, 5.0);
+    nh.param("grid_map/local_update_range_x", prm_.local_update_range[0], 5.0);
+    nh.param("grid_map/local_update_range_y", prm_.local_update_range[1], 5.0);
+    nh.param("grid_map/local_update_range_z", prm_.local_update_range[2], 5.0);
+    nh.param("grid_map/obstacles_inflation", prm_.obstacles_inflation, 0.099);
+    nh.param("grid_map/ground_height", prm_.ground_height, -0.01);
+    prm_.origin[0] = -x_size / 2.0; prm_.origin[1] = -y_size / 2.0; prm_.origin[2] = prm_.ground_height;  // grid_map.cpp:53
+    prm_.size[0] = x_size; prm_.size[1] = y_size; prm_.size[2] = z_size;
+    prm_.device = device;
+    prm_.reserved = 0;
+    create();
+  }
+  // explicit-origin variant (the C-ABI does not force the centred origin)
+  void initMap(const b200_map_params_t& p) { prm_ = p; create(); }
+
+  // odomCallback (grid_map.cpp:699-709)
+  void odomCallback(const Vec3d& position) { camera_pos_ = position; has_odom_ = true; }
+  // cloudCallback (grid_map.cpp:711-804) on a raw PointCloud2 payload
+  void cloudCallback(const void* data, int64_t n_points, int point_step, int off_x = 0, int off_y = 4, int off_z = 8) {
+    has_cloud_ = true;
+    if (!has_odom_) return;  // "no odom!" (:718-722)
+    const double cam[3] = {camera_pos_(0), camera_pos_(1), camera_pos_(2)};
+    b200_check(b200_map_update_cloud(h_, data, n_points, point_step, off_x, off_y, off_z, cam, 0), "cloudCallback");
+  }
+#ifdef B200_WITH_ROS
+  void cloudCallback(const sensor_msgs::PointCloud2ConstPtr& img) {
+    int ox = 0, oy = 4, oz = 8;
+    for (const auto& f : img->fields) { if (f.name == "x") ox = f.offset; else if (f.name == "y") oy = f.offset; else if (f.name == "z") oz = f.offset; }
+    cloudCallback(img->data.data(), (int64_t)img->width * img->height, img->point_step, ox, oy, oz);
+  }
+  void odomCallback(const nav_msgs::OdometryConstPtr& odom) {
+    odomCallback(Vec3d(odom->pose.pose.position.x, odom->pose.pose.position.y, odom->pose.pose.position.z));
+  }
+#endif
+
+  void resetBuffer() { b200_check(b200_map_reset(h_), "resetBuffer"); }
+  void resetBuffer(Vec3d min_pos, Vec3d max_pos) {
+    const double a[3] = {min_pos(0), min_pos(1), min_pos(2)}, b[3] = {max_pos(0), max_pos(1), max_pos(2)};
+    b200_check(b200_map_clear_box(h_, a, b), "resetBuffer(min,max)");
+  }
+
+  // grid_map.h:400-404 / :257-265 / :267-274 / :370-398 — pure host arithmetic, same expressions
+  inline void posToIndex(const Vec3d& pos, Vec3i& id) const {
+    for (int i = 0; i < 3; ++i) id(i) = (int)std::floor((pos(i) - prm_.origin[i]) * res_inv_);
+  }
+  inline void indexToPos(const Vec3i& id, Vec3d& pos) const {
+    for (int i = 0; i < 3; ++i) pos(i) = (id(i) + 0.5) * prm_.resolution + prm_.origin[i];
+  }
+  inline int toAddress(const Vec3i& id) const { return id(0) * n_[1] * n_[2] + id(1) * n_[2] + id(2); }
+  inline int toAddress(int& x, int& y, int& z) const { return x * n_[1] * n_[2] + y * n_[2] + z; }
+  inline void boundIndex(Vec3i& id) const {
+    for (int i = 0; i < 3; ++i) id(i) = std::max(std::min(id(i), n_[i] - 1), 0);
+  }
+  inline bool isInMap(const Vec3d& pos) const {
+    for (int i = 0; i < 3; ++i)
+      if (pos(i) < prm_.origin[i] + 1e-4 || pos(i) > prm_.origin[i] + prm_.size[i] - 1e-4) return false;
+    return true;
+  }
+  inline bool isInMap(const Vec3i& idx) const {
+    for (int i = 0; i < 3; ++i)
+      if (idx(i) < 0 || idx(i) > n_[i] - 1) return false;
+    return true;
+  }
+  // grid_map.h:350-359 — one device read (the node calls this twice per request, via detectCollision)
+  inline int getInflateOccupancy(Vec3d pos) const {
+    const double p[3] = {pos(0), pos(1), pos(2)};
+    int8_t v = 0;
+    b200_check(b200_map_get_inflate_occupancy(h_, p, 1, &v, 0), "getInflateOccupancy");
+    return (int)v;
+  }
+  void getInflateOccupancy(const std::vector<Vec3d>& pos, std::vector<int8_t>& out) const {
+    std::vector<double> flat(pos.size() * 3);
+    for (size_t i = 0; i < pos.size(); ++i) for (int k = 0; k < 3; ++k) flat[3 * i + k] = pos[i](k);
+    out.resize(pos.size());
+    b200_check(b200_map_get_inflate_occupancy(h_, flat.data(), (int64_t)pos.size(), out.data(), 0), "getInflateOccupancy");
+  }
+  void getRegion(Vec3d& ori, Vec3d& size) const {
+    ori = Vec3d(prm_.origin[0], prm_.origin[1], prm_.origin[2]);
+    size = Vec3d(prm_.size[0], prm_.size[1], prm_.size[2]);
+  }
+  inline double getResolution() const { return prm_.resolution; }
+  Vec3d getOrigin() const { return Vec3d(prm_.origin[0], prm_.origin[1], prm_.origin[2]); }
+  int getVoxelNum() const { return n_[0] * n_[1] * n_[2]; }
+  bool odomValid() const { return has_odom_; }
+  void getLocalBounds(Vec3i& mn, Vec3i& mx) const {
+    int32_t a[3], b[3];
+    b200_check(b200_map_local_bounds(h_, a, b), "local bounds");
+    mn = Vec3i(a[0], a[1], a[2]); mx = Vec3i(b[0], b[1], b[2]);
+  }
+  // occupancy_buffer_inflate_ (reference byte layout) for publishers / parity
+  std::vector<uint8_t> downloadInflate() const {
+    std::vector<uint8_t> g((size_t)getVoxelNum());
+    b200_check(b200_map_download_inflate(h_, g.data()), "download");
+    return g;
+  }
+  // new: exact squared EDT + safety cost field (replaces the commented-out evaluateCoarseEDT hook)
+  void buildDistanceField(double d_safe) { b200_check(b200_map_build_edt(h_, d_safe), "build_edt"); }
+
+  b200_map_t* handle() const { return h_; }
+  const int* voxelNum() const { return n_; }
+
+ private:
+  void create() {
+    if (h_) { b200_map_destroy(h_); h_ = nullptr; }
+    res_inv_ = 1 / prm_.resolution;
+    b200_check(b200_map_create(&prm_, &h_), "initMap");
+    int32_t n[3];
+    b200_map_dims(h_, n);
+    for (int i = 0; i < 3; ++i) n_[i] = n[i];
+  }
+  b200_map_params_t prm_{};
+  b200_map_t* h_ = nullptr;
+  int n_[3] = {0, 0, 0};
+  double res_inv_ = 0;
+  Vec3d camera_pos_;
+  bool has_odom_ = false, has_cloud_ = false;
+};
+
+}  // namespace b200host

@@ -1,0 +1,74 @@
+// host_selftest.cpp — exercises the C++ adapter classes (GridMap / Planners::*) the way the reference's ROS
+// node drives its own classes (planner_ros_node.cpp:135-214, :261-296) and prints one JSON line per query so
+// tests/test_gpu_host_adapter.py can compare with the ctypes path.  No ROS, no Eigen.
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+
+#include "b200_planners.hpp"
+
+using namespace b200host;
+
+int main(int argc, char** argv) {
+  const char* algo = argc > 1 ? argv[1] : "thetastar";
+  try {
+    ParamMap nh;
+    nh.num["grid_map/resolution"] = 0.1;
+    nh.num["grid_map/map_size_x"] = 12.8; nh.num["grid_map/map_size_y"] = 12.8; nh.num["grid_map/map_size_z"] = 3.2;
+    nh.num["grid_map/local_update_range_x"] = 100; nh.num["grid_map/local_update_range_y"] = 100; nh.num["grid_map/local_update_range_z"] = 100;
+    for (const char* a : {"astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar"}) {
+      nh.num[std::string(a) + "/resolution"] = 0.1;
+      nh.num[std::string(a) + "/lambda_heuristic"] = 5.0;
+      nh.num[std::string(a) + "/allocate_num"] = 100000;
+    }
+    // configureAlgorithm (planner_ros_node.cpp:261-296)
+    std::unique_ptr<Planners::AlgorithmBase> algorithm;
+    const std::string name(algo);
+    if (name == "astar") algorithm.reset(new Planners::AStar());
+    else if (name == "thetastar") algorithm.reset(new Planners::ThetaStar());
+    else if (name == "lazythetastar") algorithm.reset(new Planners::LazyThetaStar());
+    else if (name == "costastar") algorithm.reset(new Planners::CostAStar());
+    else if (name == "costlazythetastar") algorithm.reset(new Planners::CostLazyThetaStar());
+    else algorithm.reset(new Planners::AStar());
+    algorithm->setCostFactor(2.0f);
+    algorithm->setParam(nh);
+    GridMap::Ptr grid_map(new GridMap);
+    grid_map->initMap(nh);
+    algorithm->setGridMap(grid_map);
+    algorithm->init();
+
+    // a deterministic free-standing wall (PointXYZ stride 16): y in [-2.4, 2.4), full height; paths go round its end.
+    // (A wall that seals the map except for one gap makes the reference's own A* take 5.8e7 iterations and
+    // 1.9e7 open-set entries — DESIGN.md "Reference pathologies" — so it is not a useful smoke scenario.)
+    std::vector<float> cloud;
+    for (int j = 40; j < 88; ++j)
+      for (int k = 0; k < 32; ++k) {
+        cloud.push_back(0.05f); cloud.push_back(-6.4f + (j + 0.5f) * 0.1f); cloud.push_back(-0.01f + (k + 0.5f) * 0.1f); cloud.push_back(0.f);
+      }
+    grid_map->odomCallback(Vec3d(0, 0, 1));
+    grid_map->cloudCallback(cloud.data(), (int64_t)cloud.size() / 4, 16);
+    if (name.rfind("cost", 0) == 0) grid_map->buildDistanceField(1.0);
+
+    // requestPathService (planner_ros_node.cpp:135-214)
+    algorithm->reset();
+    Vec3d start(-3.0, -1.0, 1.0), goal(3.0, 1.0, 1.5), blocked(0.05, 0.0, 1.0), outside(100, 0, 0);
+    if (algorithm->detectCollision(start) || algorithm->detectCollision(goal)) { std::printf("{\"error\": \"endpoints\"}\n"); return 1; }
+    const bool c1 = algorithm->detectCollision(blocked), c2 = algorithm->detectCollision(outside);
+    auto path_data = algorithm->findPath(start, goal, Vec3d(), Vec3d(), Vec3d());
+    const bool solved = std::get<bool>(path_data["solved"]);
+    const auto path = algorithm->getPath();
+    const Vec3d gc = std::get<Vec3d>(path_data["goal_coords"]);
+    std::printf("{\"algorithm\": \"%s\", \"solved\": %d, \"n_path\": %zu, \"g_final_node\": %.17g, \"path_length\": %.17g, "
+                "\"explored_nodes\": %zu, \"line_of_sight_checks\": %u, \"goal_coords\": [%.17g, %.17g, %.17g], "
+                "\"collide_wall\": %d, \"collide_outside\": %d, \"total_cost1\": %u, \"time_spent_us\": %.3f}\n",
+                std::get<std::string>(path_data["algorithm"]).c_str(), solved ? 1 : 0, path.size(), std::get<double>(path_data["g_final_node"]),
+                std::get<double>(path_data["path_length"]), std::get<size_t>(path_data["explored_nodes"]),
+                std::get<unsigned int>(path_data["line_of_sight_checks"]), gc(0), gc(1), gc(2), c1 ? 1 : 0, c2 ? 1 : 0,
+                std::get<unsigned int>(path_data["total_cost1"]), std::get<double>(path_data["time_spent"]));
+    algorithm->reset();
+    return solved ? 0 : 2;
+  } catch (const std::exception& e) {
+    std::printf("{\"error\": \"%s\"}\n", e.what());
+    return 3;
+  }
+}

@@ -26,7 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D_SAFE = 1.0
-QUERY_ALGOS = (("lazythetastar", 16384), ("astar", 16384), ("thetastar", 2048))
+# (algorithm, semantics, queries per rank): faithful = bit-identical to the reference's std::set behaviour
+QUERY_ALGOS = (("lazythetastar", "canonical", 16384), ("astar", "faithful", 8192), ("astar", "canonical", 16384),
+               ("thetastar", "faithful", 2048), ("thetastar", "canonical", 2048))
 
 
 def build_world(synth):
@@ -130,7 +132,7 @@ def main():
     import torch
     import torch.distributed as dist
     import astar_planners_b200 as b200
-    from astar_planners_b200 import synth
+    from astar_planners_b200 import shard, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
@@ -247,13 +249,16 @@ def main():
     extra = {"edt_hbm_gbs_survey_def": edt_gbs, "edt_ms": float(edt_ms), "wall_ms_timed_region": wall_ms}
     if not args.no_extra:
         occ = lambda p: gm.getInflateOccupancy(p)
-        for algo, nq in QUERY_ALGOS:
-            s, g = synth.random_queries(6 + rank, occ, c["origin"], c["size"], nq, min_dist=5.0, z_range=(0.3, 3.0))
-            pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0)
+        for algo, sem, nq in QUERY_ALGOS:
+            # every rank draws the same global batch and takes its contiguous shard (map replicated, no collective)
+            s, g = synth.random_queries(6, occ, c["origin"], c["size"], nq * world, min_dist=5.0, z_range=(0.3, 3.0))
+            lo, hi = shard.query_shard(nq * world, rank, world)
+            s, g = np.ascontiguousarray(s[lo:hi]), np.ascontiguousarray(g[lo:hi])
+            pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0, semantics=sem)
             pl.setGridMap(gm)
             ds, dg = torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
             dres = torch.empty(nq * 128, dtype=torch.uint8, device=dev)
-            pl.findPaths(ds[:256], dg[:256], results=dres)  # warm-up (workspace allocation)
+            pl.findPaths(ds, dg, results=dres)  # warm-up at full size (workspace allocation, both tiers)
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -271,11 +276,12 @@ def main():
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(tot, op=dist.ReduceOp.SUM)
                 ms, ms_h = float(mx[0]), float(mx[1])
-            extra[f"{algo}_queries_per_s"] = float(tot[2]) / (ms * 1e-3)
-            extra[f"{algo}_queries_per_s_e2e"] = float(tot[2]) / (ms_h * 1e-3)
-            extra[f"{algo}_queries"] = int(tot[2])
-            extra[f"{algo}_solved"] = int(tot[3])
-            extra[f"{algo}_expansions_per_query"] = float(tot[4]) / float(tot[2])
+            key = f"{algo}_{sem}"
+            extra[f"{key}_queries_per_s"] = float(tot[2]) / (ms * 1e-3)
+            extra[f"{key}_queries_per_s_e2e"] = float(tot[2]) / (ms_h * 1e-3)
+            extra[f"{key}_queries"] = int(tot[2])
+            extra[f"{key}_solved"] = int(tot[3])
+            extra[f"{key}_expansions_per_query"] = float(tot[4]) / float(tot[2])
             pl.close()
 
     # ---- cpu_baseline: the oracle on this box's host cores (rank 0, N = 1 only)

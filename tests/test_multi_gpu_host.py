@@ -1,0 +1,70 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic — contiguous query shards, no data-path collective, results
+gathered on the control path — with a stand-in for Planner.findPaths (the CUDA path itself needs a GPU)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nq, out_dir):
+    sys.path.insert(0, ROOT)
+    import astar_planners_b200  # noqa: F401
+    from astar_planners_b200 import shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    starts, goals = rng.random((nq, 3)), rng.random((nq, 3))
+    dt = np.dtype([("solved", "i4"), ("g_final", "f8"), ("rank", "i4")])
+    calls = []
+
+    def fake_find_paths(s, g):
+        calls.append(len(s))
+        r = np.zeros(len(s), dtype=dt)
+        r["solved"] = 1
+        r["g_final"] = np.linalg.norm(s - g, axis=1)
+        r["rank"] = rank
+        return r
+
+    res = shard.find_paths_sharded(fake_find_paths, starts, goals, rank, world, dist)
+    lo, hi = shard.query_shard(nq, rank, world)
+    assert calls == [hi - lo]
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_query_shards_cover_everything_once():
+    sys.path.insert(0, ROOT)
+    import astar_planners_b200  # noqa: F401
+    from astar_planners_b200 import shard
+    for nq in (0, 1, 7, 10000, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard.query_shard(nq, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nq
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_queries_two_ranks_gloo(tmp_path):
+    nq, world = 1001, 2
+    mp.spawn(_worker, args=(world, _free_port(), nq, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    assert np.array_equal(r0, r1) and len(r0) == nq                      # every rank ends with the full result set
+    rng = np.random.default_rng(0)
+    starts, goals = rng.random((nq, 3)), rng.random((nq, 3))
+    assert np.array_equal(r0["g_final"], np.linalg.norm(starts - goals, axis=1))   # order preserved
+    assert (r0["rank"][:500] == 0).all() and (r0["rank"][500:] == 1).all()         # contiguous shards
