@@ -67,6 +67,8 @@ ABI = [
     ("b200_map_upload_inflate", C.c_int, [_vp, _vp]),
     ("b200_map_device_bits", C.c_int, [_vp, _pp, C.POINTER(_i64)]),
     ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
+    ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
+    ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
     ("b200_map_download_dist2", C.c_int, [_vp, _vp]),
     ("b200_map_download_costq", C.c_int, [_vp, _vp]),
     ("b200_map_download_cost", C.c_int, [_vp, _vp]),
@@ -241,6 +243,25 @@ class GridMap:
     # --- new functionality ------------------------------------------------------------------------
     def build_edt(self, d_safe=0.0):
         _ck(lib().b200_map_build_edt(self.h, float(d_safe)))
+
+    def column_extents(self, lowest=None, highest=None):
+        """Lowest / highest occupied z per (x,y) column (-1 = empty): what a z-slab publishes to the others."""
+        if _is_dev(lowest):
+            _ck(lib().b200_map_column_extents(self.h, _ptr(lowest), _ptr(highest), 1))
+            return lowest, highest
+        lo = np.empty(self.dims[:2], dtype=np.int32)
+        hi = np.empty(self.dims[:2], dtype=np.int32)
+        _ck(lib().b200_map_column_extents(self.h, _ptr(lo), _ptr(hi), 0))
+        return lo, hi
+
+    def build_edt_slab(self, d_safe=0.0, below_gap=None, above_gap=None):
+        """EDT of one z-slab given the per-column gaps to the nearest occupied voxel in the slabs below / above."""
+        dev = 1 if (_is_dev(below_gap) or _is_dev(above_gap)) else 0
+        if not dev:
+            below_gap = None if below_gap is None else np.ascontiguousarray(below_gap, dtype=np.int32)
+            above_gap = None if above_gap is None else np.ascontiguousarray(above_gap, dtype=np.int32)
+        self._keep_gaps = (below_gap, above_gap)
+        _ck(lib().b200_map_build_edt_slab(self.h, float(d_safe), _ptr(below_gap), _ptr(above_gap), dev))
 
     def dist2(self):
         out = np.empty(self.dims, dtype=np.int32)

@@ -59,6 +59,7 @@ struct b200_map {
   int32_t* d_tmp;
   uint2* d_st;
   void* d_dz;
+  int dz_bytes;
   int* d_counts;
   uint16_t* d_lut;
   int lut_cap;
@@ -171,6 +172,7 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->d_tmp = nullptr;
   m->d_st = nullptr;
   m->d_dz = nullptr;
+  m->dz_bytes = 0;
   m->d_counts = nullptr;
   m->d_lut = nullptr;
   m->lut_cap = 0;
@@ -365,19 +367,32 @@ int b200_map_device_bits(b200_map_t* m, void** p, int64_t* n_words) {
   return B200_OK;
 }
 
-int b200_map_build_edt(b200_map_t* m, double d_safe) {
+static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap, const int32_t* above_gap, int on_device) {
   REQUIRE(m, "NULL map");
   CK(cudaSetDevice(m->prm.device));
   const size_t nv = (size_t)m->N[0] * m->N[1] * m->N[2];
+  const size_t cols = (size_t)m->N[0] * m->N[1];
   auto need = [&](void** p, size_t bytes) -> bool {
     if (*p) return true;
     if (cudaMalloc(p, bytes) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return false; }
     return true;
   };
+  const bool halo = below_gap || above_gap;
+  const int dz_bytes = edt_dz_is_wide(m->d, halo) ? 2 : 1;
+  if (m->d_dz && m->dz_bytes < dz_bytes) { cudaFree(m->d_dz); m->d_dz = nullptr; }
   const size_t max_lines = (size_t)std::max(m->N[0], m->N[1]) * m->N[2];
   if (!need((void**)&m->d_tmp, nv * 4) || !need((void**)&m->d_st, nv * 8) || !need((void**)&m->d.dist2, nv * 4) ||
-      !need((void**)&m->d_dz, nv * (m->N[2] > 254 ? 2 : 1)) || !need((void**)&m->d_counts, max_lines * 4))
+      !need((void**)&m->d_dz, nv * dz_bytes) || !need((void**)&m->d_counts, max_lines * 4))
     return fail(B200_ERR_NOMEM, "distance-field buffers");
+  m->dz_bytes = std::max(m->dz_bytes, dz_bytes);
+  const int32_t* d_below = below_gap;
+  const int32_t* d_above = above_gap;
+  if (halo && !on_device) {  // stage the two per-column halo arrays
+    if (m->stage_in.ensure(cols * 8)) return fail(B200_ERR_NOMEM, "halo staging");
+    int32_t* base = (int32_t*)m->stage_in.p;
+    if (below_gap) { CK(cudaMemcpyAsync(base, below_gap, cols * 4, cudaMemcpyHostToDevice, m->stream)); d_below = base; }
+    if (above_gap) { CK(cudaMemcpyAsync(base + cols, above_gap, cols * 4, cudaMemcpyHostToDevice, m->stream)); d_above = base + cols; }
+  }
   int lut_n = 0;
   if (d_safe > 0) {
     if (!need((void**)&m->d.costq, nv * 2)) return fail(B200_ERR_NOMEM, "cost field");
@@ -389,12 +404,37 @@ int b200_map_build_edt(b200_map_t* m, double d_safe) {
       m->lut_cap = lut_n;
     }
   }
-  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, m->stream,
-             m->profiling ? &m->ev[3] : nullptr);
+  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, d_below, d_above,
+             m->stream, m->profiling ? &m->ev[3] : nullptr);
   m->launches += 5 + (lut_n > 0 ? 1 : 0);
   CK(cudaGetLastError());
+  if (halo && !on_device) CK(cudaStreamSynchronize(m->stream));  // staging buffer is reused by other calls
   m->has_edt = true;
   m->d_safe = d_safe;
+  return B200_OK;
+}
+int b200_map_build_edt(b200_map_t* m, double d_safe) { return build_edt_impl(m, d_safe, nullptr, nullptr, 0); }
+int b200_map_build_edt_slab(b200_map_t* m, double d_safe, const int32_t* below_gap, const int32_t* above_gap, int32_t on_device) {
+  return build_edt_impl(m, d_safe, below_gap, above_gap, on_device);
+}
+int b200_map_column_extents(b200_map_t* m, int32_t* lowest, int32_t* highest, int32_t on_device) {
+  REQUIRE(m && lowest && highest, "NULL argument");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t cols = (size_t)m->N[0] * m->N[1];
+  if (on_device) {
+    launch_column_extents(m->d, lowest, highest, m->stream);
+    m->launches++;
+    CK(cudaGetLastError());
+    return B200_OK;
+  }
+  if (m->stage_out.ensure(cols * 8)) return fail(B200_ERR_NOMEM, "extent staging");
+  int32_t* base = (int32_t*)m->stage_out.p;
+  launch_column_extents(m->d, base, base + cols, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(lowest, base, cols * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(highest, base + cols, cols * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
   return B200_OK;
 }
 

@@ -27,8 +27,11 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------------
 // z pass
 // ---------------------------------------------------------------------------------------------------
+// halo (optional, z-slab sharding): below_gap[c] / above_gap[c] = distance in voxels from the slab's first / last
+// z-plane to the nearest occupied voxel in the slabs below / above (>= 1), or < 0 when there is none.
 template <class T>
-__global__ void __launch_bounds__(256) edt_z_kernel(MapDev m, T* __restrict__ dz) {
+__global__ void __launch_bounds__(256) edt_z_kernel(MapDev m, T* __restrict__ dz, const int32_t* __restrict__ below_gap,
+                                                    const int32_t* __restrict__ above_gap) {
   constexpr int kNone = sizeof(T) == 1 ? 255 : 65535;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (column, word)
   const long long total = (long long)m.Nx * m.Ny * m.wz;
@@ -39,6 +42,8 @@ __global__ void __launch_bounds__(256) edt_z_kernel(MapDev m, T* __restrict__ dz
   const uint32_t own = __ldg(c + wi);
   // nearest set bit outside the own word (absolute z), far away when none
   int below = -(1 << 20), above = 1 << 20;
+  if (below_gap) { const int g = __ldg(below_gap + col); if (g > 0) below = -g; }
+  if (above_gap) { const int g = __ldg(above_gap + col); if (g > 0) above = m.Nz - 1 + g; }
   for (int j = wi - 1; j >= 0; --j) {
     const uint32_t v = __ldg(c + j);
     if (v) { below = (j << 5) + 31 - __clz(v); break; }
@@ -82,6 +87,25 @@ __global__ void __launch_bounds__(256) edt_z_kernel(MapDev m, T* __restrict__ dz
     for (int b = 0; b < 32; ++b)
       if (z0 + b < m.Nz) o[b] = (T)up[b];
   }
+}
+
+// per (x,y) column: lowest and highest occupied z of this map (-1 when the column is empty) — what a z-slab
+// publishes to the other slabs
+__global__ void __launch_bounds__(256) column_extents_kernel(MapDev m, int32_t* __restrict__ lowest, int32_t* __restrict__ highest) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)m.Nx * m.Ny) return;
+  const uint32_t* c = m.occ + col * m.wz;
+  int lo = -1, hi = -1;
+  for (int j = 0; j < m.wz; ++j) {
+    const uint32_t v = __ldg(c + j);
+    if (v) { if (lo < 0) lo = (j << 5) + __ffs(v) - 1; hi = (j << 5) + 31 - __clz(v); }
+  }
+  lowest[col] = lo;
+  highest[col] = hi;
+}
+void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream) {
+  const long long cols = (long long)m.Nx * m.Ny;
+  column_extents_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(m, lowest, highest);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -278,18 +302,20 @@ int edt_lut_size(double res, double d_safe) {
 }
 
 // ev (optional): 6 events recorded before z, scan_y, fill_y, scan_x, fill_x and after fill_x
+bool edt_dz_is_wide(const MapDev& m, bool halo) { return m.Nz > 254 || halo; }  // halo: z distances are not bounded by the slab
+
 void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int32_t* dist2, uint16_t* costq, uint16_t* lut,
-                int lut_n, double d_safe, cudaStream_t stream, cudaEvent_t* ev) {
+                int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev) {
   const long long lines1 = (long long)m.Nx * m.Nz, lines2 = (long long)m.Ny * m.Nz;
   const unsigned g1 = (unsigned)((lines1 + 127) / 128), g2 = (unsigned)((lines2 + 127) / 128);
   const dim3 f1(g1, (unsigned)((m.Ny + SPT - 1) / SPT)), f2(g2, (unsigned)((m.Nx + SPT - 1) / SPT));
   const long long words = (long long)m.Nx * m.Ny * m.wz;
   const unsigned gz = (unsigned)((words + 255) / 256);
-  const bool wide = m.Nz > 254;
+  const bool wide = edt_dz_is_wide(m, below_gap || above_gap);
   if (d_safe > 0 && lut_n > 0) cost_lut_kernel<<<(lut_n + 255) / 256, 256, 0, stream>>>(lut, lut_n, (float)m.res, (float)d_safe);
   if (ev) cudaEventRecord(ev[0], stream);
-  if (wide) edt_z_kernel<uint16_t><<<gz, 256, 0, stream>>>(m, (uint16_t*)dzbuf);
-  else edt_z_kernel<uint8_t><<<gz, 256, 0, stream>>>(m, (uint8_t*)dzbuf);
+  if (wide) edt_z_kernel<uint16_t><<<gz, 256, 0, stream>>>(m, (uint16_t*)dzbuf, below_gap, above_gap);
+  else edt_z_kernel<uint8_t><<<gz, 256, 0, stream>>>(m, (uint8_t*)dzbuf, below_gap, above_gap);
   if (ev) cudaEventRecord(ev[1], stream);
   if (wide) edt_scan_y_kernel<uint16_t><<<g1, 128, 0, stream>>>(m, (const uint16_t*)dzbuf, st, counts);
   else edt_scan_y_kernel<uint8_t><<<g1, 128, 0, stream>>>(m, (const uint8_t*)dzbuf, st, counts);

@@ -25,3 +25,30 @@ def find_paths_sharded(find_paths, starts, goals, rank, world, dist=None):
     for plo, phi, raw, _ in parts:
         out[plo:phi] = np.frombuffer(raw, dtype=local.dtype)
     return out
+
+
+def slab_gaps(lowest, highest, slab_nz, rank):
+    """z-slab EDT halo from the all-gathered column extents (include/b200_planner.h b200_map_build_edt_slab).
+
+    lowest[r], highest[r]: int32 [Nx,Ny] lowest / highest occupied z of slab r in slab-local voxels (-1 = empty column);
+    slab_nz[r]: z extent of slab r.  Returns (below_gap, above_gap) for `rank`: voxels from its first / last z-plane to
+    the nearest occupied voxel in the slabs below / above (>= 1), -1 where there is none."""
+    world = len(slab_nz)
+    shape = np.asarray(lowest[0]).shape
+    below = np.full(shape, -1, dtype=np.int32)
+    gap = 0  # voxels between this slab's first plane and the top plane of slab r, minus one
+    for r in range(rank - 1, -1, -1):
+        hi = np.asarray(highest[r])
+        cand = gap + (slab_nz[r] - hi)          # local z = hi sits (slab_nz[r] - hi) voxels below our z = 0, plus the slabs in between
+        take = (hi >= 0) & (below < 0)
+        below[take] = cand[take].astype(np.int32)
+        gap += slab_nz[r]
+    above = np.full(shape, -1, dtype=np.int32)
+    gap = 0
+    for r in range(rank + 1, world):
+        lo = np.asarray(lowest[r])
+        cand = gap + lo + 1                     # local z = lo of slab r is lo + 1 voxels above our last plane, plus the slabs in between
+        take = (lo >= 0) & (above < 0)
+        above[take] = cand[take].astype(np.int32)
+        gap += slab_nz[r]
+    return below, above

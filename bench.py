@@ -76,7 +76,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """CPU arm: the oracle's restatement of cloudCallback + (our) EDT/cost on all host threads."""
     if rank != 0:
         return
@@ -107,7 +107,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": ms, "unit": "ms/frame", "cores": nthreads, "kind": "port",
                              "sample": f"{args.steps} full C2 frames (cloud update + EDT + cost), oracle/liboracle.so, {nthreads} threads"},
             "e2e": {"value": ms, "unit": "ms/frame", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def main():
@@ -124,9 +124,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly ONE JSON line: send everything libraries print (e.g. the NCCL version banner)
+    # to stderr and keep the real stdout for the final line
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
 
     import torch
@@ -320,7 +325,7 @@ def main():
             "gpu_launches": int(args.steps * 7), "kernels_per_step": ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_fill_y_kernel", "edt_scan_x_kernel", "edt_fill_x_kernel", "(+1 cudaMemsetAsync clear)"],
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

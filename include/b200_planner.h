@@ -102,6 +102,15 @@ int b200_map_device_bits(b200_map_t* map, void** dev_ptr, int64_t* n_words);
  * the nearest inflated-occupied voxel, plus — when d_safe > 0 — the safety-cost field
  * c = max(0, 1 - sqrt(d2)*res/d_safe) (float32) and its uint16 quantisation the cost-aware planners read. */
 int b200_map_build_edt(b200_map_t* map, double d_safe);
+/* z-slab sharding of the distance transform for grids too large for one GPU (north star).  The map is
+ * one z-slab (full x,y extent).  Because the z pass runs first and on bits, the only information an EXACT,
+ * untruncated transform needs from the other slabs is, per (x,y) column (index x*Ny + y), the distance in voxels
+ * from this slab's first / last z-plane to the nearest occupied voxel below / above it (>= 1; < 0 = none).
+ * b200_map_column_extents publishes a slab's lowest / highest occupied z per column (-1 = empty column); the host
+ * all-gathers those (NCCL/NVLink) and derives the gaps (shard.py: slab_gaps). NULL gap arrays = no neighbour. */
+int b200_map_column_extents(b200_map_t* map, int32_t* lowest_z, int32_t* highest_z, int32_t on_device);
+int b200_map_build_edt_slab(b200_map_t* map, double d_safe, const int32_t* below_gap, const int32_t* above_gap,
+                            int32_t on_device);
 int b200_map_download_dist2(b200_map_t* map, int32_t* dst);
 int b200_map_download_costq(b200_map_t* map, uint16_t* dst);
 int b200_map_download_cost(b200_map_t* map, float* dst);

@@ -73,3 +73,41 @@ def test_cost_planner_without_edt_fails_loudly(b200, po, synth):
     pl.setGridMap(gm)
     with pytest.raises(b200.B200Error):
         pl.findPaths(np.zeros((1, 3)), np.ones((1, 3)))
+
+
+@pytest.mark.parametrize("splits", [(32, 32, 32), (64, 32), (32, 64), (96,)])
+def test_z_slab_edt_equals_full_transform(b200, po, splits):
+    """z-slab sharded EDT. Slabs exchange only per-column extents (lowest/highest occupied z); the
+    result must equal the unsharded transform exactly (untruncated)."""
+    from astar_planners_b200 import shard
+    rng = np.random.default_rng(7)
+    dims = (40, 24, 96)
+    grid = (rng.random(dims) < 0.004).astype(np.uint8)
+    grid[:, :, 40:70] = 0                       # a thick empty band: distances must cross an entire slab
+    grid[5:9, 3:7, :] = 0                       # columns with no obstacle at all
+    res = 0.5
+    full = b200.GridMap(tuple(d * res for d in dims), res, origin=(0, 0, 0))
+    full.set_inflate(grid)
+    full.build_edt(d_safe=3.0)
+    want_d2, want_cq = full.dist2(), full.costq()
+    slabs, z0 = [], 0
+    for nz in splits:
+        m = b200.GridMap((dims[0] * res, dims[1] * res, nz * res), res, origin=(0, 0, z0 * res))
+        m.set_inflate(np.ascontiguousarray(grid[:, :, z0:z0 + nz]))
+        slabs.append(m)
+        z0 += nz
+    ext = [m.column_extents() for m in slabs]
+    lows, highs = [e[0] for e in ext], [e[1] for e in ext]
+    for r, (m, nz) in enumerate(zip(slabs, splits)):
+        lo_np = np.where(grid[:, :, sum(splits[:r]):sum(splits[:r]) + nz].any(axis=2),
+                         grid[:, :, sum(splits[:r]):sum(splits[:r]) + nz].argmax(axis=2), -1)
+        assert np.array_equal(lows[r], lo_np)
+    got_d2, got_cq = [], []
+    for r, m in enumerate(slabs):
+        below, above = shard.slab_gaps(lows, highs, list(splits), r)
+        m.build_edt_slab(3.0, below if r > 0 else None, above if r < len(slabs) - 1 else None)
+        got_d2.append(m.dist2())
+        got_cq.append(m.costq())
+    assert np.array_equal(np.concatenate(got_d2, axis=2), want_d2)
+    assert np.array_equal(np.concatenate(got_cq, axis=2), want_cq)
+    assert (want_d2[:, :, 50] > 100).any()      # the band really is far from everything

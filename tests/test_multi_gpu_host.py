@@ -68,3 +68,48 @@ def test_sharded_queries_two_ranks_gloo(tmp_path):
     starts, goals = rng.random((nq, 3)), rng.random((nq, 3))
     assert np.array_equal(r0["g_final"], np.linalg.norm(starts - goals, axis=1))   # order preserved
     assert (r0["rank"][:500] == 0).all() and (r0["rank"][500:] == 1).all()         # contiguous shards
+
+
+def _slab_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import astar_planners_b200  # noqa: F401
+    from astar_planners_b200 import shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    grid = (rng.random((12, 10, 48)) < 0.02).astype(np.uint8)
+    grid[:, :, 16:32] = 0 if world == 3 else grid[:, :, 16:32]   # middle slab empty: gaps must skip over it
+    nz = 48 // world
+    mine = grid[:, :, rank * nz:(rank + 1) * nz]
+    has = mine.any(axis=2)
+    lo = np.where(has, mine.argmax(axis=2), -1).astype(np.int32)
+    hi = np.where(has, nz - 1 - mine[:, :, ::-1].argmax(axis=2), -1).astype(np.int32)
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, hi))            # the one exchange step of the slab EDT (tiny)
+    below, above = shard.slab_gaps([p[0] for p in parts], [p[1] for p in parts], [nz] * world, rank)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), below=below, above=above)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_halo_exchange_three_ranks_gloo(tmp_path):
+    world = 3
+    mp.spawn(_slab_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    grid = (rng.random((12, 10, 48)) < 0.02).astype(np.uint8)
+    grid[:, :, 16:32] = 0
+    nz = 16
+    for r in range(world):
+        got = np.load(tmp_path / f"s{r}.npz")
+        z_first, z_last = r * nz, (r + 1) * nz - 1
+        below = np.full(grid.shape[:2], -1)
+        above = np.full(grid.shape[:2], -1)
+        for x in range(grid.shape[0]):
+            for y in range(grid.shape[1]):
+                zs = np.nonzero(grid[x, y])[0]
+                lower, upper = zs[zs < z_first], zs[zs > z_last]
+                if len(lower):
+                    below[x, y] = z_first - lower.max()
+                if len(upper):
+                    above[x, y] = upper.min() - z_last
+        assert np.array_equal(got["below"], below) and np.array_equal(got["above"], above)
