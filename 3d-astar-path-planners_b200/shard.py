@@ -52,3 +52,24 @@ def slab_gaps(lowest, highest, slab_nz, rank):
         above[take] = cand[take].astype(np.int32)
         gap += slab_nz[r]
     return below, above
+
+
+def slab_gaps_torch(lowest, highest, slab_nz, rank):
+    """Same as slab_gaps on torch tensors of shape [world, Nx, Ny] (device-resident, after an NCCL all_gather)."""
+    import torch
+    world = lowest.shape[0]
+    below = torch.full_like(lowest[0], -1)
+    gap = 0
+    for r in range(rank - 1, -1, -1):
+        cand = gap + (slab_nz[r] - highest[r])
+        take = (highest[r] >= 0) & (below < 0)
+        below = torch.where(take, cand.to(below.dtype), below)
+        gap += slab_nz[r]
+    above = torch.full_like(lowest[0], -1)
+    gap = 0
+    for r in range(rank + 1, world):
+        cand = gap + lowest[r] + 1
+        take = (lowest[r] >= 0) & (above < 0)
+        above = torch.where(take, cand.to(above.dtype), above)
+        gap += slab_nz[r]
+    return below.contiguous(), above.contiguous()

@@ -110,6 +110,63 @@ def run_reference(args, rank, world, out):
     print(json.dumps(line), file=out, flush=True)
 
 
+def run_slab_edt(b200, shard, torch, dist, dev, rank, world, local_rank, nxy=2048, nz_total=512, res=0.1):
+    nz = nz_total // world
+    size = (nxy * res, nxy * res, nz * res)
+    origin = (-size[0] / 2, -size[1] / 2, -0.01 + rank * nz * res)
+    gm = b200.GridMap(size, res, origin=origin, local_update_range=(1e4, 1e4, 1e4), ground_height=-0.01, device=local_rank)
+    # device-generated forest (same seed on every rank): ground plane + pillars, ~2e7 points
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    n_pil = 11000
+    cx = (torch.rand(n_pil, generator=g, device=dev) - 0.5) * (size[0] - 2)
+    cy = (torch.rand(n_pil, generator=g, device=dev) - 0.5) * (size[1] - 2)
+    w = 0.5 + 0.7 * torch.rand(n_pil, generator=g, device=dev)
+    h = 0.8 + 2.2 * torch.rand(n_pil, generator=g, device=dev) + 40.0 * (torch.rand(n_pil, generator=g, device=dev) < 0.02)
+    per = 1500
+    u = torch.rand(n_pil, per, 3, generator=g, device=dev)
+    pts = torch.stack([cx[:, None] + (u[..., 0] - 0.5) * w[:, None], cy[:, None] + (u[..., 1] - 0.5) * w[:, None],
+                       u[..., 2] * h[:, None]], dim=-1).reshape(-1, 3)
+    gxy = (torch.arange(nxy, device=dev, dtype=torch.float32) + 0.5) * res - size[0] / 2
+    ground = torch.stack(torch.meshgrid(gxy, gxy, indexing="ij"), dim=-1).reshape(-1, 2)
+    ground = torch.cat([ground, torch.full((ground.shape[0], 1), 0.04, device=dev)], dim=1)
+    cloud = torch.zeros(pts.shape[0] + ground.shape[0], 4, device=dev, dtype=torch.float32)
+    cloud[:, :3] = torch.cat([pts, ground]).to(torch.float32)
+    gm.cloudCallback(cloud, (0.0, 0.0, 1.0), point_step=16)
+    lo = torch.empty(nxy, nxy, dtype=torch.int32, device=dev)
+    hi = torch.empty(nxy, nxy, dtype=torch.int32, device=dev)
+    all_lo = torch.empty(world, nxy, nxy, dtype=torch.int32, device=dev)
+    all_hi = torch.empty(world, nxy, nxy, dtype=torch.int32, device=dev)
+
+    def step():
+        gm.column_extents(lo, hi)
+        dist.all_gather_into_tensor(all_lo, lo)
+        dist.all_gather_into_tensor(all_hi, hi)
+        below, above = shard.slab_gaps_torch(all_lo, all_hi, [nz] * world, rank)
+        gm.build_edt_slab(D_SAFE, below if rank > 0 else None, above if rank < world - 1 else None)
+        return below, above
+
+    keep = step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        keep = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nvox_total = nxy * nxy * nz_total
+    occ_frac = float((hi >= 0).float().mean())
+    gm.close()
+    del keep
+    return {"grid": [nxy, nxy, nz_total], "slabs": world, "points": int(cloud.shape[0]), "ms": float(ms),
+            "gbs_survey_def_total": (nvox_total / 8 + 4 * nvox_total) / (float(ms) * 1e-3) / 1e9,
+            "exchange_bytes_per_rank": int(2 * world * nxy * nxy * 4), "columns_with_obstacle_frac": occ_frac}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,6 +345,14 @@ def main():
             extra[f"{key}_solved"] = int(tot[3])
             extra[f"{key}_expansions_per_query"] = float(tot[4]) / float(tot[2])
             pl.close()
+
+    # ---- extra (N >= 2): BASELINE config 5 — 2048x2048x512 exact EDT, z-slab sharded, one NCCL all-gather of the
+    # per-column extents.  Every rank voxelises the same device-generated cloud into its own slab.
+    if world >= 2 and not args.no_extra and 512 % world == 0:
+        try:
+            extra["edt_slab_c5"] = run_slab_edt(b200, shard, torch, dist, dev, rank, world, local_rank)
+        except Exception as e:  # never let the extra take the headline down
+            extra["edt_slab_c5"] = {"error": repr(e)[:200]}
 
     # ---- cpu_baseline: the oracle on this box's host cores (rank 0, N = 1 only)
     cpu = None
