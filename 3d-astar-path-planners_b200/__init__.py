@@ -300,7 +300,7 @@ class GridMap:
         _ck(lib().b200_map_set_profiling(self.h, 1 if on else 0))
 
     def stage_ms(self):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 16)()
         _ck(lib().b200_map_get_stage_ms(self.h, out))
         return list(out)
 

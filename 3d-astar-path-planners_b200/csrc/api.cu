@@ -61,14 +61,15 @@ struct b200_map {
   void* d_dz;
   int dz_bytes;
   int* d_counts;
+  int4* d_cross;
   uint16_t* d_lut;
   int lut_cap;
   double* d_dk;
   double d_safe;
   bool has_edt;
   bool profiling;
-  cudaEvent_t ev[10];
-  double stage_ms[8];
+  cudaEvent_t ev[12];
+  double stage_ms[16];
   long long launches;
 };
 
@@ -174,6 +175,7 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->d_dz = nullptr;
   m->dz_bytes = 0;
   m->d_counts = nullptr;
+  m->d_cross = nullptr;
   m->d_lut = nullptr;
   m->lut_cap = 0;
   m->has_edt = false;
@@ -198,6 +200,7 @@ int b200_map_destroy(b200_map_t* m) {
   if (m->d_st) cudaFree(m->d_st);
   if (m->d_dz) cudaFree(m->d_dz);
   if (m->d_counts) cudaFree(m->d_counts);
+  if (m->d_cross) cudaFree(m->d_cross);
   if (m->d_lut) cudaFree(m->d_lut);
   cudaFree(m->d_dk);
   cudaFree(m->d_bounds);
@@ -382,7 +385,8 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   if (m->d_dz && m->dz_bytes < dz_bytes) { cudaFree(m->d_dz); m->d_dz = nullptr; }
   const size_t max_lines = (size_t)std::max(m->N[0], m->N[1]) * m->N[2];
   if (!need((void**)&m->d_tmp, nv * 4) || !need((void**)&m->d_st, nv * 8) || !need((void**)&m->d.dist2, nv * 4) ||
-      !need((void**)&m->d_dz, nv * dz_bytes) || !need((void**)&m->d_counts, max_lines * 4))
+      !need((void**)&m->d_dz, nv * dz_bytes) || !need((void**)&m->d_counts, max_lines * 4 * 4) ||
+      !need((void**)&m->d_cross, max_lines * sizeof(int4)))
     return fail(B200_ERR_NOMEM, "distance-field buffers");
   m->dz_bytes = std::max(m->dz_bytes, dz_bytes);
   const int32_t* d_below = below_gap;
@@ -404,9 +408,9 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
       m->lut_cap = lut_n;
     }
   }
-  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, d_below, d_above,
+  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d_cross, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, d_below, d_above,
              m->stream, m->profiling ? &m->ev[3] : nullptr);
-  m->launches += 5 + (lut_n > 0 ? 1 : 0);
+  m->launches += 7 + (lut_n > 0 ? 1 : 0);
   CK(cudaGetLastError());
   if (halo && !on_device) CK(cudaStreamSynchronize(m->stream));  // staging buffer is reused by other calls
   m->has_edt = true;
@@ -483,15 +487,15 @@ int b200_map_set_profiling(b200_map_t* m, int32_t enable) {
   m->profiling = enable != 0;
   return B200_OK;
 }
-int b200_map_get_stage_ms(b200_map_t* m, double out[8]) {
+int b200_map_get_stage_ms(b200_map_t* m, double out[16]) {
   REQUIRE(m && out, "NULL argument");
   CK(cudaSetDevice(m->prm.device));
   CK(cudaStreamSynchronize(m->stream));
-  memset(out, 0, 8 * sizeof(double));
+  memset(out, 0, 16 * sizeof(double));
   float t;
   if (cudaEventElapsedTime(&t, m->ev[0], m->ev[1]) == cudaSuccess) out[0] = t;
   if (cudaEventElapsedTime(&t, m->ev[1], m->ev[2]) == cudaSuccess) out[1] = t;
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 7; ++i)
     if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[2 + i] = t;
   cudaGetLastError();
   return B200_OK;

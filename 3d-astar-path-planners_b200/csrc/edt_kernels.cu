@@ -144,24 +144,31 @@ __device__ __forceinline__ int floor_div_small(int num, int den) {
   return q;
 }
 
-// Stack construction for one line of n sites (Meijster et al. 2000, integer separator):
-// st[k*stride] = (s_k | t_k << 16, g_k) for k = 0..q; returns q.
+// Stack construction (Meijster et al. 2000, integer separator) for the sites [u_begin, u_end) of a line whose
+// domain is [0, n): st[k*stride] = (s_k | t_k << 16, g_k) for k = 0..q; returns q.  `st` points at the band's own
+// stack region and `in` at site u_begin.
+//
+// Bands: a line is cut into B bands scanned by B independent threads (B x the warps: the scan is latency-bound,
+// one line per thread gives only ~14 warps/SM at 512x512x128).  Band b's stack is the lower envelope of ITS sites
+// over the whole domain.  Envelopes of site sets that are ordered left-to-right cross exactly once (the right
+// one's parabolas all have larger abscissae, so E_right - E_left is non-increasing), so a tiny per-line kernel
+// finds the crossover positions and the fill kernel still does one search per site, in the band that owns it.
 constexpr int PF = 4;
 template <class In>
-__device__ __forceinline__ int envelope_scan(In& in, uint2* __restrict__ st, size_t stride, int n) {
+__device__ __forceinline__ int envelope_scan(In& in, uint2* __restrict__ st, size_t stride, int n, int u_begin, int u_end) {
   int q = 0;
-  int sq = 0, tq = 0, sb = 0, tb = 0;  // top entry, entry below it
+  int sq = u_begin, tq = 0, sb = 0, tb = 0;  // top entry, entry below it
   int32_t gq = in.first(), gb = 0;
-  uint2* sp = st;                      // slot of the top entry
-  *sp = make_uint2(pack_st(0, 0), (uint32_t)gq);
-  for (int u0 = 1; u0 < n; u0 += PF) {
+  uint2* sp = st;                            // slot of the top entry
+  *sp = make_uint2(pack_st(u_begin, 0), (uint32_t)gq);
+  for (int u0 = u_begin + 1; u0 < u_end; u0 += PF) {
     int32_t gbuf[PF];
 #pragma unroll
-    for (int j = 0; j < PF; ++j) gbuf[j] = (u0 + j < n) ? in.next() : 0;
+    for (int j = 0; j < PF; ++j) gbuf[j] = (u0 + j < u_end) ? in.next() : 0;
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int u = u0 + j;
-      if (u < n) {
+      if (u < u_end) {
         const int32_t gu = gbuf[j];
         while (q >= 0) {
           const int a = tq - sq, b = tq - u;
@@ -198,24 +205,135 @@ __device__ __forceinline__ int envelope_scan(In& in, uint2* __restrict__ st, siz
   return q;
 }
 
-// pass 1 scan: one thread per (x, z) line along y, input = z distances
+__host__ __device__ inline int band_len(int n, int nb) { return (n + nb - 1) / nb; }
+
+// pass 1 scan: thread (band, line) with line = (x, z) along y; input = z distances
 template <class T>
-__global__ void __launch_bounds__(128) edt_scan_y_kernel(MapDev m, const T* __restrict__ dz, uint2* __restrict__ st, int* __restrict__ counts) {
+__global__ void __launch_bounds__(128) edt_scan_y_kernel(MapDev m, const T* __restrict__ dz, uint2* __restrict__ st, int* __restrict__ counts,
+                                                         int nb) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (l >= (long long)m.Nx * m.Nz) return;
+  const int band = blockIdx.y, bl = band_len(m.Ny, nb);
+  const int u0 = band * bl, u1 = min(m.Ny, u0 + bl);
+  if (u0 >= u1) { counts[l * nb + band] = -1; return; }
   const int x = (int)(l / m.Nz), z = (int)(l % m.Nz);
-  const size_t base = (size_t)x * m.Ny * m.Nz + z;
+  const size_t base = (size_t)x * m.Ny * m.Nz + z + (size_t)u0 * m.Nz;
   DzInput<T> in{dz + base, (size_t)m.Nz};
-  counts[l] = envelope_scan(in, st + base, (size_t)m.Nz, m.Ny);
+  counts[l * nb + band] = envelope_scan(in, st + base, (size_t)m.Nz, m.Ny, u0, u1);
 }
-// pass 2 scan: one thread per (y, z) line along x
+// pass 2 scan: thread (band, line) with line = (y, z) along x
 __global__ void __launch_bounds__(128) edt_scan_x_kernel(MapDev m, const int32_t* __restrict__ in_arr, uint2* __restrict__ st,
-                                                         int* __restrict__ counts) {
+                                                         int* __restrict__ counts, int nb) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long plane = (long long)m.Ny * m.Nz;
   if (l >= plane) return;
-  ArrayInput in{in_arr + l, (size_t)plane};
-  counts[l] = envelope_scan(in, st + l, (size_t)plane, m.Nx);
+  const int band = blockIdx.y, bl = band_len(m.Nx, nb);
+  const int u0 = band * bl, u1 = min(m.Nx, u0 + bl);
+  if (u0 >= u1) { counts[l * nb + band] = -1; return; }
+  ArrayInput in{in_arr + l + (size_t)u0 * plane, (size_t)plane};
+  counts[l * nb + band] = envelope_scan(in, st + l + (size_t)u0 * plane, (size_t)plane, m.Nx, u0, u1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// envelope evaluation and band crossovers
+// ---------------------------------------------------------------------------------------------------
+// index of the stack entry covering site u: largest k in [0, q] with t_k <= u (t_0 == 0)
+__device__ __forceinline__ int covering_entry(const uint2* __restrict__ st, size_t stride, int q, int u) {
+  int lo = 0, hi = q;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int tm = (int)(__ldg(&st[(size_t)mid * stride].x) >> 16);
+    if (tm <= u) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// same, but starting from one end of the stack and galloping: near a band boundary the covering entry of the left
+// band is at (or just below) its top and that of the right band at (or just above) its bottom
+__device__ __forceinline__ int covering_entry_finger(const uint2* __restrict__ st, size_t stride, int q, int u, bool from_top) {
+  auto T = [&](int k) { return (int)(__ldg(&st[(size_t)k * stride].x) >> 16); };
+  int lo, hi;  // invariant: t_lo <= u, and (hi > q or t_hi > u); answer in [lo, hi)
+  if (from_top) {
+    if (T(q) <= u) return q;
+    hi = q; lo = q - 1;
+    int step = 1;
+    while (lo > 0 && T(lo) > u) { hi = lo; lo -= step; step <<= 1; }
+    if (lo < 0) lo = 0;
+  } else {
+    if (q == 0 || T(1) > u) return 0;
+    lo = 1; hi = 2;
+    int step = 1;
+    while (hi <= q && T(hi) <= u) { lo = hi; hi += step; step <<= 1; }
+    if (hi > q + 1) hi = q + 1;
+  }
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (T(mid) <= u) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ long long envelope_at(const uint2* __restrict__ st, size_t stride, int q, int u, bool from_top) {
+  const uint2 e = __ldg(st + (size_t)covering_entry_finger(st, stride, q, u, from_top) * stride);
+  const long long d = u - (int)(e.x & 0xffffu);
+  return d * d + (long long)(int32_t)e.y;
+}
+struct LineBands {  // one line's band stacks + crossovers (nb <= 4)
+  const uint2* st;  // slot of site 0 of the line
+  size_t stride;
+  int n, nb, bl;
+  int q[4];
+  int c01, cmid, c23;  // first site where band 1 beats band 0 / bands {2,3} beat {0,1} / band 3 beats band 2
+  __device__ __forceinline__ int band_of(int u) const {
+    if (nb == 1) return 0;
+    if (nb == 2) return u < c01 ? 0 : 1;
+    return u < cmid ? (u < c01 ? 0 : 1) : (u < c23 ? 2 : 3);
+  }
+  __device__ __forceinline__ const uint2* band_stack(int b) const { return st + (size_t)b * bl * stride; }
+};
+// first u in [0, n] with F_right(u) < F_left(u) (monotone predicate: false ... false true ... true).
+// The crossover of two neighbouring band envelopes is almost always at (or a few sites from) their common
+// boundary b0, so gallop outward from b0 and bisect only the last bracket.
+template <class FL, class FR>
+__device__ __forceinline__ int first_right_wins(int n, int b0, const FL& left, const FR& right) {
+  int lo, hi;  // predicate false at lo (or lo == -1), true at hi (or hi == n)
+  if (b0 < n && right(b0) < left(b0)) {
+    hi = b0; lo = b0 - 1;
+    int step = 1;
+    while (lo >= 0 && right(lo) < left(lo)) { hi = lo; lo -= step; step <<= 1; }
+    if (lo < -1) lo = -1;
+  } else {
+    lo = min(b0, n - 1); hi = lo + 1;
+    int step = 1;
+    while (hi < n && !(right(hi) < left(hi))) { lo = hi; hi += step; step <<= 1; }
+    if (hi > n) hi = n;
+  }
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (right(mid) < left(mid)) hi = mid; else lo = mid;
+  }
+  return hi;
+}
+// thread (line, which): crossover positions c[which] of a line — which = 0: band 1 over band 0; 1: bands {2,3} over
+// bands {0,1}; 2: band 3 over band 2.  The three are independent (the pair envelopes are evaluated as minima).
+// A band that does not exist (counts < 0) never wins.
+__global__ void __launch_bounds__(128) edt_cross_kernel(const uint2* __restrict__ st, const int* __restrict__ counts, int* __restrict__ cross,
+                                                        long long lines, int n, int nb, size_t stride, int line_div, size_t line_mul) {
+  const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (l >= lines) return;
+  const int which = blockIdx.y;
+  // slot of site 0: pass 1 lines are (x,z): x*line_mul + z with line_div = Nz; pass 2 lines are flat (line_div = 0)
+  const size_t base = line_div ? (size_t)(l / line_div) * line_mul + (size_t)(l % line_div) : (size_t)l;
+  const int bl = band_len(n, nb);
+  const int* q = counts + l * nb;
+  const long long kNever = 1LL << 60;
+  auto E = [&](int b, int u, bool from_top) -> long long {
+    return q[b] < 0 ? kNever : envelope_at(st + base + (size_t)b * bl * stride, stride, q[b], u, from_top);
+  };
+  int c = n;
+  if (nb == 2 || which == 0) c = first_right_wins(n, bl, [&](int u) { return E(0, u, true); }, [&](int u) { return E(1, u, false); });
+  else if (which == 2) c = first_right_wins(n, 3 * bl, [&](int u) { return E(2, u, true); }, [&](int u) { return E(3, u, false); });
+  else c = first_right_wins(n, 2 * bl, [&](int u) { return min(E(0, u, true), E(1, u, true)); },
+                            [&](int u) { return min(E(2, u, false), E(3, u, false)); });
+  cross[l * 4 + which] = c;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -223,30 +341,32 @@ __global__ void __launch_bounds__(128) edt_scan_x_kernel(MapDev m, const int32_t
 // ---------------------------------------------------------------------------------------------------
 constexpr int SPT = 8;
 template <class Emit>
-__device__ __forceinline__ void envelope_fill(const uint2* __restrict__ st, size_t stride, int n, int q, int u0, const Emit& emit) {
-  if (u0 >= n) return;
-  int lo = 0, hi = q;  // invariant: t_lo <= u0 (t_0 == 0)
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    const int tm = (int)(__ldg(&st[(size_t)mid * stride].x) >> 16);
-    if (tm <= u0) lo = mid; else hi = mid - 1;
-  }
-  int k = lo;
-  const uint2* ep = st + (size_t)k * stride;
-  uint2 e = __ldg(ep);
-  uint2 en = make_uint2(0u, 0u);
-  int tnext = n;
-  if (k < q) { en = __ldg(ep + stride); tnext = (int)(en.x >> 16); }
+__device__ __forceinline__ void envelope_fill(const LineBands& L, int u0, const Emit& emit) {
+  if (u0 >= L.n) return;
+  int band = -1, k = 0, q = 0, tnext = 0;
+  const uint2* ep = nullptr;
+  uint2 e = make_uint2(0u, 0u), en = make_uint2(0u, 0u);
 #pragma unroll
   for (int j = 0; j < SPT; ++j) {
     const int u = u0 + j;
-    if (u < n) {
+    if (u < L.n) {
+      const int b = L.band_of(u);
+      if (b != band) {  // (re)locate: binary search in the owning band's stack
+        band = b;
+        q = L.q[b];
+        const uint2* bs = L.band_stack(b);
+        k = covering_entry(bs, L.stride, q, u);
+        ep = bs + (size_t)k * L.stride;
+        e = __ldg(ep);
+        tnext = L.n;
+        if (k < q) { en = __ldg(ep + L.stride); tnext = (int)(en.x >> 16); }
+      }
       while (u >= tnext) {  // t is strictly increasing: at most one step per site on average
         ++k;
-        ep += stride;
+        ep += L.stride;
         e = en;
-        tnext = n;
-        if (k < q) { en = __ldg(ep + stride); tnext = (int)(en.x >> 16); }
+        tnext = L.n;
+        if (k < q) { en = __ldg(ep + L.stride); tnext = (int)(en.x >> 16); }
       }
       const int d = u - (int)(e.x & 0xffffu);
       const int32_t v = d * d + (int32_t)e.y;
@@ -254,29 +374,41 @@ __device__ __forceinline__ void envelope_fill(const uint2* __restrict__ st, size
     }
   }
 }
+__device__ __forceinline__ LineBands load_bands(const uint2* st_line, size_t stride, int n, int nb, const int* __restrict__ counts,
+                                                const int4* __restrict__ cross, long long l) {
+  LineBands L;
+  L.st = st_line; L.stride = stride; L.n = n; L.nb = nb; L.bl = band_len(n, nb);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) L.q[b] = b < nb ? __ldg(counts + l * nb + b) : -1;
+  const int4 c = nb > 1 ? __ldg(cross + l) : make_int4(n, n, n, 0);
+  L.c01 = c.x; L.cmid = nb == 4 ? c.y : n; L.c23 = nb == 4 ? c.z : n;
+  return L;
+}
 
 __global__ void __launch_bounds__(128) edt_fill_y_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts,
-                                                         int32_t* __restrict__ out) {
+                                                         const int4* __restrict__ cross, int nb, int32_t* __restrict__ out) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (l >= (long long)m.Nx * m.Nz) return;
   const int x = (int)(l / m.Nz), z = (int)(l % m.Nz);
   const size_t base = (size_t)x * m.Ny * m.Nz + z, stride = (size_t)m.Nz;
   const int u0 = blockIdx.y * SPT;
+  const LineBands L = load_bands(st + base, stride, m.Ny, nb, counts, cross, l);
   int32_t* o = out + base + (size_t)u0 * stride;
-  envelope_fill(st + base, stride, m.Ny, counts[l], u0, [&](int j, int32_t v) { o[(size_t)j * stride] = v; });
+  envelope_fill(L, u0, [&](int j, int32_t v) { o[(size_t)j * stride] = v; });
 }
 
 __global__ void __launch_bounds__(128)
-edt_fill_x_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts, int32_t* __restrict__ out,
-                  uint16_t* __restrict__ costq, const uint16_t* __restrict__ lut, int lut_n) {
+edt_fill_x_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts, const int4* __restrict__ cross, int nb,
+                  int32_t* __restrict__ out, uint16_t* __restrict__ costq, const uint16_t* __restrict__ lut, int lut_n) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long plane = (long long)m.Ny * m.Nz;
   if (l >= plane) return;
   const size_t stride = (size_t)plane;
   const int u0 = blockIdx.y * SPT;
+  const LineBands L = load_bands(st + l, stride, m.Nx, nb, counts, cross, l);
   int32_t* o = out + l + (size_t)u0 * stride;
   uint16_t* c = costq ? costq + l + (size_t)u0 * stride : nullptr;
-  envelope_fill(st + l, stride, m.Nx, counts[l], u0, [&](int j, int32_t v) {
+  envelope_fill(L, u0, [&](int j, int32_t v) {
     o[(size_t)j * stride] = v;
     if (c) c[(size_t)j * stride] = v < lut_n ? __ldg(lut + v) : (uint16_t)0;
   });
@@ -303,11 +435,16 @@ int edt_lut_size(double res, double d_safe) {
 
 // ev (optional): 6 events recorded before z, scan_y, fill_y, scan_x, fill_x and after fill_x
 bool edt_dz_is_wide(const MapDev& m, bool halo) { return m.Nz > 254 || halo; }  // halo: z distances are not bounded by the slab
+int edt_bands(int n) { return n >= 256 ? 4 : (n >= 64 ? 2 : 1); }
 
-void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int32_t* dist2, uint16_t* costq, uint16_t* lut,
-                int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev) {
+// ev (optional): 8 events recorded before z, scan_y, cross_y, fill_y, scan_x, cross_x, fill_x and after fill_x
+void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int4* cross, int32_t* dist2, uint16_t* costq,
+                uint16_t* lut, int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream,
+                cudaEvent_t* ev) {
   const long long lines1 = (long long)m.Nx * m.Nz, lines2 = (long long)m.Ny * m.Nz;
   const unsigned g1 = (unsigned)((lines1 + 127) / 128), g2 = (unsigned)((lines2 + 127) / 128);
+  const int nb1 = edt_bands(m.Ny), nb2 = edt_bands(m.Nx);
+  const dim3 s1(g1, nb1), s2(g2, nb2);
   const dim3 f1(g1, (unsigned)((m.Ny + SPT - 1) / SPT)), f2(g2, (unsigned)((m.Nx + SPT - 1) / SPT));
   const long long words = (long long)m.Nx * m.Ny * m.wz;
   const unsigned gz = (unsigned)((words + 255) / 256);
@@ -317,15 +454,19 @@ void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* coun
   if (wide) edt_z_kernel<uint16_t><<<gz, 256, 0, stream>>>(m, (uint16_t*)dzbuf, below_gap, above_gap);
   else edt_z_kernel<uint8_t><<<gz, 256, 0, stream>>>(m, (uint8_t*)dzbuf, below_gap, above_gap);
   if (ev) cudaEventRecord(ev[1], stream);
-  if (wide) edt_scan_y_kernel<uint16_t><<<g1, 128, 0, stream>>>(m, (const uint16_t*)dzbuf, st, counts);
-  else edt_scan_y_kernel<uint8_t><<<g1, 128, 0, stream>>>(m, (const uint8_t*)dzbuf, st, counts);
+  if (wide) edt_scan_y_kernel<uint16_t><<<s1, 128, 0, stream>>>(m, (const uint16_t*)dzbuf, st, counts, nb1);
+  else edt_scan_y_kernel<uint8_t><<<s1, 128, 0, stream>>>(m, (const uint8_t*)dzbuf, st, counts, nb1);
   if (ev) cudaEventRecord(ev[2], stream);
-  edt_fill_y_kernel<<<f1, 128, 0, stream>>>(m, st, counts, tmp);
+  if (nb1 > 1) edt_cross_kernel<<<dim3(g1, nb1 == 4 ? 3 : 1), 128, 0, stream>>>(st, counts, (int*)cross, lines1, m.Ny, nb1, (size_t)m.Nz, m.Nz, (size_t)m.Ny * m.Nz);
   if (ev) cudaEventRecord(ev[3], stream);
-  edt_scan_x_kernel<<<g2, 128, 0, stream>>>(m, tmp, st, counts);
+  edt_fill_y_kernel<<<f1, 128, 0, stream>>>(m, st, counts, cross, nb1, tmp);
   if (ev) cudaEventRecord(ev[4], stream);
-  edt_fill_x_kernel<<<f2, 128, 0, stream>>>(m, st, counts, dist2, d_safe > 0 ? costq : nullptr, lut, lut_n);
+  edt_scan_x_kernel<<<s2, 128, 0, stream>>>(m, tmp, st, counts, nb2);
   if (ev) cudaEventRecord(ev[5], stream);
+  if (nb2 > 1) edt_cross_kernel<<<dim3(g2, nb2 == 4 ? 3 : 1), 128, 0, stream>>>(st, counts, (int*)cross, lines2, m.Nx, nb2, (size_t)m.Ny * m.Nz, 0, 0);
+  if (ev) cudaEventRecord(ev[6], stream);
+  edt_fill_x_kernel<<<f2, 128, 0, stream>>>(m, st, counts, cross, nb2, dist2, d_safe > 0 ? costq : nullptr, lut, lut_n);
+  if (ev) cudaEventRecord(ev[7], stream);
 }
 
 }  // namespace b200

@@ -19,10 +19,11 @@ void launch_los_batch(const MapDev& m, const double* s, const double* e, long lo
 
 // ---- edt_kernels.cu
 int edt_lut_size(double res, double d_safe);
-// ev (optional): 6 events recorded before z, scan_y, fill_y, scan_x, fill_x and after fill_x
+// ev (optional): 8 events recorded before z, scan_y, cross_y, fill_y, scan_x, cross_x, fill_x and after fill_x
 bool edt_dz_is_wide(const MapDev& m, bool halo);
-void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int32_t* dist2, uint16_t* costq, uint16_t* lut,
-                int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev);
+void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int4* cross, int32_t* dist2, uint16_t* costq,
+                uint16_t* lut, int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream,
+                cudaEvent_t* ev);
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
 
 // ---- search_kernels.cu

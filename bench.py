@@ -240,7 +240,7 @@ def main():
     sampler.start()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage = np.zeros((args.steps, 8))
+    stage = np.zeros((args.steps, 16))
     t_wall = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xff)
@@ -284,16 +284,18 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    st = stage.mean(axis=0)  # [clear, scatter, z, scan_y, fill_y, scan_x, fill_x]
+    st = stage.mean(axis=0)  # [clear, scatter, z, scan_y, cross_y, fill_y, scan_x, cross_x, fill_x]
     # algorithmic bytes per launch (DESIGN.md "Kernels"): what each kernel must move at minimum given its interface
     kernels = {
         "clear(memset)": (st[0], nvox / 8),
         "scatter_kernel": (st[1], 16 * n_pts + nvox / 8),
         "edt_z_kernel": (st[2], nvox / 8 + nvox),                       # read bits, write u8 z distance
-        "edt_scan_y_kernel": (st[3], nvox + 8 * nvox),                  # read u8, write (s,t,g) stack
-        "edt_fill_y_kernel": (st[4], 8 * nvox + 4 * nvox),              # read stack, write d_zy^2
-        "edt_scan_x_kernel": (st[5], 4 * nvox + 8 * nvox),              # read d_zy^2, write stack
-        "edt_fill_x_kernel": (st[6], 8 * nvox + 4 * nvox + 2 * nvox),   # read stack, write dist2 + costq
+        "edt_scan_y_kernel": (st[3], nvox + 8 * nvox),                  # read u8, write (s,t,g) stacks
+        "edt_cross_kernel(y)": (st[4], 0),                              # latency-bound search, no streaming traffic
+        "edt_fill_y_kernel": (st[5], 8 * nvox + 4 * nvox),              # read stacks, write d_zy^2
+        "edt_scan_x_kernel": (st[6], 4 * nvox + 8 * nvox),              # read d_zy^2, write stacks
+        "edt_cross_kernel(x)": (st[7], 0),
+        "edt_fill_x_kernel": (st[8], 8 * nvox + 4 * nvox + 2 * nvox),   # read stacks, write dist2 + costq
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]
@@ -304,7 +306,7 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
         roofline["traffic"] = json.load(open(tr_path)).get(dom)
-    edt_ms = st[2] + st[3] + st[4] + st[5] + st[6]
+    edt_ms = float(st[2:9].sum())
     edt_gbs = (nvox / 8 + 4 * nvox) / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0
 
     # ---- extras: batched query throughput on this map (sharded over ranks, no collective)
@@ -387,7 +389,7 @@ def main():
                        "multi_gpu": "map replicated: every rank rebuilds its replica (value = ms/frame / n_gpus); query batches sharded, no collective"},
             "e2e": {"value": e2e_ms / world, "unit": "ms/frame", "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": 48,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(args.steps * 7), "kernels_per_step": ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_fill_y_kernel", "edt_scan_x_kernel", "edt_fill_x_kernel", "(+1 cudaMemsetAsync clear)"],
+            "gpu_launches": int(args.steps * 9), "kernels_per_step": ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_cross_kernel", "edt_fill_y_kernel", "edt_scan_x_kernel", "edt_cross_kernel", "edt_fill_x_kernel", "(+1 cudaMemsetAsync clear)"],
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line), file=real_stdout, flush=True)

@@ -122,10 +122,10 @@ int b200_los_batch(b200_map_t* map, const double* seg_start_xyz, const double* s
                    uint8_t* visible, int32_t* n_samples, int32_t on_device);
 
 /* Per-stage device times (ms, CUDA events on the map's stream) of the last update_cloud / build_edt when
- * profiling is enabled: [0] clear, [1] scatter, [2] edt z, [3] edt scan y, [4] edt fill y,
- * [5] edt scan x, [6] edt fill x (+cost), [7] reserved. */
+ * profiling is enabled: [0] clear, [1] scatter, [2] edt z, [3] scan y, [4] band crossovers y,
+ * [5] fill y, [6] scan x, [7] band crossovers x, [8] fill x (+cost), [9..15] reserved. */
 int b200_map_set_profiling(b200_map_t* map, int32_t enable);
-int b200_map_get_stage_ms(b200_map_t* map, double out_ms[8]);
+int b200_map_get_stage_ms(b200_map_t* map, double out_ms[16]);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* Planners                                                                                             */
