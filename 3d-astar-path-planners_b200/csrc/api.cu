@@ -676,7 +676,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
 
   // workspace tiers: a small one for the common query, the full allocate_num one for the rare big query
   const int tpb = search_threads_per_block(pl->algo);
-  const int per_sm = pl->faithful ? (tpb == 32 ? 8 : 4) : (tpb == 32 ? 16 : 4);
+  const int per_sm = search_slots_per_sm(pl->algo, pl->faithful);
   int slots0 = m->sm_count * per_sm;
   if ((int64_t)slots0 > nq) slots0 = (int)nq;
   const int cap0 = std::min(pl->prm.allocate_num, 16384);

@@ -86,6 +86,7 @@ inline int open_region_factor(int algo, int faithful) { return (faithful && algo
 inline size_t open_region_entries(int cap, int factor) { return (size_t)factor * (size_t)cap + 32; }
 size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out);
 int search_threads_per_block(int algo);
+int search_slots_per_sm(int algo, int faithful);
 void launch_search(const SearchParams& p, int slots, cudaStream_t st);
 
 }  // namespace b200

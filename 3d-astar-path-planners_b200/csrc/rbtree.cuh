@@ -26,14 +26,32 @@ constexpr uint32_t RB_NIL = 0xffffffffu;
 constexpr uint32_t RB_HEADER = 0u;
 constexpr uint32_t RB_RED = 0x80000000u;
 
+// Storage: pointer chasing at L2 latency (~350 cycles per dependent load) is what bounds this structure, so the
+// first `kt` tree nodes and the first `kf` comparator keys live in SHARED memory (~30 cycles) and only the excess
+// spills to the slot's global workspace.  Tree nodes are allocated lowest-index-first (free list, then bump), so
+// a typical query (a few thousand live entries) never leaves shared memory.
+struct TreeStore {
+  TreeNode* g;   // global part (indexed by the absolute node id)
+  TreeNode* s;   // shared part: ids [0, kt)
+  uint32_t kt;
+  __device__ __forceinline__ TreeNode& operator[](uint32_t x) const { return x < kt ? s[x] : g[x]; }
+};
+struct KeyStore {  // compact copy of NodeRec::f — the comparator's only input
+  double* g;
+  double* s;
+  uint32_t kf;
+  __device__ __forceinline__ double get(uint32_t i) const { return i < kf ? s[i] : g[i]; }
+  __device__ __forceinline__ void set(uint32_t i, double v) const { if (i < kf) s[i] = v; else g[i] = v; }
+};
+
 struct RbSet {
-  TreeNode* t;            // t[0] is the header: parent = root, left = leftmost, right = rightmost
-  const double* fk;       // keys are compared through the nodes' CURRENT f (that is the point); compact copy of NodeRec::f
+  TreeStore t;            // t[0] is the header: parent = root, left = leftmost, right = rightmost
+  KeyStore fk;            // keys are compared through the nodes' CURRENT f (that is the point)
   uint32_t count, top, cap, free_head;
   bool overflow;
 
-  __device__ void init(TreeNode* mem, const double* fkeys, uint32_t capacity) {
-    t = mem; fk = fkeys; cap = capacity;
+  __device__ void init(const TreeStore& mem, const KeyStore& keys, uint32_t capacity) {
+    t = mem; fk = keys; cap = capacity;
     count = 0; top = 1; free_head = RB_NIL; overflow = false;
     t[RB_HEADER].parent = RB_NIL; t[RB_HEADER].left = RB_HEADER; t[RB_HEADER].right = RB_HEADER; t[RB_HEADER].vc = RB_RED;
   }
@@ -48,7 +66,7 @@ struct RbSet {
   // NodeComparator (utils.hpp:52-61): f ascending, then node address — the pool index here (creation order,
   // what a fresh heap gives the reference's per-node `new`)
   __device__ bool key_less(uint32_t a, uint32_t b) const {
-    const double fa = fk[a], fb = fk[b];
+    const double fa = fk.get(a), fb = fk.get(b);
     if (fa != fb) return fa < fb;
     return a < b;
   }

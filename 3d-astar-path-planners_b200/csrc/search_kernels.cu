@@ -528,11 +528,19 @@ struct FShared {
   double new_g[27], new_f[27];
 };
 
+// Shared-memory residency of the tree was measured and rejected (profiles/README.md "faithful"): 96 KB per block
+// leaves 2 blocks/SM and HALVES throughput (thetastar 27k -> 14k q/s) — the kernel is bound by the number of
+// serial instruction streams in flight, not by load latency.  The stores keep the mechanism (sizes 0 = off).
+constexpr uint32_t kFaithfulSmemTree = 0;  // tree nodes (16 B) held in shared memory
+constexpr uint32_t kFaithfulSmemKeys = 0;  // comparator keys (8 B) held in shared memory
+constexpr size_t kFaithfulSmemBytes = kFaithfulSmemTree * sizeof(TreeNode) + kFaithfulSmemKeys * sizeof(double);
+
 template <int ALGO, int NW>
 __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchParams P) {
   constexpr bool IS_THETA = ALGO == ALGO_THETASTAR;
   __shared__ Shared sh;
   __shared__ FShared fs;
+  extern __shared__ __align__(16) unsigned char fsmem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const MapDev& m = P.map;
   Slot s;
@@ -540,7 +548,9 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
   s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
   s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
   s.hmask = P.hcap - 1;
-  double* fk = P.fkey + (size_t)blockIdx.x * P.cap;
+  const KeyStore fk{P.fkey + (size_t)blockIdx.x * P.cap, reinterpret_cast<double*>(fsmem + kFaithfulSmemTree * sizeof(TreeNode)),
+                    kFaithfulSmemKeys};
+  const TreeStore tstore{reinterpret_cast<TreeNode*>(s.heap), reinterpret_cast<TreeNode*>(fsmem), kFaithfulSmemTree};
   RbSet set;  // lane 0 of warp 0 owns the tree; the other lanes only see what it broadcasts
 
   const int la = lane / 9, lb = (lane / 3) % 3, lc = lane % 3;
@@ -571,8 +581,8 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
         n.slot = hash_insert(s, sx, sy, sz, 0);
         s.nodes[0] = n;
-        fk[0] = n.f;
-        set.init(reinterpret_cast<TreeNode*>(s.heap), fk, P.open_entries);
+        fk.set(0u, n.f);
+        set.init(tstore, fk, P.open_entries);
         set.insert(0u);
       }
       __syncwarp();
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
               n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_NEW; n.pad = 0;
               n.slot = hash_insert(s, nx, ny, nz, ni);
               s.nodes[ni] = n;
-              fk[ni] = n.f;
+              fk.set((uint32_t)ni, n.f);
               nb_idx = ni;
             }
             if (oom) {
@@ -722,7 +732,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
             const int fl = fs.flags[k];
             if (!(fl & 1)) continue;
             NodeRec* w = s.nodes + fs.nb_idx[k];
-            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; fk[fs.nb_idx[k]] = fs.new_f[k]; }
+            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; fk.set((uint32_t)fs.nb_idx[k], fs.new_f[k]); }
             if (fl & 4) {
               if (IS_THETA && (fl & 8)) set.erase_key((uint32_t)fs.nb_idx[k]);  // ThetaStar.cpp:80 (key already mutated)
               w->state = NODE_OPEN | (k << 8);
@@ -817,11 +827,23 @@ size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out) {
 }
 
 int search_threads_per_block(int algo) { return algo == ALGO_THETASTAR ? 128 : 32; }
+// workspace slots (= resident thread blocks) per SM.  A thread-per-query variant of faithful A* was measured too:
+// 14x slower per expansion (495 vs 35 us) because SIMT divergence serialises the 32 different queries of a warp.
+int search_slots_per_sm(int algo, int faithful) {
+  (void)faithful;
+  return algo == ALGO_THETASTAR ? 4 : 16;
+}
 
 void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
   if (p.faithful) {
-    if (p.algo == ALGO_THETASTAR) search_faithful_kernel<ALGO_THETASTAR, 4><<<slots, 128, 0, st>>>(p);
-    else search_faithful_kernel<ALGO_ASTAR, 1><<<slots, 32, 0, st>>>(p);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(search_faithful_kernel<ALGO_THETASTAR, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFaithfulSmemBytes);
+      cudaFuncSetAttribute(search_faithful_kernel<ALGO_ASTAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFaithfulSmemBytes);
+      attr_set = true;
+    }
+    if (p.algo == ALGO_THETASTAR) search_faithful_kernel<ALGO_THETASTAR, 4><<<slots, 128, kFaithfulSmemBytes, st>>>(p);
+    else search_faithful_kernel<ALGO_ASTAR, 1><<<slots, 32, kFaithfulSmemBytes, st>>>(p);
     return;
   }
   switch (p.algo) {
