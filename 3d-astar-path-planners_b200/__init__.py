@@ -19,7 +19,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200planner.so")
 
-ALGORITHMS = ("astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar")
+ALGORITHMS = ("astar", "thetastar", "thetastaragr", "thetastaragrpp", "lazythetastar", "costastar", "costlazythetastar")
+# thetastaragr/* defaults of launch/planner.launch:71-77
+AGR_DEFAULTS = dict(barrier=2.0, flying_cost=10.0, flying_cost_default=0.0, ground_judge=0.1, epsilon=0.1)
 STATUS_NAMES = {0: "solved", 1: "open_set_empty", 2: "pool_exhausted", 3: "tier_overflow", 4: "open_list_full"}
 SEMANTICS = {"default": 0, "canonical": 1, "faithful": 2}
 
@@ -36,7 +38,9 @@ class MapParams(C.Structure):
 
 class PlannerParams(C.Structure):
     _fields_ = [("resolution", C.c_double), ("lambda_heuristic", C.c_double), ("allocate_num", C.c_int32),
-                ("semantics", C.c_int32), ("cost_weight", C.c_double), ("max_los", C.c_double)]
+                ("semantics", C.c_int32), ("cost_weight", C.c_double), ("max_los", C.c_double),
+                ("agr_barrier", C.c_double), ("agr_flying_cost", C.c_double), ("agr_flying_cost_default", C.c_double),
+                ("agr_ground_judge", C.c_double), ("agr_epsilon", C.c_double)]
 
 
 RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("open_peak", "i4"), ("path_offset", "i8"),
@@ -310,11 +314,13 @@ class Planner:
     detectCollision / findPath / getPath, plus the batched `findPaths`."""
 
     def __init__(self, algorithm="astar", resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0,
-                 max_los=0.0, semantics="default"):
+                 max_los=0.0, semantics="default", **agr):
         """semantics: "faithful" (bit-identical to the reference's std::set behaviour; astar/thetastar only),
         "canonical" (exact priority queue, faster), "default" (faithful where the reference has the algorithm)."""
+        a = dict(AGR_DEFAULTS, **agr)
         p = PlannerParams(float(resolution), float(lambda_heuristic), int(allocate_num), SEMANTICS[semantics],
-                          float(cost_weight), float(max_los))
+                          float(cost_weight), float(max_los), a["barrier"], a["flying_cost"], a["flying_cost_default"],
+                          a["ground_judge"], a["epsilon"])
         self.h = C.c_void_p()
         _ck(lib().b200_planner_create(algorithm.encode(), C.byref(p), C.byref(self.h)))
         self.algorithm = algorithm if algorithm in ALGORITHMS else "astar"

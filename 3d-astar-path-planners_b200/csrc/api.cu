@@ -598,14 +598,17 @@ int b200_planner_create(const char* algorithm, const b200_planner_params_t* p, b
   else if (a == "lazythetastar") pl->algo = ALGO_LAZYTHETASTAR;
   else if (a == "costastar") pl->algo = ALGO_COSTASTAR;
   else if (a == "costlazythetastar") pl->algo = ALGO_COSTLAZYTHETASTAR;
+  else if (a == "thetastaragr") pl->algo = ALGO_THETASTARAGR;
+  else if (a == "thetastaragrpp") pl->algo = ALGO_THETASTARAGRPP;
   else pl->algo = ALGO_ASTAR;
   pl->name = pl->algo == ALGO_ASTAR ? "astar" : a;
   pl->prm = *p;
   // semantics: the two algorithms the reference implements default to its exact (rb-tree) behaviour
-  const bool has_reference = pl->algo == ALGO_ASTAR || pl->algo == ALGO_THETASTAR;
-  if (p->semantics == B200_SEMANTICS_FAITHFUL && !has_reference) {
+  const bool has_reference = pl->algo == ALGO_ASTAR || pl->algo == ALGO_THETASTAR || pl->algo == ALGO_THETASTARAGR;
+  const bool same_either_way = pl->algo == ALGO_THETASTARAGRPP;  // keys are never re-written inside the set
+  if (p->semantics == B200_SEMANTICS_FAITHFUL && !has_reference && !same_either_way) {
     delete pl;
-    return fail(B200_ERR_UNSUPPORTED, "b200_planner_create: faithful semantics exist only for astar / thetastar");
+    return fail(B200_ERR_UNSUPPORTED, "b200_planner_create: faithful semantics exist only for astar / thetastar / thetastaragr(pp)");
   }
   if (p->semantics < 0 || p->semantics > 2) { delete pl; return fail(B200_ERR_INVALID, "b200_planner_create: bad semantics"); }
   if (p->semantics == B200_SEMANTICS_FAITHFUL && p->max_los > 0) {
@@ -715,6 +718,9 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   P.tie = 1.0 + 1.0 / 10000;  // AStar.cpp:40
   P.cost_weight = pl->prm.cost_weight;
   P.max_los = pl->prm.max_los;
+  P.agr_barrier = pl->prm.agr_barrier; P.agr_flying_cost = pl->prm.agr_flying_cost;
+  P.agr_flying_cost_default = pl->prm.agr_flying_cost_default; P.agr_ground_judge = pl->prm.agr_ground_judge;
+  P.agr_epsilon = pl->prm.agr_epsilon;
   for (int i = 0; i < 3; ++i) P.dv[i] = pl->dv[i];
   P.allocate_num = pl->prm.allocate_num;
   P.algo = pl->algo;

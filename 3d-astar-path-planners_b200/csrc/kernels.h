@@ -27,7 +27,8 @@ void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* coun
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
 
 // ---- search_kernels.cu
-enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4 };
+enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4,
+            ALGO_THETASTARAGR = 5, ALGO_THETASTARAGRPP = 6 };
 enum { ST_SOLVED = 0, ST_OPEN_EMPTY = 1, ST_POOL_EXHAUSTED = 2, ST_TIER_OVERFLOW = 3, ST_OPEN_LIST_FULL = 4 };
 
 // Per-slot search workspace in HBM (one slot per resident thread block; SoA of slots, AoS inside):
@@ -41,9 +42,11 @@ struct __align__(16) NodeRec {
   int parent;     // node index or -1
   int hpos;       // heap position, -1 when not in the open list
   uint32_t slot;  // hash slot (for O(used) clearing)
-  int via;        // lazy variants: expanded node that last relaxed this one
-  int state;      // low byte: NODE_*; next byte: via direction code (0..26)
-  int pad;
+  int state;      // low byte: NODE_*; next byte: via direction code (0..26); bit 16: AGR motion_state (flying)
+  union {
+    struct { int via; int pad; };  // lazy variants: expanded node that last relaxed this one
+    double penalty;                // thetastaragr: penalty_g_score carried in g (utils.hpp:28)
+  };
 };
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte record");
 struct __align__(16) HeapEnt {
@@ -55,6 +58,7 @@ struct __align__(16) HeapEnt {
 struct SearchParams {
   MapDev map;
   double r, lambda, tie, cost_weight, max_los;
+  double agr_barrier, agr_flying_cost, agr_flying_cost_default, agr_ground_judge, agr_epsilon;  // thetastaragr/*
   double dv[3];
   int allocate_num;
   int algo;

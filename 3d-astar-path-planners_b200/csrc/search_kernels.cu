@@ -158,9 +158,65 @@ __device__ __forceinline__ double edge_cost(const SearchParams& P, double ax, do
   return dadd(len, dmul(P.cost_weight, dmul(len, __ddiv_rn(dadd(qa, qb), 131070.0))));
 }
 
+// ---- thetastaragr / thetastaragrpp (the fork's air-ground planners) -----------------------------------------
+constexpr int kMotionBit = 1 << 16;
+// start node: ThetaStarAGR.cpp:141-155 / ThetaStarAGRpp.cpp:146-155 (f was computed from the UNclamped position)
+template <bool AGR>
+__device__ __forceinline__ void agr_init_start(const SearchParams& P, NodeRec& n) {
+  if (n.pz < 0) n.pz = 0;
+  if (n.pz >= P.agr_ground_judge) {
+    if (AGR) {
+      const double pen = dadd(__ddiv_rn(dmul(P.agr_flying_cost, n.pz), P.agr_barrier), P.agr_flying_cost_default);
+      n.g = dadd(n.g, pen);
+      n.f = dadd(n.f, pen);
+      n.penalty = pen;
+    }
+    n.state |= kMotionBit;
+  } else if (AGR) {
+    n.penalty = 0.0;
+  }
+}
+__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }  // std::max: NaN in `a` survives
+struct AgrCand { double g, pen; int parent; bool motion; };
+// ThetaStarAGR::ComputeCost (ThetaStarAGR.cpp:49-103): candidate the guard `< neighbor->g_score` is applied to
+__device__ __forceinline__ AgrCand agr_candidate(const SearchParams& P, double cg, double cpen, int cur, int cpar, bool vis, double pg,
+                                                 double ppen, double pdist, double dnorm, double nz) {
+  AgrCand c;
+  c.motion = nz >= P.agr_ground_judge;
+  c.pen = c.motion ? dadd(__ddiv_rn(dmul(P.agr_flying_cost, nz), P.agr_barrier), P.agr_flying_cost_default) : 0.0;
+  double t = dsub(dadd(cg, dnorm), cpen);
+  if (c.motion) t = dadd(t, c.pen);
+  c.g = t; c.parent = cur;
+  if (cpar >= 0 && vis) {
+    double u = dsub(dadd(pg, pdist), ppen);
+    if (c.motion) u = dadd(u, c.pen);
+    c.g = u; c.parent = cpar;
+  }
+  return c;
+}
+// ThetaStarAGRpp::ComputeCost (ThetaStarAGRpp.cpp:52-109)
+__device__ __forceinline__ AgrCand agrpp_candidate(const SearchParams& P, double cg, double cz, bool cmotion, int cur, int cpar, bool vis,
+                                                   double pg, double pz, bool pmotion, double pdist, double dnorm, double nz) {
+  AgrCand c;
+  c.motion = nz >= P.agr_ground_judge;
+  c.pen = 0.0;
+  const double alpha = std_max(dadd(1.0, __ddiv_rn(dmul(P.agr_flying_cost, dsub(nz, cz)), nz)), P.agr_epsilon);
+  double t = dadd(cg, dmul(dnorm, (c.motion || cmotion) ? alpha : P.agr_epsilon));
+  if (!cmotion && c.motion) t = dadd(t, P.agr_flying_cost_default);
+  c.g = t; c.parent = cur;
+  if (cpar >= 0 && vis) {
+    const double al = std_max(dadd(1.0, __ddiv_rn(dmul(P.agr_flying_cost, dsub(nz, pz)), nz)), P.agr_epsilon);
+    double u = dadd(pg, dmul(pdist, (c.motion || pmotion) ? al : P.agr_epsilon));
+    if (!pmotion && c.motion) u = dadd(u, P.agr_flying_cost_default);
+    if (u < c.g) { c.g = u; c.parent = cpar; }
+  }
+  return c;
+}
+
 template <int ALGO, int NW>
 __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
-  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR;
+  constexpr bool IS_AGR = ALGO == ALGO_THETASTARAGR, IS_AGRPP = ALGO == ALGO_THETASTARAGRPP;
+  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR || IS_AGR || IS_AGRPP;  // one fastLOS per generated neighbour
   constexpr bool IS_LAZY = ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
   constexpr bool IS_COST = ALGO == ALGO_COSTASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
   __shared__ Shared sh;
@@ -201,7 +257,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
         n.g = 0.0;
         n.f = dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, sx), dsub(gy, sy), dsub(gz, sz))));
         n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
-        n.slot = hash_insert(s, sx, sy, sz, 0);
+        if (IS_AGR || IS_AGRPP) agr_init_start<IS_AGR>(P, n);
+        n.slot = hash_insert(s, n.px, n.py, n.pz, 0);
         s.nodes[0] = n;
       }
       __syncwarp();
@@ -211,7 +268,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
 
     // ---------------- search loop (AStar.cpp:103-173) ----------------
     int cur = 0;
-    double cx = 0, cy = 0, cz = 0, cg = 0;
+    double cx = 0, cy = 0, cz = 0, cg = 0, cpen = 0;
+    bool cmotion = false;
     int cpar = -1;
     // per-lane neighbour state, live between the phases of one expansion
     int nb_idx = -1;
@@ -285,6 +343,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
             }
           }
           cx = c.px; cy = c.py; cz = c.pz; cg = c.g; cpar = c.parent;
+          if (IS_AGR) cpen = c.penalty;
+          if (IS_AGR || IS_AGRPP) cmotion = (c.state & kMotionBit) != 0;
           // termination (AStar.cpp:110-119)
           if (fabs(dsub(cx, gx)) <= P.r && fabs(dsub(cy, gy)) <= P.r && fabs(dsub(cz, gz)) <= P.r) {
             status = ST_SOLVED; last = cur; term = cur; done = true;
@@ -302,6 +362,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
           if (valid) {
             nb_idx = hash_find(s, nx, ny, nz);                                   // :146
             if (nb_idx >= 0 && (s.nodes[nb_idx].state & 0xff) == NODE_CLOSED) valid = false;  // :147
+            if (IS_AGRPP && nb_idx >= 0) valid = false;  // ThetaStarAGRpp.cpp:208-210: a node is relaxed once, at creation
           }
           if (valid && inflate_occ(m, nx, ny, nz) == 1) valid = false;          // :151
           const bool need = valid && nb_idx < 0;
@@ -388,7 +449,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
       // ---- UpdateVertex (AStar.cpp:65-78 / ThetaStar.cpp:37-89), control warp ----
       if (warp == 0) {
         bool improved = false;
-        double new_g = 0, new_f = 0;
+        double new_g = 0, new_f = 0, new_pen = 0;
+        bool new_motion = false;
         if (valid) {
           const NodeRec nb = s.nodes[nb_idx];
           int new_parent = cur;
@@ -397,7 +459,18 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
             los_samples += sh.nsamp[lane];
             use_parent = sh.vis[lane] != 0;
           }
-          if (IS_THETA && use_parent) {  // ThetaStar.cpp:51-60
+          if (IS_AGR || IS_AGRPP) {
+            double pg = 0, ppen = 0, ppz = 0, pdist = 0;
+            bool pmotion = false;
+            if (cpar >= 0) {
+              const NodeRec pr = s.nodes[cpar];
+              pg = pr.g; ppen = pr.penalty; ppz = pr.pz; pmotion = (pr.state & kMotionBit) != 0;
+              pdist = norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz));
+            }
+            const AgrCand cand = IS_AGR ? agr_candidate(P, cg, cpen, cur, cpar, use_parent, pg, ppen, pdist, dnorm, nz)
+                                        : agrpp_candidate(P, cg, cz, cmotion, cur, cpar, use_parent, pg, ppz, pmotion, pdist, dnorm, nz);
+            new_g = cand.g; new_parent = cand.parent; new_pen = cand.pen; new_motion = cand.motion;
+          } else if (IS_THETA && use_parent) {  // ThetaStar.cpp:51-60
             const NodeRec pr = s.nodes[cpar];
             const double dist = norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz));
             new_g = dadd(pr.g, dist);
@@ -415,8 +488,9 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
             new_f = dadd(new_g, dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, nx), dsub(gy, ny), dsub(gz, nz)))));
             NodeRec* w = s.nodes + nb_idx;
             w->g = new_g; w->f = new_f; w->parent = new_parent;
-            w->state = NODE_OPEN | (lane << 8);
+            w->state = NODE_OPEN | (lane << 8) | (new_motion ? kMotionBit : 0);
             if (IS_LAZY) w->via = cur;
+            if (IS_AGR) w->penalty = new_pen;
           }
         }
         __syncwarp();
@@ -524,8 +598,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
 struct FShared {
   int nb_idx[27];
   int new_parent[27];
-  int flags[27];  // bit0 reaches UpdateVertex, bit1 write node, bit2 improved (g < old g), bit3 was IN_OPEN_SET
-  double new_g[27], new_f[27];
+  int flags[27];  // bit0 reaches UpdateVertex, bit1 write node, bit2 improved (g < old g), bit3 was IN_OPEN_SET, bit4 flying
+  double new_g[27], new_f[27], new_pen[27];
 };
 
 // Shared-memory residency of the tree was measured and rejected (profiles/README.md "faithful"): 96 KB per block
@@ -537,7 +611,8 @@ constexpr size_t kFaithfulSmemBytes = kFaithfulSmemTree * sizeof(TreeNode) + kFa
 
 template <int ALGO, int NW>
 __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchParams P) {
-  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR;
+  constexpr bool IS_AGR = ALGO == ALGO_THETASTARAGR;
+  constexpr bool IS_THETA = ALGO == ALGO_THETASTAR || IS_AGR;
   __shared__ Shared sh;
   __shared__ FShared fs;
   extern __shared__ __align__(16) unsigned char fsmem[];
@@ -579,7 +654,8 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         n.g = 0.0;
         n.f = dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, sx), dsub(gy, sy), dsub(gz, sz))));
         n.parent = -1; n.hpos = -1; n.via = -1; n.state = NODE_OPEN; n.pad = 0;
-        n.slot = hash_insert(s, sx, sy, sz, 0);
+        if (IS_AGR) agr_init_start<true>(P, n);
+        n.slot = hash_insert(s, n.px, n.py, n.pz, 0);
         s.nodes[0] = n;
         fk.set(0u, n.f);
         set.init(tstore, fk, P.open_entries);
@@ -590,7 +666,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
     }
 
     int cur = 0;
-    double cx = 0, cy = 0, cz = 0, cg = 0;
+    double cx = 0, cy = 0, cz = 0, cg = 0, cpen = 0;
     int cpar = -1;
     int nb_idx = -1;
     double nx = 0, ny = 0, nz = 0;
@@ -611,6 +687,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
           cur = popped;
           const NodeRec c = s.nodes[cur];
           cx = c.px; cy = c.py; cz = c.pz; cg = c.g; cpar = c.parent;
+          if (IS_AGR) cpen = c.penalty;
           if (fabs(dsub(cx, gx)) <= P.r && fabs(dsub(cy, gy)) <= P.r && fabs(dsub(cz, gz)) <= P.r) {  // :110-119
             status = ST_SOLVED; last = cur; term = cur; done = true;
           }
@@ -700,7 +777,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
       if (warp == 0) {
         // ---- candidates, one lane per neighbour (pure functions of cur / parent(cur) / the neighbour's own record)
         int flags = 0, new_parent = cur;
-        double new_g = 0, new_f = 0;
+        double new_g = 0, new_f = 0, new_pen = 0;
         if (valid) {
           const NodeRec nb = s.nodes[nb_idx];
           flags = 1 | (((nb.state & 0xff) == NODE_OPEN) ? 8 : 0);
@@ -709,7 +786,17 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
             los_samples += sh.nsamp[lane];
             use_parent = sh.vis[lane] != 0;
           }
-          if (IS_THETA && use_parent) {
+          if (IS_AGR) {
+            double pg = 0, ppen = 0, pdist = 0;
+            if (cpar >= 0) {
+              const NodeRec pr = s.nodes[cpar];
+              pg = pr.g; ppen = pr.penalty;
+              pdist = norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz));
+            }
+            const AgrCand cand = agr_candidate(P, cg, cpen, cur, cpar, use_parent, pg, ppen, pdist, dnorm, nz);
+            new_g = cand.g; new_parent = cand.parent; new_pen = cand.pen;
+            if (cand.motion) flags |= 16;
+          } else if (IS_THETA && use_parent) {
             const NodeRec pr = s.nodes[cpar];
             new_g = dadd(pr.g, norm3(dsub(pr.px, nx), dsub(pr.py, ny), dsub(pr.pz, nz)));
             new_parent = cpar;
@@ -724,6 +811,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         if (lane < 27) {
           fs.nb_idx[lane] = nb_idx; fs.new_parent[lane] = new_parent; fs.flags[lane] = flags;
           fs.new_g[lane] = new_g; fs.new_f[lane] = new_f;
+          if (IS_AGR) fs.new_pen[lane] = new_pen;
         }
         __syncwarp();
         // ---- sequential replay in the reference's neighbour order (lane 0 owns the tree)
@@ -732,10 +820,13 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
             const int fl = fs.flags[k];
             if (!(fl & 1)) continue;
             NodeRec* w = s.nodes + fs.nb_idx[k];
-            if (fl & 2) { w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; fk.set((uint32_t)fs.nb_idx[k], fs.new_f[k]); }
+            if (fl & 2) {
+              w->parent = fs.new_parent[k]; w->g = fs.new_g[k]; w->f = fs.new_f[k]; fk.set((uint32_t)fs.nb_idx[k], fs.new_f[k]);
+              if (IS_AGR) { w->penalty = fs.new_pen[k]; w->state = (w->state & ~kMotionBit) | ((fl & 16) ? kMotionBit : 0); }
+            }
             if (fl & 4) {
               if (IS_THETA && (fl & 8)) set.erase_key((uint32_t)fs.nb_idx[k]);  // ThetaStar.cpp:80 (key already mutated)
-              w->state = NODE_OPEN | (k << 8);
+              w->state = NODE_OPEN | (k << 8) | (w->state & kMotionBit);
               set.insert((uint32_t)fs.nb_idx[k]);                                 // AStar.cpp:71-76 / ThetaStar.cpp:81-86
             }
           }
@@ -826,12 +917,13 @@ size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out) {
   return (size_t)cap * (sizeof(NodeRec) + sizeof(double)) + (size_t)h * 4 + open_region_entries(cap, open_factor) * sizeof(HeapEnt);
 }
 
-int search_threads_per_block(int algo) { return algo == ALGO_THETASTAR ? 128 : 32; }
+static inline bool algo_has_los_phase(int algo) { return algo == ALGO_THETASTAR || algo == ALGO_THETASTARAGR || algo == ALGO_THETASTARAGRPP; }
+int search_threads_per_block(int algo) { return algo_has_los_phase(algo) ? 128 : 32; }
 // workspace slots (= resident thread blocks) per SM.  A thread-per-query variant of faithful A* was measured too:
 // 14x slower per expansion (495 vs 35 us) because SIMT divergence serialises the 32 different queries of a warp.
 int search_slots_per_sm(int algo, int faithful) {
   (void)faithful;
-  return algo == ALGO_THETASTAR ? 4 : 16;
+  return algo_has_los_phase(algo) ? 4 : 16;
 }
 
 void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
@@ -843,6 +935,7 @@ void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
       attr_set = true;
     }
     if (p.algo == ALGO_THETASTAR) search_faithful_kernel<ALGO_THETASTAR, 4><<<slots, 128, kFaithfulSmemBytes, st>>>(p);
+    else if (p.algo == ALGO_THETASTARAGR) search_faithful_kernel<ALGO_THETASTARAGR, 4><<<slots, 128, kFaithfulSmemBytes, st>>>(p);
     else search_faithful_kernel<ALGO_ASTAR, 1><<<slots, 32, kFaithfulSmemBytes, st>>>(p);
     return;
   }
@@ -851,6 +944,8 @@ void launch_search(const SearchParams& p, int slots, cudaStream_t st) {
     case ALGO_THETASTAR: search_kernel<ALGO_THETASTAR, 4><<<slots, 128, 0, st>>>(p); break;
     case ALGO_LAZYTHETASTAR: search_kernel<ALGO_LAZYTHETASTAR, 1><<<slots, 32, 0, st>>>(p); break;
     case ALGO_COSTASTAR: search_kernel<ALGO_COSTASTAR, 1><<<slots, 32, 0, st>>>(p); break;
+    case ALGO_THETASTARAGR: search_kernel<ALGO_THETASTARAGR, 4><<<slots, 128, 0, st>>>(p); break;
+    case ALGO_THETASTARAGRPP: search_kernel<ALGO_THETASTARAGRPP, 4><<<slots, 128, 0, st>>>(p); break;
     default: search_kernel<ALGO_COSTLAZYTHETASTAR, 1><<<slots, 32, 0, st>>>(p); break;
   }
 }

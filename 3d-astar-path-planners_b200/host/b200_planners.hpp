@@ -34,11 +34,17 @@ class AlgorithmBase {
   }
   // <algo>/resolution, time_resolution, lambda_heuristic, allocate_num (AStar.cpp:31-41, ThetaStar.cpp:25-35)
   virtual void setParam(const ParamMap& nh) {
-    const std::string ns = algorithm_name_ + "/";
+    const std::string ns = (algorithm_name_ == "thetastaragrpp" ? std::string("thetastaragr") : algorithm_name_) + "/";
     nh.param(ns + "resolution", prm_.resolution, -1.0);
     nh.param(ns + "lambda_heuristic", prm_.lambda_heuristic, -1.0);
     nh.param(ns + "allocate_num", prm_.allocate_num, -1);
     nh.param(ns + "max_line_of_sight_distance", prm_.max_los, 0.0);
+    // both air-ground variants read the thetastaragr/ namespace (ThetaStarAGR.cpp:33-36, ThetaStarAGRpp.cpp:28-37)
+    nh.param(std::string("thetastaragr/barrier"), prm_.agr_barrier, 0.0);
+    nh.param(std::string("thetastaragr/flying_cost"), prm_.agr_flying_cost, 0.0);
+    nh.param(std::string("thetastaragr/flying_cost_default"), prm_.agr_flying_cost_default, 0.0);
+    nh.param(std::string("thetastaragr/ground_judge"), prm_.agr_ground_judge, 0.0);
+    nh.param(std::string("thetastaragr/epsilon"), prm_.agr_epsilon, 0.0);
     double sem = 0;
     nh.param(ns + "semantics", sem, 0.0);
     prm_.semantics = (int32_t)sem;
@@ -139,6 +145,8 @@ class ThetaStar : public AStar {
   ThetaStar() : AStar("thetastar") {}
   explicit ThetaStar(std::string name) : AStar(name) {}
 };
+class ThetaStarAGR : public ThetaStar { public: ThetaStarAGR() : ThetaStar("thetastaragr") {} };
+class ThetaStarAGRpp : public ThetaStar { public: ThetaStarAGRpp() : ThetaStar("thetastaragrpp") {} };
 class LazyThetaStar : public ThetaStar { public: LazyThetaStar() : ThetaStar("lazythetastar") {} };
 class CostAStar : public AStar { public: CostAStar() : AStar("costastar") {} };
 class CostLazyThetaStar : public ThetaStar { public: CostLazyThetaStar() : ThetaStar("costlazythetastar") {} };

@@ -16,16 +16,20 @@ int main(int argc, char** argv) {
     nh.num["grid_map/resolution"] = 0.1;
     nh.num["grid_map/map_size_x"] = 12.8; nh.num["grid_map/map_size_y"] = 12.8; nh.num["grid_map/map_size_z"] = 3.2;
     nh.num["grid_map/local_update_range_x"] = 100; nh.num["grid_map/local_update_range_y"] = 100; nh.num["grid_map/local_update_range_z"] = 100;
-    for (const char* a : {"astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar"}) {
+    for (const char* a : {"astar", "thetastar", "thetastaragr", "lazythetastar", "costastar", "costlazythetastar"}) {
       nh.num[std::string(a) + "/resolution"] = 0.1;
       nh.num[std::string(a) + "/lambda_heuristic"] = 5.0;
       nh.num[std::string(a) + "/allocate_num"] = 100000;
     }
+    nh.num["thetastaragr/barrier"] = 2.0; nh.num["thetastaragr/flying_cost"] = 10.0; nh.num["thetastaragr/flying_cost_default"] = 0.0;
+    nh.num["thetastaragr/ground_judge"] = 0.1; nh.num["thetastaragr/epsilon"] = 0.1;   // launch/planner.launch:71-77
     // configureAlgorithm (planner_ros_node.cpp:261-296)
     std::unique_ptr<Planners::AlgorithmBase> algorithm;
     const std::string name(algo);
     if (name == "astar") algorithm.reset(new Planners::AStar());
     else if (name == "thetastar") algorithm.reset(new Planners::ThetaStar());
+    else if (name == "thetastaragr") algorithm.reset(new Planners::ThetaStarAGR());
+    else if (name == "thetastaragrpp") algorithm.reset(new Planners::ThetaStarAGRpp());
     else if (name == "lazythetastar") algorithm.reset(new Planners::LazyThetaStar());
     else if (name == "costastar") algorithm.reset(new Planners::CostAStar());
     else if (name == "costlazythetastar") algorithm.reset(new Planners::CostLazyThetaStar());

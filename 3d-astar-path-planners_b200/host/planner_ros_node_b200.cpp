@@ -97,13 +97,20 @@ class HeuristicPlannerROS {
       double v;
       if (lnh_.getParam(k, v)) nh.num[k] = v;
     }
-    for (const char* a : {"astar", "thetastar", "lazythetastar", "costastar", "costlazythetastar"})
+    for (const char* k : {"thetastaragr/barrier", "thetastaragr/flying_cost", "thetastaragr/flying_cost_default",
+                          "thetastaragr/ground_judge", "thetastaragr/epsilon"}) {
+      double v;
+      if (lnh_.getParam(k, v)) nh.num[k] = v;
+    }
+    for (const char* a : {"astar", "thetastar", "thetastaragr", "lazythetastar", "costastar", "costlazythetastar"})
       for (const char* k : {"resolution", "lambda_heuristic", "allocate_num", "max_line_of_sight_distance", "semantics"}) {
         double v; int iv;
         const std::string key = std::string(a) + "/" + k;
         if (lnh_.getParam(key, v)) nh.num[key] = v; else if (lnh_.getParam(key, iv)) nh.num[key] = iv;
       }
     if (algorithm_name == "thetastar") algorithm_.reset(new Planners::ThetaStar());
+    else if (algorithm_name == "thetastaragr") algorithm_.reset(new Planners::ThetaStarAGR());
+    else if (algorithm_name == "thetastaragrpp") algorithm_.reset(new Planners::ThetaStarAGRpp());
     else if (algorithm_name == "lazythetastar") algorithm_.reset(new Planners::LazyThetaStar());
     else if (algorithm_name == "costastar") algorithm_.reset(new Planners::CostAStar());
     else if (algorithm_name == "costlazythetastar") algorithm_.reset(new Planners::CostLazyThetaStar());

@@ -139,7 +139,9 @@ int b200_map_get_stage_ms(b200_map_t* map, double out_ms[16]);
  *             (AStar.cpp:56-78, ThetaStar.cpp:72-89, utils.hpp:52-61).  astar / thetastar only.
  *  CANONICAL: exact priority queue on (f, creation index), true decrease-key, guarded relaxations — the clean
  *             semantics of SURVEY Appendix B; several times faster; the only one for the extension algorithms.
- *  DEFAULT  : FAITHFUL for astar / thetastar, CANONICAL otherwise. */
+ *  DEFAULT  : FAITHFUL for astar / thetastar / thetastaragr, CANONICAL otherwise.  thetastaragrpp relaxes every node
+ *             exactly once (ThetaStarAGRpp.cpp:208-210), so its keys never change inside the set and the two semantics
+ *             coincide: it always runs the (faster) canonical open list and is still identical to the reference. */
 enum { B200_SEMANTICS_DEFAULT = 0, B200_SEMANTICS_CANONICAL = 1, B200_SEMANTICS_FAITHFUL = 2 };
 
 typedef struct {
@@ -149,6 +151,9 @@ typedef struct {
   int32_t semantics;        /* B200_SEMANTICS_* */
   double cost_weight;       /* cost-aware variants only */
   double max_los;           /* <= 0: unlimited */
+  /* thetastaragr/{barrier, flying_cost, flying_cost_default, ground_judge, epsilon} — read by BOTH air-ground
+   * variants (src/Planners/ThetaStarAGR.cpp:33-36, ThetaStarAGRpp.cpp:33-37; launch/planner.launch:71-77) */
+  double agr_barrier, agr_flying_cost, agr_flying_cost_default, agr_ground_judge, agr_epsilon;
 } b200_planner_params_t;
 
 /* AlgorithmBase::createResultDataObject (src/Planners/AlgorithmBase.cpp:123-175) as a plain struct. */
@@ -170,8 +175,8 @@ typedef struct {
   double time_us;           /* "time_spent": device time of this query (the reference reports 0) */
 } b200_path_result_t;
 
-/* algorithm: "astar", "thetastar" (reference, src/planner_ros_node.cpp:261-285), and the north-star
- * extensions "lazythetastar", "costastar", "costlazythetastar".  Unknown names fall back to "astar" exactly
+/* algorithm: "astar", "thetastar", "thetastaragr", "thetastaragrpp" (the four the reference dispatches,
+ * src/planner_ros_node.cpp:261-285), and the north-star extensions "lazythetastar", "costastar", "costlazythetastar".  Unknown names fall back to "astar" exactly
  * like planner_ros_node.cpp:280-284.  ≡ new AStar()/ThetaStar() + setParam() + init(). */
 int b200_planner_create(const char* algorithm, const b200_planner_params_t* params, b200_planner_t** out);
 int b200_planner_destroy(b200_planner_t* planner);

@@ -310,7 +310,7 @@ static inline uint16_t costq_from_cost(float c) { return (uint16_t)(c * 65535.0f
 // ------------------------------------------------------------------------------------------
 // Planner restatement
 // ------------------------------------------------------------------------------------------
-enum Algo { ASTAR = 0, THETASTAR = 1, LAZYTHETASTAR = 2, COSTASTAR = 3, COSTLAZYTHETASTAR = 4 };
+enum Algo { ASTAR = 0, THETASTAR = 1, LAZYTHETASTAR = 2, COSTASTAR = 3, COSTLAZYTHETASTAR = 4, THETASTARAGR = 5, THETASTARAGRPP = 6 };
 enum Mode { FAITHFUL = 0, CANONICAL = 1 };
 // include/utils/utils.hpp:19-21
 static const char IN_CLOSE_SET = 'a', IN_OPEN_SET = 'b', NOT_EXPAND = 'c';
@@ -323,7 +323,10 @@ struct Node {  // include/utils/utils.hpp:23-49 (live fields only)
   // lazy variants only: the expanded node that last relaxed this one, and that step's length
   Node* via;
   double via_step;
-  Node() : parent(nullptr), node_state(NOT_EXPAND), via(nullptr), via_step(0) {}
+  // AGR variants (utils.hpp:28,33): flying penalty carried in g, and rolling(0)/flying(1)
+  double penalty_g_score;
+  int motion_state;
+  Node() : parent(nullptr), node_state(NOT_EXPAND), via(nullptr), via_step(0), penalty_g_score(0), motion_state(0) {}
 };
 
 // include/utils/utils.hpp:52-61: (f_score, pointer). Pool is one contiguous array here, so pointer
@@ -356,6 +359,8 @@ struct PlannerParams {
   int allocate_num;         // <algo>/allocate_num       (AStar.cpp:35)
   double cost_weight;       // setCostFactor (AlgorithmBase.hpp:39); cost variants only
   double max_los;           // GetPath.srv:26 max_los; <=0 = unlimited (extension; lazy/theta variants)
+  // thetastaragr/* (ThetaStarAGR.cpp:33-36, ThetaStarAGRpp.cpp:33-37)
+  double barrier, flying_cost, flying_cost_default, ground_judge, epsilon;
 };
 
 struct Result {  // mirrors b200_path_result_t (include/b200_planner.h)
@@ -511,6 +516,98 @@ struct Planner {
     }
   }
 
+  // shared tail of ThetaStar/AGR::UpdateVertex (ThetaStar.cpp:76-88, ThetaStarAGR.cpp:109-120, ThetaStarAGRpp.cpp:115-126)
+  void reinsert_if_improved(Node* nb, double old_g, double old_f) {
+    if (!(nb->g_score < old_g)) return;
+    if (mode == FAITHFUL) {
+      if (nb->node_state == IN_OPEN_SET) {
+        open_faithful.erase(nb);  // lookup by the ALREADY MUTATED key (may miss)
+        open_faithful.insert(nb);
+      } else {
+        nb->node_state = IN_OPEN_SET;
+        open_faithful.insert(nb);
+      }
+    } else {
+      if (nb->node_state == IN_OPEN_SET) open_canon.erase({old_f, nb});
+      nb->node_state = IN_OPEN_SET;
+      open_canon.insert({nb->f_score, nb});
+    }
+  }
+  // ThetaStarAGR.cpp:49-103
+  void update_vertex_agr(Node* cur, Node* nb, const V3& d_pos, const V3& target) {
+    const double old_g = nb->g_score, old_f = nb->f_score;
+    double direct_cost = norm(d_pos);                                            // :51
+    double tmp_g_score = cur->g_score + direct_cost;                             // :52
+    double penalty_g_score = 0.0;
+    bool next_motion_state = (nb->position.z >= pp.ground_judge);                // :54
+    if (next_motion_state) {                                                     // :56-62
+      penalty_g_score = pp.flying_cost * nb->position.z / pp.barrier + pp.flying_cost_default;
+      tmp_g_score -= cur->penalty_g_score;
+      tmp_g_score += penalty_g_score;
+    } else {
+      tmp_g_score -= cur->penalty_g_score;
+    }
+    auto assign = [&](Node* parent, double g) {
+      nb->parent = parent;
+      nb->g_score = g;
+      nb->f_score = nb->g_score + pp.lambda_heuristic * heu(nb->position, target);
+      nb->motion_state = next_motion_state;
+      nb->penalty_g_score = penalty_g_score;
+    };
+    if (cur->parent == nullptr) {                                                // :64-73
+      if (tmp_g_score < nb->g_score) assign(cur, tmp_g_score);
+    } else {
+      los_checks++;                                                              // :77
+      if (fast_los(*map, cur->parent->position, nb->position, &los_samples)) {   // :78
+        double los_distance = norm(cur->parent->position - nb->position);        // :80
+        tmp_g_score = cur->parent->g_score + los_distance;                       // :81
+        if (next_motion_state) {                                                 // :82-87
+          tmp_g_score -= cur->parent->penalty_g_score;
+          tmp_g_score += penalty_g_score;
+        } else {
+          tmp_g_score -= cur->parent->penalty_g_score;
+        }
+        if (tmp_g_score < nb->g_score) assign(cur->parent, tmp_g_score);         // :88-95
+      } else if (tmp_g_score < nb->g_score) {                                    // :96-102
+        assign(cur, tmp_g_score);
+      }
+    }
+    reinsert_if_improved(nb, old_g, old_f);
+  }
+  // ThetaStarAGRpp.cpp:52-109.  std::max(a, b) is (a < b) ? b : a — matters for the NaN of 0/0 at z == 0.
+  static double stdmax(double a, double b) { return (a < b) ? b : a; }
+  void update_vertex_agrpp(Node* cur, Node* nb, const V3& d_pos, const V3& target) {
+    const double old_g = nb->g_score, old_f = nb->f_score;
+    double direct_cost = norm(d_pos);                                            // :54
+    bool next_motion_state = (nb->position.z >= pp.ground_judge);                // :56
+    double delta_z = nb->position.z - cur->position.z;                           // :62
+    double alpha = stdmax(1 + pp.flying_cost * delta_z / nb->position.z, pp.epsilon);   // :63
+    direct_cost *= (next_motion_state || cur->motion_state == 1) ? alpha : pp.epsilon;  // :64
+    double tmp_g_score = cur->g_score + direct_cost;                             // :66
+    if (cur->motion_state == 0 && next_motion_state) tmp_g_score += pp.flying_cost_default;  // :69-71
+    double best_cost = tmp_g_score;
+    Node* best_parent = cur;
+    if (cur->parent != nullptr) {                                                // :76
+      los_checks++;
+      if (fast_los(*map, cur->parent->position, nb->position, &los_samples)) {   // :78
+        double los_distance = norm(cur->parent->position - nb->position);
+        double delta_los_z = nb->position.z - cur->parent->position.z;
+        double alpha_los = stdmax(1 + pp.flying_cost * delta_los_z / nb->position.z, pp.epsilon);
+        los_distance *= (next_motion_state || cur->parent->motion_state == 1) ? alpha_los : pp.epsilon;
+        double tmp_g_score_parent = cur->parent->g_score + los_distance;
+        if (cur->parent->motion_state == 0 && next_motion_state) tmp_g_score_parent += pp.flying_cost_default;
+        if (tmp_g_score_parent < best_cost) { best_cost = tmp_g_score_parent; best_parent = cur->parent; }
+      }
+    }
+    if (best_cost < nb->g_score) {                                               // :101-108
+      nb->parent = best_parent;
+      nb->g_score = best_cost;
+      nb->f_score = nb->g_score + pp.lambda_heuristic * heu(nb->position, target);
+      nb->motion_state = next_motion_state ? 1 : 0;
+    }
+    reinsert_if_improved(nb, old_g, old_f);
+  }
+
   // Lazy Theta* (Nash, Koenig, Tovey 2010) on this code base's conventions — OURS, parity unpinned.
   // Generation: optimistic path-2 from parent(cur) (no LoS); verification at expansion (set_vertex).
   void update_vertex_lazy(Node* cur, Node* nb, const V3& d_pos, const V3& target) {
@@ -595,9 +692,26 @@ struct Planner {
     start->f_score = pp.lambda_heuristic * heu(start->position, target);
     start->node_state = IN_OPEN_SET;
     start->via = nullptr;
+    const bool agr = algo == THETASTARAGR || algo == THETASTARAGRPP;
+    if (agr) {  // ThetaStarAGR.cpp:141-155, ThetaStarAGRpp.cpp:146-155 (the set holds one element, so mutating after
+                // the insert, as the reference does, is the same as inserting the final key)
+      if (start->position.z < 0) start->position.z = 0;
+      if (start->position.z >= pp.ground_judge) {
+        if (algo == THETASTARAGR) {
+          const double pen = pp.flying_cost * start->position.z / pp.barrier + pp.flying_cost_default;
+          start->g_score += pen;
+          start->f_score += pen;
+          start->penalty_g_score = pen;
+        }
+        start->motion_state = 1;
+      } else {
+        start->motion_state = 0;
+        if (algo == THETASTARAGR) start->penalty_g_score = 0;
+      }
+    }
     open_insert(start);  // :94
     use_node_num += 1;   // :95
-    expanded.insert({Key{source.x, source.y, source.z}, start});  // :97
+    expanded.insert({Key{start->position.x, start->position.y, start->position.z}, start});  // :97 (AGR: clamped z)
 
     Node* cur = nullptr;
     Node* last = nullptr;
@@ -633,12 +747,14 @@ struct Planner {
             auto it = expanded.find(Key{nb_pos.x, nb_pos.y, nb_pos.z});  // :146
             if (it != expanded.end()) nb = it->second;
             if (nb != nullptr && nb->node_state == IN_CLOSE_SET) continue;  // :147
+            if (nb != nullptr && algo == THETASTARAGRPP) continue;          // ThetaStarAGRpp.cpp:208-210: never revisit a node
             if (get_inflate_occupancy(*map, nb_pos) == 1) continue;         // :151 (== true)
             if (nb == nullptr) {  // :156-169
               nb = &pool[use_node_num];
               nb->position = nb_pos;
               nb->g_score = std::numeric_limits<double>::infinity();
               nb->f_score = std::numeric_limits<double>::infinity();
+              if (algo == THETASTARAGRPP) nb->motion_state = (nb_pos.z >= pp.ground_judge) ? 1 : 0;  // ThetaStarAGRpp.cpp:216
               expanded.insert({Key{nb_pos.x, nb_pos.y, nb_pos.z}, nb});
               use_node_num += 1;
               if (use_node_num == pp.allocate_num) { oom = true; break; }  // :165-168
@@ -646,6 +762,8 @@ struct Planner {
             switch (algo) {  // :170 (virtual UpdateVertex)
               case ASTAR: case COSTASTAR: update_vertex_astar(cur, nb, d_pos, target); break;
               case THETASTAR: update_vertex_theta(cur, nb, d_pos, target); break;
+              case THETASTARAGR: update_vertex_agr(cur, nb, d_pos, target); break;
+              case THETASTARAGRPP: update_vertex_agrpp(cur, nb, d_pos, target); break;
               default: update_vertex_lazy(cur, nb, d_pos, target); break;
             }
           }
@@ -775,11 +893,11 @@ void orc_map_build_edt(void* h, double d_safe, int32_t* out, uint16_t* costq_out
 }
 
 void* orc_planner_create(int algo, int mode, double resolution, double lambda_heuristic, int allocate_num,
-                         double cost_weight, double max_los) {
+                         double cost_weight, double max_los, const double agr[5]) {
   Planner* p = new Planner();
   p->algo = (Algo)algo;
   p->mode = (Mode)mode;
-  p->pp = {resolution, lambda_heuristic, allocate_num, cost_weight, max_los};
+  p->pp = {resolution, lambda_heuristic, allocate_num, cost_weight, max_los, agr[0], agr[1], agr[2], agr[3], agr[4]};
   p->init();
   return p;
 }
@@ -799,14 +917,14 @@ int orc_planner_find_path(void* ph, const double s[3], const double g[3], Result
 // batched: queries are independent; one private planner per thread (reference is single-threaded;
 // this is the "ref-NT" baseline of BASELINE.md §3).  Paths go to path[qi*path_stride ...].
 int orc_planner_find_paths(int algo, int mode, double resolution, double lambda_heuristic, int allocate_num,
-                           double cost_weight, double max_los, void* map, const double* starts, const double* goals,
+                           double cost_weight, double max_los, const double agr[5], void* map, const double* starts, const double* goals,
                            int64_t nq, Result* res, double* path, int64_t path_stride, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   std::vector<Planner> planners(nthreads);
   for (auto& p : planners) {
     p.algo = (Algo)algo;
     p.mode = (Mode)mode;
-    p.pp = {resolution, lambda_heuristic, allocate_num, cost_weight, max_los};
+    p.pp = {resolution, lambda_heuristic, allocate_num, cost_weight, max_los, agr[0], agr[1], agr[2], agr[3], agr[4]};
     p.map = (OMap*)map;
     p.init();
   }

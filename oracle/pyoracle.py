@@ -10,7 +10,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-ALGOS = {"astar": 0, "thetastar": 1, "lazythetastar": 2, "costastar": 3, "costlazythetastar": 4}
+ALGOS = {"astar": 0, "thetastar": 1, "lazythetastar": 2, "costastar": 3, "costlazythetastar": 4, "thetastaragr": 5,
+         "thetastaragrpp": 6}
+# thetastaragr/{barrier, flying_cost, flying_cost_default, ground_judge, epsilon}: launch/planner.launch:71-77 defaults
+AGR_DEFAULTS = dict(barrier=2.0, flying_cost=10.0, flying_cost_default=0.0, ground_judge=0.1, epsilon=0.1)
 FAITHFUL, CANONICAL = 0, 1
 
 
@@ -58,11 +61,11 @@ def lib():
         L.orc_edt_brute.argtypes = [vp, vp]
         L.orc_map_build_edt.argtypes = [vp, C.c_double, vp, vp, vp, C.c_int]
         L.orc_planner_create.restype = vp
-        L.orc_planner_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.orc_planner_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp]
         L.orc_planner_destroy.argtypes = [vp]
         L.orc_planner_set_map.argtypes = [vp, vp]
         L.orc_planner_find_path.argtypes = [vp, dp, dp, C.POINTER(Result), vp, i64]
-        L.orc_planner_find_paths.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+        L.orc_planner_find_paths.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp,
                                              vp, vp, vp, i64, vp, vp, i64, C.c_int]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
@@ -169,9 +172,11 @@ class OraclePlanner:
     """Restatement of AStar/ThetaStar::findPath (AStar.cpp:80-179, ThetaStar.cpp:37-89) + our lazy/cost variants."""
 
     def __init__(self, algo, omap, resolution, lambda_heuristic=5.0, allocate_num=1000000, mode=CANONICAL,
-                 cost_weight=0.0, max_los=0.0):
+                 cost_weight=0.0, max_los=0.0, **agr):
         self.algo, self.mode, self.map = ALGOS[algo], mode, omap
-        self.args = (float(resolution), float(lambda_heuristic), int(allocate_num), float(cost_weight), float(max_los))
+        a = dict(AGR_DEFAULTS, **agr)
+        self._agr = (C.c_double * 5)(a["barrier"], a["flying_cost"], a["flying_cost_default"], a["ground_judge"], a["epsilon"])
+        self.args = (float(resolution), float(lambda_heuristic), int(allocate_num), float(cost_weight), float(max_los), self._agr)
         self.h = lib().orc_planner_create(self.algo, mode, *self.args)
         lib().orc_planner_set_map(self.h, omap.h)
 

@@ -40,6 +40,7 @@ def lib():
         L.ref_map_is_in_map.argtypes = [vp, vp, i64, vp]
         L.ref_pos_to_index.argtypes = [vp, vp, i64, vp]
         L.ref_los_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.ref_set_param.argtypes = [C.c_char_p, C.c_double]
         L.ref_planner_create.restype = vp
         L.ref_planner_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, vp]
         L.ref_planner_destroy.argtypes = [vp]
@@ -120,9 +121,13 @@ class RefMap:
 class RefPlanner:
     """The reference's AStar / ThetaStar (setParam + setGridMap + init; reset + findPath per query)."""
 
-    def __init__(self, algo, rmap, resolution, lambda_heuristic=5.0, allocate_num=100000):
+    def __init__(self, algo, rmap, resolution, lambda_heuristic=5.0, allocate_num=100000, **agr):
         self.map = rmap
-        self.h = lib().ref_planner_create({"astar": 0, "thetastar": 1}[algo], resolution, lambda_heuristic, allocate_num, rmap.h)
+        from .pyoracle import AGR_DEFAULTS
+        for k, v in dict(AGR_DEFAULTS, **agr).items():      # thetastaragr/* ROS params (launch/planner.launch:71-77)
+            lib().ref_set_param(("thetastaragr/" + k).encode(), float(v))
+        self.h = lib().ref_planner_create({"astar": 0, "thetastar": 1, "thetastaragr": 2, "thetastaragrpp": 3}[algo], resolution,
+                                          lambda_heuristic, allocate_num, rmap.h)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -33,6 +33,8 @@
 #include "plan_env/grid_map.h"
 #include "Planners/AStar.hpp"
 #include "Planners/ThetaStar.hpp"
+#include "Planners/ThetaStarAGR.hpp"
+#include "Planners/ThetaStarAGRpp.hpp"
 #undef private
 #undef protected
 
@@ -149,10 +151,11 @@ void ref_los_batch(void* h, const double* s, const double* e, int64_t n, uint8_t
   }
 }
 
-// algo: 0 astar, 1 thetastar (planner_ros_node.cpp:261-270: new AStar()/ThetaStar(); setParam(); setGridMap; init())
+// algo: 0 astar, 1 thetastar, 2 thetastaragr, 3 thetastaragrpp (planner_ros_node.cpp:261-279: new X(); setParam();
+// setGridMap; init()).  Both AGR variants read the thetastaragr/ namespace (ThetaStarAGRpp.cpp:28-37).
 void* ref_planner_create(int algo, double resolution, double lambda_heuristic, int allocate_num, void* map) {
   Silence s;
-  const std::string ns = algo == 1 ? "thetastar/" : "astar/";
+  const std::string ns = algo == 0 ? "astar/" : (algo == 1 ? "thetastar/" : "thetastaragr/");
   auto& P = shim::num_params();
   P[ns + "resolution"] = resolution;
   P[ns + "time_resolution"] = 0.8;
@@ -167,7 +170,11 @@ void* ref_planner_create(int algo, double resolution, double lambda_heuristic, i
   for (int attempt = 0; attempt < 8; ++attempt) {
     p = new RefPlanner();
     if (algo == 1) p->algo.reset(new Planners::ThetaStar());
+    else if (algo == 2) p->algo.reset(new Planners::ThetaStarAGR());
+    else if (algo == 3) p->algo.reset(new Planners::ThetaStarAGRpp());
     else p->algo.reset(new Planners::AStar());
+    // setParam is virtual in AlgorithmBase but ThetaStar and the AGR classes re-declare it non-virtually with the same
+    // signature, so the call through the base pointer dispatches to the most derived one, as in the node
     p->algo->setParam();
     p->gm = ((RefMap*)map)->gm;
     p->algo->setGridMap(p->gm);

@@ -87,6 +87,19 @@ def main():
         pl = pr.RefPlanner(algo, rm, RES, 5.0, 300)
         res, paths = pl.find_paths(qs[:16], qg[:16])
         out[f"{algo}_oom_res"] = res
+    # the fork's air-ground planners (ThetaStarAGR.cpp, ThetaStarAGRpp.cpp), launch-file parameters; some starts on /
+    # below the ground plane exercise the z clamp and the 0/0 -> NaN cost of ThetaStarAGRpp.cpp:63
+    qs2, qg2 = qs[:48].copy(), qg[:48].copy()
+    qs2[:8, 2] = 0.0
+    qs2[8:12, 2] = -0.005
+    qg2[12:20, 2] = 0.05
+    out["agr_start"], out["agr_goal"] = qs2, qg2
+    for algo in ("thetastaragr", "thetastaragrpp"):
+        pl = pr.RefPlanner(algo, rm, RES, 5.0, 100000)
+        assert pl.pool_disorder() == 0
+        res, paths = pl.find_paths(qs2, qg2)
+        out[f"{algo}_res"] = res
+        out[f"{algo}_path"] = np.concatenate(paths) if paths else np.zeros((0, 3))
     # unreachable goal: sealed hollow box -> open set empties (AStar.cpp:175-178)
     grid = np.zeros((128, 128, 32), np.uint8)
     grid[40:52, 40:52, 5:17] = 1

@@ -47,7 +47,7 @@ def test_struct_layouts(b200, tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert sizes[0] == C.sizeof(b200.MapParams) == 104
-    assert sizes[1] == C.sizeof(b200.PlannerParams) == 40
+    assert sizes[1] == C.sizeof(b200.PlannerParams) == 80
     assert sizes[2] == b200.RESULT_DTYPE.itemsize == 128
     assert sizes[3] == b200.RESULT_DTYPE.fields["g_final"][1]
     assert sizes[4] == b200.RESULT_DTYPE.fields["goal_coords"][1]

@@ -88,3 +88,15 @@ def test_failure_modes_match_the_reference(b200, gmap, algo):
     pl.setGridMap(m)
     res, _ = pl.findPaths(G["sealed_start"], G["sealed_goal"])
     _check(res, G[f"{algo}_sealed_res"])
+
+
+@pytest.mark.parametrize("algo", ["thetastaragr", "thetastaragrpp"])
+def test_air_ground_planners_are_bit_identical_to_the_reference(b200, gmap, algo):
+    gold = G[f"{algo}_res"]
+    n = len(gold)
+    pl = b200.Planner(algo, resolution=RES, lambda_heuristic=5.0, allocate_num=100000)   # launch-file AGR parameters
+    pl.setGridMap(gmap)
+    res, path = pl.findPaths(G["agr_start"], G["agr_goal"], path_cap=int(gold["n_path"].sum()) + 16)
+    _check(res, gold)
+    flat = np.concatenate([b200.path_of(res, path, i) for i in range(n) if res["n_path"][i] > 0])
+    assert np.array_equal(flat.view(np.uint64), G[f"{algo}_path"].view(np.uint64))

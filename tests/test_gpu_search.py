@@ -169,3 +169,18 @@ def test_max_los_extension(b200, po, world):
         pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s[:40], g[:40], max_los=2.0)
         assert_results_equal(rg, ro)
         _assert_paths_equal(b200, rg, pg, ro, pth)
+
+
+@pytest.mark.parametrize("algo,semantics", [("thetastaragr", "faithful"), ("thetastaragr", "canonical"), ("thetastaragrpp", "canonical"),
+                                            ("thetastaragrpp", "faithful")])
+def test_air_ground_planners_match_oracle(b200, po, world, algo, semantics):
+    gm, om, c, s, g = world
+    s, g = s[:60].copy(), g[:60].copy()
+    s[:6, 2] = 0.0          # on the ground plane: rolling start, and AGRpp's 0/0 = NaN edge
+    s[6:9, 2] = -0.004      # below it: clamped to 0 (ThetaStarAGR.cpp:141-142)
+    g[9:15, 2] = 0.05
+    kw = dict(barrier=2.0, flying_cost=10.0, flying_cost_default=0.3, ground_judge=0.1, epsilon=0.1)
+    pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s, g, allocate_num=200000, semantics=semantics, **kw)
+    assert ro["solved"].sum() > 40
+    assert_results_equal(rg, ro)
+    _assert_paths_equal(b200, rg, pg, ro, pth)

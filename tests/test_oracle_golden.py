@@ -108,3 +108,15 @@ def test_canonical_vs_reference_deviation_is_bounded(po, omap):
         rel = np.abs(res["g_final"] - gold["g_final"]) / gold["g_final"]
         assert same >= min_same, (algo, same)
         assert rel.max() < tol, (algo, rel.max())
+
+
+@pytest.mark.parametrize("algo", ["thetastaragr", "thetastaragrpp"])
+def test_air_ground_planners_faithful_mode_is_the_reference(po, omap, algo):
+    gold = G[f"{algo}_res"]
+    n = len(gold)
+    for mode in ([po.FAITHFUL] if algo == "thetastaragr" else [po.FAITHFUL, po.CANONICAL]):   # AGRpp: both coincide
+        pl = po.OraclePlanner(algo, omap, RES, 5.0, 100000, mode=mode)
+        res, paths = pl.find_paths(G["agr_start"], G["agr_goal"], path_stride=8192, nthreads=4)
+        flat = np.concatenate([paths[i * 8192: i * 8192 + res["n_path"][i]] for i in range(n)])
+        _check(res, gold, flat, G[f"{algo}_path"])
+    assert gold["solved"].sum() > 30
