@@ -70,6 +70,7 @@ ABI = [
     ("b200_map_download_inflate", C.c_int, [_vp, _vp]),
     ("b200_map_upload_inflate", C.c_int, [_vp, _vp]),
     ("b200_map_device_bits", C.c_int, [_vp, _pp, C.POINTER(_i64)]),
+    ("b200_map_export_inflate_cloud", C.c_int, [_vp, _i32, _dbl, _vp, _i64, C.POINTER(_i64), _i32]),
     ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
@@ -243,6 +244,15 @@ class GridMap:
         grid = np.ascontiguousarray(grid, dtype=np.uint8)
         assert grid.shape == self.dims
         _ck(lib().b200_map_upload_inflate(self.h, _ptr(grid)))
+
+    def publishMapInflate(self, all_info=False, local_map_margin=1, visualization_truncate_height=2.4, cap=None):
+        """publishMapInflate (grid_map.cpp:851-900): the PointXYZ records (x, y, z, 1.0) of the PointCloud2 it publishes."""
+        cap = int(np.prod(self.dims)) if cap is None else int(cap)
+        out = np.empty((cap, 4), dtype=np.float32)
+        n = C.c_int64()
+        _ck(lib().b200_map_export_inflate_cloud(self.h, local_map_margin if all_info else 0, float(visualization_truncate_height),
+                                                _ptr(out), cap, C.byref(n), 0))
+        return out[: min(n.value, cap)].copy()
 
     # --- new functionality ------------------------------------------------------------------------
     def build_edt(self, d_safe=0.0):

@@ -17,6 +17,10 @@ void launch_pos_to_index(const MapDev& m, const double* pos, long long n, int32_
 void launch_los_batch(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* nsamples, int sm_count,
                       cudaStream_t st);
 
+size_t export_scan_temp_bytes(long long cols);
+void launch_export(const MapDev& m, const int a[3], const int b[3], double truncate, int* counts, int* offsets, void* temp,
+                   size_t temp_bytes, float4* out, long long cap, cudaStream_t st);
+
 // ---- edt_kernels.cu
 int edt_lut_size(double res, double d_safe);
 // ev (optional): 8 events recorded before z, scan_y, cross_y, fill_y, scan_x, cross_x, fill_x and after fill_x

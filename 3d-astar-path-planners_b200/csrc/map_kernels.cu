@@ -4,6 +4,8 @@
 // Reference behaviour restated (not ported): src/plan_env/grid_map.cpp:155-171 (resetBuffer),
 // :711-804 (cloudCallback), include/plan_env/grid_map.h:350-404 (occupancy inlines),
 // src/utils/LineOfSight.cpp:9-27 (fastLOS).
+#include <cub/device/device_scan.cuh>
+
 #include "kernels.h"
 
 namespace b200 {
@@ -205,6 +207,72 @@ __global__ void __launch_bounds__(256) los_batch_kernel(MapDev m, const double* 
       if (nsamples) nsamples[i] = samples;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// map publisher (grid_map.cpp:851-900 publishMapInflate): ordered stream compaction of the occupied voxels of an
+// index box into PointXYZ records (x, y, z, 1.0f), x -> y -> z order like the reference's triple loop.
+// count per column -> exclusive scan (CUB, not a hot path) -> ordered write.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool export_keep(const MapDev& m, int z, double truncate) {
+  return !(dadd(dmul(dadd((double)z, 0.5), m.res), m.oz) > truncate);  // indexToPos (grid_map.h:406-410), :875-876
+}
+__global__ void __launch_bounds__(256) export_count_kernel(MapDev m, int ax, int ay, int az, int bx, int by, int bz, double truncate,
+                                                           int* __restrict__ counts) {
+  const int ny = by - ay + 1;
+  const long long cols = (long long)(bx - ax + 1) * ny;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= cols) return;
+  const int x = ax + (int)(i / ny), y = ay + (int)(i % ny);
+  const uint32_t* c = m.occ + ((size_t)x * m.Ny + y) * m.wz;
+  int n = 0;
+  for (int w = az >> 5; w <= bz >> 5; ++w) {
+    uint32_t v = __ldg(c + w);
+    while (v) {
+      const int z = (w << 5) + __ffs(v) - 1;
+      v &= v - 1;
+      if (z >= az && z <= bz && export_keep(m, z, truncate)) ++n;
+    }
+  }
+  counts[i] = n;
+}
+__global__ void __launch_bounds__(256) export_write_kernel(MapDev m, int ax, int ay, int az, int bx, int by, int bz, double truncate,
+                                                           const int* __restrict__ offsets, float4* __restrict__ out, long long cap) {
+  const int ny = by - ay + 1;
+  const long long cols = (long long)(bx - ax + 1) * ny;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= cols) return;
+  const int x = ax + (int)(i / ny), y = ay + (int)(i % ny);
+  const uint32_t* c = m.occ + ((size_t)x * m.Ny + y) * m.wz;
+  long long o = offsets[i];
+  const float px = __double2float_rn(dadd(dmul(dadd((double)x, 0.5), m.res), m.ox));
+  const float py = __double2float_rn(dadd(dmul(dadd((double)y, 0.5), m.res), m.oy));
+  for (int w = az >> 5; w <= bz >> 5; ++w) {
+    uint32_t v = __ldg(c + w);
+    while (v) {
+      const int z = (w << 5) + __ffs(v) - 1;
+      v &= v - 1;
+      if (z >= az && z <= bz && export_keep(m, z, truncate)) {
+        if (o < cap) out[o] = make_float4(px, py, __double2float_rn(dadd(dmul(dadd((double)z, 0.5), m.res), m.oz)), 1.0f);
+        ++o;
+      }
+    }
+  }
+}
+size_t export_scan_temp_bytes(long long cols) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (int)cols);
+  return bytes;
+}
+// counts/offsets: cols + 1 ints each (the extra element receives the total); temp: export_scan_temp_bytes(cols + 1)
+void launch_export(const MapDev& m, const int a[3], const int b[3], double truncate, int* counts, int* offsets, void* temp,
+                   size_t temp_bytes, float4* out, long long cap, cudaStream_t st) {
+  const long long cols = (long long)(b[0] - a[0] + 1) * (b[1] - a[1] + 1);
+  const unsigned g = (unsigned)((cols + 255) / 256);
+  cudaMemsetAsync(counts + cols, 0, sizeof(int), st);
+  export_count_kernel<<<g, 256, 0, st>>>(m, a[0], a[1], a[2], b[0], b[1], b[2], truncate, counts);
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, (int)(cols + 1), st);
+  export_write_kernel<<<g, 256, 0, st>>>(m, a[0], a[1], a[2], b[0], b[1], b[2], truncate, offsets, out, cap);
 }
 
 // ---------------------------------------------------------------------------------------------------

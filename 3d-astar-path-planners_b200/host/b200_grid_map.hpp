@@ -183,6 +183,14 @@ class GridMap {
     b200_check(b200_map_download_inflate(h_, g.data()), "download");
     return g;
   }
+  // publishMapInflate (grid_map.cpp:851-900): the PointXYZ records (x, y, z, 1.0f) of the cloud the reference publishes
+  std::vector<float> publishMapInflate(bool all_info = false, int local_map_margin = 1, double visualization_truncate_height = 2.4) const {
+    int64_t n = 0;
+    b200_check(b200_map_export_inflate_cloud(h_, all_info ? local_map_margin : 0, visualization_truncate_height, nullptr, 0, &n, 0), "publishMapInflate");
+    std::vector<float> pts((size_t)n * 4);
+    if (n) b200_check(b200_map_export_inflate_cloud(h_, all_info ? local_map_margin : 0, visualization_truncate_height, pts.data(), n, &n, 0), "publishMapInflate");
+    return pts;
+  }
   // new: exact squared EDT + safety cost field (replaces the commented-out evaluateCoarseEDT hook)
   void buildDistanceField(double d_safe) { b200_check(b200_map_build_edt(h_, d_safe), "build_edt"); }
 

@@ -97,6 +97,13 @@ int b200_map_upload_inflate(b200_map_t* map, const uint8_t* src);
 /* Device pointer + word count of the bit-packed grid (uint32 words, [x][y][ceil(Nz/32)], bit z&31). */
 int b200_map_device_bits(b200_map_t* map, void** dev_ptr, int64_t* n_words);
 
+/* GridMap::publishMapInflate (grid_map.cpp:851-900): the occupied inflated voxels of the local-bounds box (extended by
+ * `margin` voxels = local_map_margin when all_info, 0 otherwise), x -> y -> z order, voxel centres not above
+ * `truncate_height` (grid_map/visualization_truncate_height), as 16-byte PointXYZ records (float x, y, z, 1.0f) — the
+ * PointCloud2 data blob the reference publishes.  *n_out = number of points (may exceed cap; only cap are written). */
+int b200_map_export_inflate_cloud(b200_map_t* map, int32_t margin, double truncate_height, float* xyz1, int64_t cap,
+                                  int64_t* n_out, int32_t on_device);
+
 /* NEW (not in the reference; replaces the commented-out evaluateCoarseEDT hook, AlgorithmBase.cpp:40-42):
  * exact squared Euclidean distance (voxel units, int32; 1<<29 where no obstacle exists) of every voxel to
  * the nearest inflated-occupied voxel, plus — when d_safe > 0 — the safety-cost field

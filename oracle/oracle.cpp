@@ -187,6 +187,27 @@ static void cloud_update(OMap& m, const uint8_t* pts, int64_t n, int step, int o
   bound_index(m, m.lb_max);                                        // :803
 }
 
+// grid_map.cpp:851-900 publishMapInflate: occupied inflated voxels of the local-bounds box (+- margin when all_info),
+// in x -> y -> z order, voxel centres (grid_map.h:406-410 indexToPos) not above visualization_truncate_height, as
+// PointXYZ records (float x, y, z and PCL's padding float 1.0f).
+static int64_t export_inflate_cloud(const OMap& m, int margin, double truncate_height, float* out, int64_t cap) {
+  int a[3], b[3];
+  for (int i = 0; i < 3; ++i) { a[i] = m.lb_min[i] - margin; b[i] = m.lb_max[i] + margin; }
+  bound_index(m, a);
+  bound_index(m, b);
+  int64_t n = 0;
+  for (int x = a[0]; x <= b[0]; ++x)
+    for (int y = a[1]; y <= b[1]; ++y)
+      for (int z = a[2]; z <= b[2]; ++z) {
+        if (m.inflate[to_address(m, x, y, z)] == 0) continue;
+        const double px = (x + 0.5) * m.res + m.origin.x, py = (y + 0.5) * m.res + m.origin.y, pz = (z + 0.5) * m.res + m.origin.z;
+        if (pz > truncate_height) continue;
+        if (n < cap) { out[4 * n] = (float)px; out[4 * n + 1] = (float)py; out[4 * n + 2] = (float)pz; out[4 * n + 3] = 1.0f; }
+        ++n;
+      }
+  return n;
+}
+
 // src/utils/LineOfSight.cpp:9-27 fastLOS.  Returns visible; *nsamples = samples evaluated.
 static const double kLosStep = 0.1 / 2.0;  // LineOfSight.cpp:13-14 (resolution hard-coded 0.1)
 // `sumq` (extension, cost variants only): adds the quantised cost of every sampled voxel.
@@ -841,6 +862,9 @@ void orc_map_upload_inflate(void* h, const uint8_t* src) {
 void orc_map_local_bounds(void* h, int mn[3], int mx[3]) {
   OMap* m = (OMap*)h;
   for (int i = 0; i < 3; ++i) { mn[i] = m->lb_min[i]; mx[i] = m->lb_max[i]; }
+}
+int64_t orc_map_export_inflate_cloud(void* h, int margin, double truncate_height, float* out, int64_t cap) {
+  return export_inflate_cloud(*(OMap*)h, margin, truncate_height, out, cap);
 }
 void orc_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   OMap* m = (OMap*)h;

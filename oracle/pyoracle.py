@@ -54,6 +54,8 @@ def lib():
         L.orc_map_upload_inflate.argtypes = [vp, vp]
         L.orc_map_local_bounds.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_map_get_inflate_occupancy.argtypes = [vp, vp, i64, vp]
+        L.orc_map_export_inflate_cloud.argtypes = [vp, C.c_int, C.c_double, vp, i64]
+        L.orc_map_export_inflate_cloud.restype = i64
         L.orc_map_is_in_map.argtypes = [vp, vp, i64, vp]
         L.orc_pos_to_index.argtypes = [vp, vp, i64, vp]
         L.orc_los_batch.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int]
@@ -121,6 +123,12 @@ class OracleMap:
         a, b = (C.c_int * 3)(), (C.c_int * 3)()
         lib().orc_map_local_bounds(self.h, a, b)
         return tuple(a), tuple(b)
+
+    def export_inflate_cloud(self, margin=0, truncate_height=2.4, cap=None):
+        cap = int(np.prod(self.dims)) if cap is None else cap
+        out = np.empty((cap, 4), dtype=np.float32)
+        n = lib().orc_map_export_inflate_cloud(self.h, margin, truncate_height, _ptr(out), cap)
+        return out[: min(n, cap)].copy(), n
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

@@ -37,6 +37,8 @@ def lib():
         L.ref_map_upload_inflate.argtypes = [vp, vp]
         L.ref_map_local_bounds.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_map_get_inflate_occupancy.argtypes = [vp, vp, i64, vp]
+        L.ref_map_publish_inflate.argtypes = [vp, C.c_int, vp, i64]
+        L.ref_map_publish_inflate.restype = i64
         L.ref_map_is_in_map.argtypes = [vp, vp, i64, vp]
         L.ref_pos_to_index.argtypes = [vp, vp, i64, vp]
         L.ref_los_batch.argtypes = [vp, vp, vp, i64, vp]
@@ -91,6 +93,14 @@ class RefMap:
         a, b = (C.c_int * 3)(), (C.c_int * 3)()
         lib().ref_map_local_bounds(self.h, a, b)
         return tuple(a), tuple(b)
+
+    def publish_inflate(self, all_info=False):
+        """publishMapInflate (grid_map.cpp:851-900): the PointXYZ records (x, y, z, 1.0) it would publish; uses the
+        reference defaults grid_map/visualization_truncate_height = 2.4 and local_map_margin = 1."""
+        cap = int(np.prod(self.dims))
+        out = np.empty((cap, 4), dtype=np.float32)
+        n = lib().ref_map_publish_inflate(self.h, 1 if all_info else 0, _ptr(out), cap)
+        return out[:n].copy()
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

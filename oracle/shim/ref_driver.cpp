@@ -124,6 +124,17 @@ void ref_map_local_bounds(void* h, int mn[3], int mx[3]) {
   GridMap& g = *((RefMap*)h)->gm;
   for (int i = 0; i < 3; ++i) { mn[i] = g.md_.local_bound_min_(i); mx[i] = g.md_.local_bound_max_(i); }
 }
+// GridMap::publishMapInflate (grid_map.cpp:851-900) with one fake subscriber; returns the PointXYZ records it published
+int64_t ref_map_publish_inflate(void* h, int all_info, float* out, int64_t cap) {
+  GridMap& g = *((RefMap*)h)->gm;
+  shim::fake_subscribers() = 1;
+  shim::last_cloud_blob().clear();
+  g.publishMapInflate(all_info != 0);
+  shim::fake_subscribers() = 0;
+  const int64_t n = (int64_t)(shim::last_cloud_blob().size() / 16);
+  std::memcpy(out, shim::last_cloud_blob().data(), (size_t)std::min<int64_t>(n, cap) * 16);
+  return n;
+}
 void ref_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   GridMap& g = *((RefMap*)h)->gm;
   for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)g.getInflateOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));

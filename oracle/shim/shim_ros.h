@@ -13,6 +13,9 @@
 #include <vector>
 
 namespace shim {
+// what the last ros::Publisher::publish(sensor_msgs::PointCloud2) carried (the map publishers' output)
+inline std::vector<uint8_t>& last_cloud_blob() { static std::vector<uint8_t> b; return b; }
+inline int& fake_subscribers() { static int n = 0; return n; }
 inline std::map<std::string, double>& num_params() { static std::map<std::string, double> m; return m; }
 inline std::map<std::string, std::string>& str_params() { static std::map<std::string, std::string> m; return m; }
 template <class T> struct ParamGet {
@@ -49,8 +52,11 @@ struct TimerEvent {};
 struct Timer {};
 struct Subscriber {};
 struct Publisher {
-  int getNumSubscribers() const { return 0; }
-  template <class M> void publish(const M&) const {}
+  int getNumSubscribers() const { return shim::fake_subscribers(); }
+  template <class M> void publish(const M& m) const { capture(m, 0); }
+ private:
+  template <class M> static auto capture(const M& m, int) -> decltype((void)m.data, (void)m.point_step) { shim::last_cloud_blob() = m.data; }
+  template <class M> static void capture(const M&, long) {}
 };
 class NodeHandle {
  public:
@@ -119,7 +125,7 @@ inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr&, const std::string&
 
 namespace pcl {
 struct PCLHeader { std::string frame_id; };
-struct PointXYZ { float x = 0, y = 0, z = 0, pad = 0; };
+struct PointXYZ { float x = 0, y = 0, z = 0, pad = 1.0f; };  // PCL initialises data[3] to 1
 template <class P> struct PointCloud {
   std::vector<P> points;
   uint32_t width = 0, height = 0;
@@ -141,7 +147,14 @@ inline void fromROSMsg(const sensor_msgs::PointCloud2& msg, PointCloud<PointXYZ>
   }
   cloud.width = (uint32_t)n; cloud.height = 1;
 }
-template <class P> inline void toROSMsg(const PointCloud<P>&, sensor_msgs::PointCloud2&) {}
+// what pcl::toROSMsg does for PointXYZ: the point array copied verbatim (16-byte records, padding float included)
+template <class P> inline void toROSMsg(const PointCloud<P>& c, sensor_msgs::PointCloud2& msg) {
+  msg.point_step = sizeof(P);
+  msg.width = (uint32_t)c.points.size();
+  msg.height = 1;
+  msg.data.resize(c.points.size() * sizeof(P));
+  if (!c.points.empty()) std::memcpy(msg.data.data(), c.points.data(), msg.data.size());
+}
 }
 
 namespace message_filters {

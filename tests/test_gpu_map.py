@@ -127,3 +127,18 @@ def test_c2_full_size_cloud_1m_points(b200, po, synth):
     # idempotence: the same frame again gives the same grid (clear + set-union)
     gm.cloudCallback(synth.pack_cloud(cloud), (0.0, 0.0, 1.0))
     assert np.array_equal(gm.inflate(), o)
+
+
+def test_publish_map_inflate_matches_oracle(b200, po, synth):
+    """publishMapInflate (grid_map.cpp:851-900): ordered export of the occupied voxels; the oracle's export is pinned
+    against the reference's own publisher in tests/test_oracle_vs_ref.py."""
+    c = synth.CONFIGS["C3"]
+    for rng, cam in [((1e3, 1e3, 1e3), (0.0, 0.0, 1.0)), ((4.0, 3.0, 1.5), (2.0, -3.0, 1.0))]:
+        gm, om, _ = make_pair(b200, po, synth, "C3", rng=rng, cam=cam)
+        for all_info in (False, True):
+            for trunc in (2.4, 0.77, -1.0):
+                want, n = om.export_inflate_cloud(1 if all_info else 0, trunc)
+                got = gm.publishMapInflate(all_info, 1, trunc)
+                assert len(got) == n
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert len(gm.publishMapInflate(cap=10)) == 10      # truncated buffer: first 10 points, still ordered

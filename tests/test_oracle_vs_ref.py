@@ -45,3 +45,19 @@ def test_clear_box_matches_reference(po, synth):
         rm.clear_box(mn, mx)
         om.clear_box(mn, mx)
         assert np.array_equal(rm.inflate(), om.inflate())
+
+
+def test_map_publisher_matches_reference(po, synth):
+    size, res = (12.8, 12.8, 3.2), 0.1
+    origin = (-6.4, -6.4, -0.01)
+    cloud = synth.pack_cloud(synth.forest(21, origin, size, res, 22))
+    for rng, cam in [((1e3, 1e3, 1e3), (0, 0, 1)), ((3.0, 2.5, 1.2), (1.7, -2.2, 0.9))]:
+        rm = pr.RefMap(size, res, 0.099, rng, -0.01)
+        om = po.OracleMap(origin, size, res, 0.099, rng, -0.01)
+        rm.update_cloud(cloud, cam)
+        om.update_cloud(cloud, cam)
+        for all_info in (False, True):
+            ref = rm.publish_inflate(all_info)                 # grid_map/visualization_truncate_height 2.4, local_map_margin 1
+            mine, n = om.export_inflate_cloud(1 if all_info else 0, 2.4)
+            assert n == len(ref) and n > 1000
+            assert np.array_equal(ref.view(np.uint32), mine.view(np.uint32))
