@@ -598,7 +598,7 @@ struct b200_planner {
   b200_map* map;
   double dv[3];
   Tier tier[2];
-  DevBuf q_in, q_res, q_path, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
+  DevBuf q_in, q_res, q_path, q_order, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
   int last_launches;
 };
 
@@ -673,7 +673,7 @@ int b200_planner_destroy(b200_planner_t* pl) {
   if (pl->map) cudaSetDevice(pl->map->prm.device);
   tier_free(pl->tier[0]);
   tier_free(pl->tier[1]);
-  pl->q_in.release(); pl->q_res.release(); pl->q_path.release(); pl->ctl.release();
+  pl->q_in.release(); pl->q_res.release(); pl->q_path.release(); pl->q_order.release(); pl->ctl.release();
   delete pl;
   return B200_OK;
 }
@@ -722,8 +722,19 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   const int per_sm = search_slots_per_sm(pl->algo, pl->faithful);
   int slots0 = m->sm_count * per_sm;
   if ((int64_t)slots0 > nq) slots0 = (int)nq;
-  const int cap0 = std::min(pl->prm.allocate_num, 16384);
   const int factor = open_region_factor(pl->algo, pl->faithful);
+  // tier 0 holds 32 768 nodes per slot when that fits in a quarter of the free memory (a rerun in tier 1 costs a
+  // second launch that waits for the first: 2 of 131 072 Lazy Theta* queries needed > 16 384 nodes and their
+  // rerun took 75 of 290 ms), else 16 384, else fewer slots
+  int cap0 = std::min(pl->prm.allocate_num, 32768);
+  if (!(pl->tier[0].base && pl->tier[0].cap == cap0 && pl->tier[0].slots >= slots0)) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (pl->tier[0].base) free_b += (size_t)pl->tier[0].slots * search_slot_bytes(pl->tier[0].cap, pl->tier[0].factor, nullptr);
+    const size_t budget = free_b / 4;
+    if (cap0 > 16384 && (size_t)slots0 * search_slot_bytes(cap0, factor, nullptr) > budget) cap0 = 16384;
+    while (slots0 > 1 && (size_t)slots0 * search_slot_bytes(cap0, factor, nullptr) > budget) slots0 = (slots0 + 1) / 2;
+  }
   if (tier_alloc(pl->tier[0], cap0, std::max(slots0, pl->tier[0].cap == cap0 ? pl->tier[0].slots : 0), factor))
     return fail(B200_ERR_NOMEM, "search workspace (tier 0)");
 
@@ -766,6 +777,10 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   P.algo = pl->algo;
   P.faithful = pl->faithful;
   P.starts = d_starts; P.goals = d_goals; P.qlist = nullptr; P.nq = nq;
+  if (nq > 2 * (int64_t)pl->tier[0].slots) {  // more than two waves: issue the expected-longest queries first
+    if (pl->q_order.ensure(query_order_bytes((int)nq))) return fail(B200_ERR_NOMEM, "query order");
+    P.qlist = launch_query_order(d_starts, d_goals, (int)nq, pl->q_order.p, st);
+  }
   P.results = d_res; P.path_pool = d_path; P.path_cap = path_cap; P.path_cursor = path_cursor;
   P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;
   const Tier& t0 = pl->tier[0];

@@ -41,12 +41,14 @@ enum { ST_SOLVED = 0, ST_OPEN_EMPTY = 1, ST_POOL_EXHAUSTED = 2, ST_TIER_OVERFLOW
 //   heap   HeapEnt [2cap+32]  canonical: 32-ary min-heap on (f, creation index), children of k are one aligned 512 B row;
 //                             faithful: the red-black tree nodes of rbtree.cuh (16 B each, duplicates possible)
 struct __align__(16) NodeRec {
+  // first 32-byte sector: what the neighbour probe reads (key compare, closed test, open-list position)
   double px, py, pz;
+  int state;      // low byte: NODE_*; next byte: via direction code (0..26); bit 16: AGR motion_state (flying)
+  int hpos;       // heap position, -1 when not in the open list
+  // second sector: what UpdateVertex reads and writes
   double g, f;
   int parent;     // node index or -1
-  int hpos;       // heap position, -1 when not in the open list
   uint32_t slot;  // hash slot (for O(used) clearing)
-  int state;      // low byte: NODE_*; next byte: via direction code (0..26); bit 16: AGR motion_state (flying)
   union {
     struct { int via; int pad; };  // lazy variants: expanded node that last relaxed this one
     double penalty;                // thetastaragr: penalty_g_score carried in g (utils.hpp:28)
@@ -96,5 +98,7 @@ size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out);
 int search_threads_per_block(int algo);
 int search_slots_per_sm(int algo, int faithful);
 void launch_search(const SearchParams& p, int slots, cudaStream_t st);
+size_t query_order_bytes(int nq);
+const int* launch_query_order(const double* starts, const double* goals, int nq, void* buf, cudaStream_t st);
 
 }  // namespace b200

@@ -19,6 +19,7 @@
 //     warp-per-segment, lanes = consecutive 0.05 m samples, __ballot_sync early-out (common.cuh).
 //   * FP64 everywhere positions are touched (voxel registration is rounding-dependent).
 #include "kernels.h"
+#include <cub/device/device_radix_sort.cuh>
 #include "rbtree.cuh"
 
 namespace b200 {
@@ -50,24 +51,34 @@ struct Slot {
   NodeRec* nodes;
   uint32_t* hash;
   HeapEnt* heap;  // physical index = logical + 31 (children of k: physical 32k+32 .. 32k+63)
+  HeapEnt* top;   // shared memory: logical entries 0..32 (root + its 32 children) live here, not in `heap`
   uint32_t hmask;
   int heap_n;
   int use;
 };
+// The two top levels of the heap are the ancestors of every entry: keeping them in shared memory makes every
+// sift-up step of a heap of <= 1057 entries, and the first level of every pop, an on-chip access instead of a
+// dependent global-memory round trip (the ncu source view charged 15-20 % of all stall samples to those loads).
+constexpr int kHeapTop = 33;
+__device__ __forceinline__ HeapEnt heap_ld(const Slot& s, int k) { return k < kHeapTop ? s.top[k] : s.heap[k + 31]; }
+__device__ __forceinline__ void heap_st(const Slot& s, int k, const HeapEnt& e) {
+  if (k < kHeapTop) s.top[k] = e;
+  else s.heap[k + 31] = e;
+}
 
 // ---- 32-ary heap, all 32 lanes of the control warp call these with warp-uniform arguments ----------
 __device__ __forceinline__ void heap_place(Slot& s, int k, unsigned long long key, uint32_t idx, int lane) {
   if (lane == 0) {
     HeapEnt e;
     e.key = key; e.idx = idx; e.pad = 0;
-    s.heap[k + 31] = e;
+    heap_st(s, k, e);
     s.nodes[idx].hpos = k;
   }
 }
 __device__ __forceinline__ void heap_sift_up(Slot& s, int k, unsigned long long key, uint32_t idx, int lane) {
   while (k > 0) {
     const int par = (k - 1) >> 5;
-    const HeapEnt pe = s.heap[par + 31];
+    const HeapEnt pe = heap_ld(s, par);
     if (!key_less(key, idx, pe.key, pe.idx)) break;
     heap_place(s, k, pe.key, pe.idx, lane);
     k = par;
@@ -79,13 +90,57 @@ __device__ __forceinline__ void heap_push(Slot& s, unsigned long long key, uint3
   const int k = s.heap_n++;
   heap_sift_up(s, k, key, idx, lane);
 }
+// One expansion's open-list updates (<= 26, one per lane): `improved` lanes either decrease the key of the entry at
+// `hpos` (>= 0, read before any of this expansion's updates) or append a new entry.
+// The serial version costs two dependent global-memory round trips per update (the ncu source view put 20 % of the
+// kernel's stall samples there).  Here every lane reads its parent entry at once; an update whose key is not below
+// its parent's is written in place — that can never break the heap property, whatever the other lanes do: an
+// entry's key only ever decreases, and appended leaves have old entries as parents once the heap is non-empty —
+// and only the few that must move up are replayed one at a time with fresh reads.
+__device__ __forceinline__ void heap_update_batch(Slot& s, bool improved, int hpos, unsigned long long key, uint32_t idx, int lane) {
+  const unsigned im = __ballot_sync(0xffffffffu, improved);
+  if (!im) return;
+  const int n0 = s.heap_n;
+  const bool is_new = improved && hpos < 0;
+  const unsigned newmask = __ballot_sync(0xffffffffu, is_new);
+  const int k = is_new ? n0 + __popc(newmask & ((1u << lane) - 1u)) : hpos;
+  bool stay = false;
+  if (improved && n0 > 0) {
+    if (k == 0) {
+      stay = true;
+    } else {
+      const HeapEnt pe = heap_ld(s, (k - 1) >> 5);
+      stay = !key_less(key, idx, pe.key, pe.idx);
+    }
+  }
+  s.heap_n = n0 + __popc(newmask);
+  __syncwarp();
+  if (stay) {
+    HeapEnt e;
+    e.key = key; e.idx = idx; e.pad = 0;
+    heap_st(s, k, e);
+    if (is_new) s.nodes[idx].hpos = k;
+  }
+  __syncwarp();
+  unsigned mv = __ballot_sync(0xffffffffu, improved && !stay);
+  while (mv) {
+    const int b = __ffs(mv) - 1;
+    mv &= mv - 1;
+    const uint32_t bi = __shfl_sync(0xffffffffu, idx, b);
+    const unsigned long long bk = __shfl_sync(0xffffffffu, key, b);
+    const int bnew = __shfl_sync(0xffffffffu, (int)is_new, b);
+    const int bk0 = __shfl_sync(0xffffffffu, k, b);
+    // an appended entry starts from its reserved leaf; an existing one from wherever earlier moves left it
+    const int from = bnew ? bk0 : s.nodes[bi].hpos;
+    heap_sift_up(s, from, bk, bi, lane);
+  }
+}
 // removes the root; returns its node index
-__device__ __forceinline__ uint32_t heap_pop(Slot& s, int lane) {
-  const HeapEnt top = s.heap[31];
+__device__ __forceinline__ uint32_t heap_pop(Slot& s, int lane, const HeapEnt top) {
   const int n = --s.heap_n;
   if (lane == 0) s.nodes[top.idx].hpos = -1;
   if (n > 0) {
-    const HeapEnt last = s.heap[n + 31];
+    const HeapEnt last = heap_ld(s, n);
     int k = 0;
     for (;;) {
       const int c0 = 32 * k + 1;
@@ -94,7 +149,7 @@ __device__ __forceinline__ uint32_t heap_pop(Slot& s, int lane) {
       const bool valid = ci < n;
       HeapEnt ce;
       ce.key = ~0ULL; ce.idx = 0xffffffffu; ce.pad = 0;
-      if (valid) ce = s.heap[ci + 31];
+      if (valid) ce = heap_ld(s, ci);
       const uint32_t hi = valid ? (uint32_t)(ce.key >> 32) : 0xffffffffu;
       const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
       const uint32_t lo = (valid && hi == mhi) ? (uint32_t)ce.key : 0xffffffffu;
@@ -121,6 +176,21 @@ __device__ __forceinline__ int hash_find(const Slot& s, double x, double y, doub
     if (e == 0) return -1;
     const NodeRec* n = s.nodes + (e - 1);
     if (n->px == x && n->py == y && n->pz == z) return (int)(e - 1);
+    h = (h + 1) & s.hmask;
+  }
+}
+// same probe; on a hit also returns the fields UpdateVertex needs: state/hpos share the key's 32-byte sector and g
+// is requested at once, so its round trip overlaps the rest of the neighbour phase
+__device__ __forceinline__ int hash_find_ex(const Slot& s, double x, double y, double z, int& state, int& hpos, double& g) {
+  uint32_t h = hash3(x, y, z) & s.hmask;
+  for (;;) {
+    const uint32_t e = s.hash[h];
+    if (e == 0) return -1;
+    const NodeRec* n = s.nodes + (e - 1);
+    if (n->px == x && n->py == y && n->pz == z) {
+      state = n->state; hpos = n->hpos; g = n->g;
+      return (int)(e - 1);
+    }
     h = (h + 1) & s.hmask;
   }
 }
@@ -213,19 +283,30 @@ __device__ __forceinline__ AgrCand agrpp_candidate(const SearchParams& P, double
   return c;
 }
 
+// resident blocks per SM the register allocation is capped for.  Measured (1xB200, C2 world, queries/s): the
+// 32-thread kernels at 28 blocks (<= 72 registers, a few spills) — Lazy Theta* 593k -> 723k, A* 992k -> 983k;
+// the 128-thread LoS kernels at 6 blocks (<= 80 registers) — Theta* 79.7k -> 87.5k, 8 blocks no better.
+#ifndef SEARCH_MINB1
+#define SEARCH_MINB1 28
+#endif
+#ifndef SEARCH_MINB4
+#define SEARCH_MINB4 6
+#endif
 template <int ALGO, int NW>
-__global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? SEARCH_MINB1 : SEARCH_MINB4) search_kernel(const SearchParams P) {
   constexpr bool IS_AGR = ALGO == ALGO_THETASTARAGR, IS_AGRPP = ALGO == ALGO_THETASTARAGRPP;
   constexpr bool IS_THETA = ALGO == ALGO_THETASTAR || IS_AGR || IS_AGRPP;  // one fastLOS per generated neighbour
   constexpr bool IS_LAZY = ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
   constexpr bool IS_COST = ALGO == ALGO_COSTASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
   __shared__ Shared sh;
+  __shared__ HeapEnt heap_top[kHeapTop];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const MapDev& m = P.map;
   Slot s;
   s.nodes = P.nodes + (size_t)blockIdx.x * P.cap;
   s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
   s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
+  s.top = heap_top;
   s.hmask = P.hcap - 1;
 
   // neighbour offset of this lane: L = 9a + 3b + c <-> (dx,dy,dz) = (dv[a],dv[b],dv[c])  (AStar.cpp:131-133)
@@ -272,7 +353,8 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
     bool cmotion = false;
     int cpar = -1;
     // per-lane neighbour state, live between the phases of one expansion
-    int nb_idx = -1;
+    int nb_idx = -1, nb_state = NODE_NEW, nb_hpos = -1;
+    double nb_g = 0;
     double nx = 0, ny = 0, nz = 0;
     for (;;) {
       bool valid = false;
@@ -282,8 +364,9 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
           status = ST_OPEN_EMPTY; last = cur; done = true;
         } else {
           open_peak = max(open_peak, s.heap_n);
-          cur = (int)heap_pop(s, lane);
-          NodeRec c = s.nodes[cur];
+          const HeapEnt top = s.top[0];
+          NodeRec c = s.nodes[top.idx];  // in flight while the root is being replaced
+          cur = (int)heap_pop(s, lane, top);
           if (IS_LAZY && c.parent >= 0 && c.parent != c.via) {
             // SetVertex: verify the optimistic parent with one fastLOS; fall back to the best closed neighbour
             const NodeRec pr = s.nodes[c.parent];
@@ -355,16 +438,19 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
           ++iter_num;
           __syncwarp();
           // ---- neighbour resolution (AStar.cpp:131-169), one lane per offset ----
-          nb_idx = -1;
+          nb_idx = -1; nb_state = NODE_NEW; nb_hpos = -1;
+          nb_g = __longlong_as_double(0x7ff0000000000000LL);  // what a node created below holds
           valid = lane_nb;
           nx = dadd(cx, ddx); ny = dadd(cy, ddy); nz = dadd(cz, ddz);            // :138
           if (valid && !is_in_map(m, nx, ny, nz)) valid = false;                 // :141
+          int occ = 0;
+          if (valid) occ = inflate_occ(m, nx, ny, nz);  // issued before the hash probe (independent loads overlap), used at :151
           if (valid) {
-            nb_idx = hash_find(s, nx, ny, nz);                                   // :146
-            if (nb_idx >= 0 && (s.nodes[nb_idx].state & 0xff) == NODE_CLOSED) valid = false;  // :147
+            nb_idx = hash_find_ex(s, nx, ny, nz, nb_state, nb_hpos, nb_g);       // :146
+            if (nb_idx >= 0 && (nb_state & 0xff) == NODE_CLOSED) valid = false;  // :147
             if (IS_AGRPP && nb_idx >= 0) valid = false;  // ThetaStarAGRpp.cpp:208-210: a node is relaxed once, at creation
           }
-          if (valid && inflate_occ(m, nx, ny, nz) == 1) valid = false;          // :151
+          if (valid && occ == 1) valid = false;                                  // :151
           const bool need = valid && nb_idx < 0;
           const unsigned cm = __ballot_sync(0xffffffffu, need);
           const int ncreate = __popc(cm);
@@ -452,7 +538,6 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
         double new_g = 0, new_f = 0, new_pen = 0;
         bool new_motion = false;
         if (valid) {
-          const NodeRec nb = s.nodes[nb_idx];
           int new_parent = cur;
           bool use_parent = false;
           if (IS_THETA && cpar >= 0) {
@@ -483,7 +568,7 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
           } else {  // AStar.cpp:57 / ThetaStar.cpp:39-47,61-69
             new_g = dadd(cg, edge_cost<IS_COST>(P, cx, cy, cz, nx, ny, nz, dnorm));
           }
-          if (new_g < nb.g) {
+          if (new_g < nb_g) {
             improved = true;
             new_f = dadd(new_g, dmul(P.lambda, dmul(P.tie, norm3(dsub(gx, nx), dsub(gy, ny), dsub(gz, nz)))));
             NodeRec* w = s.nodes + nb_idx;
@@ -494,17 +579,9 @@ __global__ void __launch_bounds__(NW * 32) search_kernel(const SearchParams P) {
           }
         }
         __syncwarp();
-        // open-list updates in lane (= expansion) order; (f, index) is a total order so the order is immaterial
-        unsigned im = __ballot_sync(0xffffffffu, improved);
-        while (im) {
-          const int b = __ffs(im) - 1;
-          im &= im - 1;
-          const uint32_t bi = (uint32_t)__shfl_sync(0xffffffffu, nb_idx, b);
-          const unsigned long long bk = fkey(__shfl_sync(0xffffffffu, new_f, b));
-          const int hp = s.nodes[bi].hpos;
-          if (hp >= 0) heap_sift_up(s, hp, bk, bi, lane);
-          else heap_push(s, bk, bi, lane);
-        }
+        // open-list updates.  (f, index) is a total order, so the pop sequence does not depend on the heap's layout:
+        // any valid heap holding the same entries will do.
+        heap_update_batch(s, improved, nb_hpos, fkey(new_f), (uint32_t)nb_idx, lane);
         if (status == ST_POOL_EXHAUSTED) {
           if (lane == 0) sh.state = 1;
         }
@@ -918,12 +995,54 @@ size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out) {
 }
 
 static inline bool algo_has_los_phase(int algo) { return algo == ALGO_THETASTAR || algo == ALGO_THETASTARAGR || algo == ALGO_THETASTARAGRPP; }
+// ---------------------------------------------------------------------------------------------------
+// launch order: longest-expected-first.  Blocks pull queries from a counter, so a long query that starts late
+// leaves its slot busy while every other slot idles (measured on 131 072 Lazy Theta* queries: slot time sums to
+// 180 ms per slot, batch takes 216 ms because the slowest query runs 88 ms).  Search effort correlates with the
+// start-goal distance (r = 0.69 on the C2 world), so queries are issued in descending distance; results are
+// indexed by the caller's query id either way.
+// ---------------------------------------------------------------------------------------------------
+__global__ void query_order_keys_kernel(const double* __restrict__ starts, const double* __restrict__ goals, int nq,
+                                        float* __restrict__ keys, int* __restrict__ ids) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const double dx = goals[3 * (size_t)q] - starts[3 * (size_t)q], dy = goals[3 * (size_t)q + 1] - starts[3 * (size_t)q + 1],
+               dz = goals[3 * (size_t)q + 2] - starts[3 * (size_t)q + 2];
+  const float d2 = (float)(dx * dx + dy * dy + dz * dz);
+  keys[q] = d2 == d2 ? d2 : 0.0f;  // NaN coordinates: any position in the order will do
+  ids[q] = q;
+}
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+static size_t query_order_sort_bytes(int nq) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, nq);
+  return bytes;
+}
+size_t query_order_bytes(int nq) { return 4 * align256((size_t)nq * 4) + align256(query_order_sort_bytes(nq)); }
+// returns the device array of nq query ids inside `buf` (query_order_bytes(nq) bytes)
+const int* launch_query_order(const double* starts, const double* goals, int nq, void* buf, cudaStream_t st) {
+  const size_t a = align256((size_t)nq * 4);
+  float* k_in = (float*)buf;
+  float* k_out = (float*)((char*)buf + a);
+  int* v_in = (int*)((char*)buf + 2 * a);
+  int* v_out = (int*)((char*)buf + 3 * a);
+  void* tmp = (char*)buf + 4 * a;
+  size_t tmp_bytes = query_order_sort_bytes(nq);
+  query_order_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(starts, goals, nq, k_in, v_in);
+  cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nq, 0, 32, st);
+  return v_out;
+}
+
 int search_threads_per_block(int algo) { return algo_has_los_phase(algo) ? 128 : 32; }
 // workspace slots (= resident thread blocks) per SM.  A thread-per-query variant of faithful A* was measured too:
 // 14x slower per expansion (495 vs 35 us) because SIMT divergence serialises the 32 different queries of a warp.
 int search_slots_per_sm(int algo, int faithful) {
   (void)faithful;
-  return algo_has_los_phase(algo) ? 4 : 16;
+  // measured on 1xB200, C2 world (queries/s): canonical A* 16 -> 685k, 24 -> 870k, 32 -> 911k slots/SM (32 resident
+  // blocks is the SM's limit); faithful A* 16 -> 6.99k, 32 -> 7.08k (kept at 16: half the workspace); 128-thread LoS
+  // kernels 4 -> 70.8k, 8 -> 78.2k, more is flat (registers allow 5 resident blocks).
+  if (algo_has_los_phase(algo)) return 6;
+  return faithful ? 16 : 32;
 }
 
 void launch_search(const SearchParams& p, int slots, cudaStream_t st) {

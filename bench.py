@@ -30,7 +30,7 @@ D_SAFE = 1.0
 # batch sizes are large enough that a reference-pathological query (faithful A* has a 1-in-2000 query with 100x the
 # expansions) amortises, as it does in the 1M-query configuration C4
 QUERY_ALGOS = (("lazythetastar", "canonical", 131072), ("astar", "faithful", 32768), ("astar", "canonical", 131072),
-               ("thetastar", "faithful", 8192), ("thetastar", "canonical", 16384))
+               ("thetastar", "faithful", 16384), ("thetastar", "canonical", 65536))
 
 
 def build_world(synth):
