@@ -43,6 +43,24 @@ class PlannerParams(C.Structure):
                 ("agr_ground_judge", C.c_double), ("agr_epsilon", C.c_double)]
 
 
+class DepthParams(C.Structure):
+    """b200_depth_params_t: the grid_map/* depth-fusion parameters (grid_map.cpp:21-43)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k_depth_scaling_factor", C.c_double), ("depth_filter_mindist", C.c_double),
+                ("depth_filter_maxdist", C.c_double), ("max_ray_length", C.c_double),
+                ("p_hit", C.c_double), ("p_miss", C.c_double), ("p_min", C.c_double), ("p_max", C.c_double),
+                ("p_occ", C.c_double), ("virtual_ceil_height", C.c_double),
+                ("use_depth_filter", C.c_int32), ("depth_filter_margin", C.c_int32), ("skip_pixel", C.c_int32),
+                ("local_map_margin", C.c_int32)]
+
+
+# the reference's defaults (grid_map.cpp:21-43)
+DEPTH_DEFAULTS = dict(fx=387.229248046875, fy=387.229248046875, cx=321.04638671875, cy=243.44969177246094,
+                      k_depth_scaling_factor=1000.0, depth_filter_mindist=0.2, depth_filter_maxdist=5.0, max_ray_length=4.5,
+                      p_hit=0.70, p_miss=0.35, p_min=0.12, p_max=0.97, p_occ=0.80, virtual_ceil_height=2.5,
+                      use_depth_filter=1, depth_filter_margin=1, skip_pixel=2, local_map_margin=1)
+
+
 RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), ("open_peak", "i4"), ("path_offset", "i8"),
                          ("g_final", "f8"), ("path_length", "f8"), ("explored_nodes", "i8"), ("iter_num", "i8"),
                          ("los_checks", "i8"), ("los_samples", "i8"), ("goal_coords", "f8", 3),
@@ -71,6 +89,12 @@ ABI = [
     ("b200_map_upload_inflate", C.c_int, [_vp, _vp]),
     ("b200_map_device_bits", C.c_int, [_vp, _pp, C.POINTER(_i64)]),
     ("b200_map_export_inflate_cloud", C.c_int, [_vp, _i32, _dbl, _vp, _i64, C.POINTER(_i64), _i32]),
+    ("b200_map_set_depth_params", C.c_int, [_vp, C.POINTER(DepthParams)]),
+    ("b200_map_update_depth", C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _i32, C.POINTER(_i32)]),
+    ("b200_map_get_occupancy", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
+    ("b200_map_download_occupancy", C.c_int, [_vp, _vp]),
+    ("b200_map_depth_stats", C.c_int, [_vp, C.POINTER(_i64)]),
+    ("b200_map_set_depth_frame_count", C.c_int, [_vp, _i32]),
     ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
@@ -198,6 +222,51 @@ class GridMap:
             _ck(lib().b200_map_reset(self.h))
         else:
             _ck(lib().b200_map_clear_box(self.h, _d3(min_pos), _d3(max_pos)))
+
+    # ---- depth-image fusion (grid_map.cpp:195-687) ----
+    def set_depth_params(self, **kw):
+        """grid_map/* depth parameters by the reference's names; unspecified ones take its defaults."""
+        d = dict(DEPTH_DEFAULTS)
+        d.update(kw)
+        p = DepthParams()
+        for k, v in d.items():
+            setattr(p, k, v)
+        _ck(lib().b200_map_set_depth_params(self.h, C.byref(p)))
+        self.depth_params = d
+
+    def depthPoseCallback(self, depth, cam_pos, cam_rot):
+        """depthPoseCallback + updateOccupancyCallback (grid_map.cpp:627-687) for one CV_16UC1 frame (numpy uint16
+        (rows, cols) or a CUDA tensor); cam_rot = camera-to-world rotation (3x3). Returns False if the frame was dropped."""
+        rot = (C.c_double * 9)(*[float(x) for x in np.asarray(cam_rot, dtype=np.float64).reshape(9)])
+        fused = C.c_int32(0)
+        if _is_dev(depth):
+            rows, cols, dev = depth.shape[0], depth.shape[1], 1
+        else:
+            depth = np.ascontiguousarray(depth, dtype=np.uint16)
+            rows, cols, dev = depth.shape[0], depth.shape[1], 0
+        _ck(lib().b200_map_update_depth(self.h, _ptr(depth), rows, cols, _d3(cam_pos), rot, dev, C.byref(fused)))
+        return bool(fused.value)
+
+    def getOccupancy(self, pos):
+        """getOccupancy(Vector3d) (grid_map.h:339-348) for an (n,3) batch -> int8 {-1,0,1}."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        _ck(lib().b200_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out), 0))
+        return out
+
+    def occupancy(self):
+        """occupancy_buffer_ (log-odds) as a (Nx,Ny,Nz) float64 array."""
+        out = np.empty(self.dims, dtype=np.float64)
+        _ck(lib().b200_map_download_occupancy(self.h, _ptr(out)))
+        return out
+
+    def depth_stats(self):
+        out = (C.c_int64 * 8)()
+        _ck(lib().b200_map_depth_stats(self.h, out))
+        return dict(zip(("projected", "rays_cast", "ray_steps", "updates", "order_rounds", "frames"), list(out)[:6]))
+
+    def set_depth_frame_count(self, n):
+        _ck(lib().b200_map_set_depth_frame_count(self.h, int(n)))
 
     def getInflateOccupancy(self, pos, out=None):
         """getInflateOccupancy (grid_map.h:350-359) for an (n,3) batch -> int8 {-1,0,1}."""

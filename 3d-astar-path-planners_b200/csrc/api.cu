@@ -71,6 +71,14 @@ struct b200_map {
   cudaEvent_t ev[12];
   double stage_ms[16];
   long long launches;
+  // depth-image fusion
+  b200_depth_params_t dprm;
+  bool depth_set, depth_ready, has_first_depth;
+  DepthDev dd;
+  void* depth_state;  // one allocation: occ | cnt_all | cnt_hit | F | Fnew | E | touched | walked | ctl
+  DevBuf depth_img, depth_rays, depth_paths;
+  int raycast_num;
+  int64_t depth_stats[8];
 };
 
 static inline int host_floor_idx(double pos, double origin, double inv, int n) {
@@ -181,6 +189,11 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->has_edt = false;
   m->d_safe = 0;
   m->profiling = false;
+  m->depth_set = m->depth_ready = m->has_first_depth = false;
+  m->depth_state = nullptr;
+  m->raycast_num = 0;
+  memset(&m->dd, 0, sizeof m->dd);
+  memset(m->depth_stats, 0, sizeof m->depth_stats);
   for (auto& ev : m->ev) cudaEventCreate(&ev);
   memset(m->stage_ms, 0, sizeof m->stage_ms);
   m->launches = 0;
@@ -205,6 +218,8 @@ int b200_map_destroy(b200_map_t* m) {
   cudaFree(m->d_dk);
   cudaFree(m->d_bounds);
   m->cloud.release(); m->stage_in.release(); m->stage_out.release(); m->stage_aux.release();
+  if (m->depth_state) cudaFree(m->depth_state);
+  m->depth_img.release(); m->depth_rays.release(); m->depth_paths.release();
   for (auto& ev : m->ev) cudaEventDestroy(ev);
   delete m;
   return B200_OK;
@@ -417,6 +432,236 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   m->d_safe = d_safe;
   return B200_OK;
 }
+// ---------------------------------------------------------------------------------------------------
+// depth-image fusion
+// ---------------------------------------------------------------------------------------------------
+static double order_key_to_double(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  double d;
+  memcpy(&d, &u, 8);
+  return d;
+}
+static int depth_ensure_state(b200_map* m) {
+  if (m->depth_ready) return B200_OK;
+  const size_t nvox = (size_t)m->N[0] * m->N[1] * m->N[2];
+  if (nvox >= 0xfffffffeULL) return fail(B200_ERR_UNSUPPORTED, "depth fusion: more than 2^32-2 voxels");
+  const size_t bytes = nvox * 8 + 7 * nvox * 4 + 2 * nvox + 512;
+  cudaError_t e = cudaMalloc(&m->depth_state, bytes);
+  if (e != cudaSuccess) { m->depth_state = nullptr; return fail(B200_ERR_NOMEM, "depth fusion state (38 bytes per voxel)", e); }
+  char* p = (char*)m->depth_state;
+  DepthDev& D = m->dd;
+  D.occ = (double*)p; p += nvox * 8;
+  D.cnt_all = (uint32_t*)p; p += nvox * 4;
+  D.cnt_hit = (uint32_t*)p; p += nvox * 4;
+  D.F = (uint32_t*)p; p += nvox * 4;
+  D.Fnew = (uint32_t*)p; p += nvox * 4;
+  D.E = (uint32_t*)p; p += nvox * 4;
+  D.touched = (uint32_t*)p; p += nvox * 4;
+  D.walked = (uint32_t*)p; p += nvox * 4;
+  D.flagT = (int8_t*)p; p += nvox;
+  D.flagE = (int8_t*)p; p += nvox;
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  D.ctl = (DepthCtl*)p;
+  static_assert(sizeof(DepthCtl) <= 256, "ctl block");
+  CK(cudaMemsetAsync(D.cnt_all, 0, nvox * 8, m->stream));  // cnt_all + cnt_hit (grid_map.cpp:82-83)
+  CK(cudaMemsetAsync(D.flagT, 0xff, nvox * 2, m->stream));  // flag_traverse_, flag_rayend_ = -1 (:84-85)
+  launch_depth_init(D, D.unknown, (long long)nvox, m->stream);  // :79 occupancy_buffer_ = clamp_min - unknown_flag; flags = none
+  m->launches++;
+  CK(cudaGetLastError());
+  m->depth_ready = true;
+  return B200_OK;
+}
+
+int b200_map_set_depth_params(b200_map_t* m, const b200_depth_params_t* p) {
+  REQUIRE(m && p, "NULL argument");
+  REQUIRE(p->fx != 0 && p->fy != 0 && p->k_depth_scaling_factor != 0, "depth params: fx, fy, k_depth_scaling_factor must be non-zero");
+  REQUIRE(p->skip_pixel >= 1 && p->depth_filter_margin >= 0, "depth params: skip_pixel >= 1, depth_filter_margin >= 0");
+  for (double q : {p->p_hit, p->p_miss, p->p_min, p->p_max, p->p_occ}) REQUIRE(q > 0 && q < 1, "depth params: probabilities must be in (0, 1)");
+  m->dprm = *p;
+  DepthDev& D = m->dd;
+  D.fx = p->fx; D.fy = p->fy; D.cx = p->cx; D.cy = p->cy;
+  D.scale = p->k_depth_scaling_factor;
+  D.inv_scale = 1.0 / p->k_depth_scaling_factor;  // grid_map.cpp:243
+  D.mindist = p->depth_filter_mindist; D.maxdist = p->depth_filter_maxdist; D.max_ray_length = p->max_ray_length;
+  // grid_map.h:27 `#define logit(x) (log((x) / (1 - (x))))` with the host's libm, exactly like the reference (:57-62)
+  D.prob_hit_log = std::log(p->p_hit / (1 - p->p_hit));
+  D.prob_miss_log = std::log(p->p_miss / (1 - p->p_miss));
+  D.clamp_min_log = std::log(p->p_min / (1 - p->p_min));
+  D.clamp_max_log = std::log(p->p_max / (1 - p->p_max));
+  D.min_occ_log = std::log(p->p_occ / (1 - p->p_occ));
+  const double unknown = D.clamp_min_log - 0.01;  // unknown_flag_, :62
+  if (m->depth_ready && unknown != D.unknown) return fail(B200_ERR_UNSUPPORTED, "depth params: p_min cannot change once the log-odds grid exists");
+  D.unknown = unknown;
+  D.use_filter = p->use_depth_filter ? 1 : 0; D.margin = p->depth_filter_margin; D.skip = p->skip_pixel;
+  for (int i = 0; i < 3; ++i) { D.minb[i] = m->minb[i]; D.maxb[i] = m->maxb[i]; }
+  D.max_steps = m->N[0] + m->N[1] + m->N[2] + 4;
+  m->depth_set = true;
+  return B200_OK;
+}
+
+int b200_map_set_depth_frame_count(b200_map_t* m, int32_t raycast_num) {
+  REQUIRE(m, "NULL map");
+  m->raycast_num = (int)(signed char)raycast_num;
+  return B200_OK;
+}
+int b200_map_depth_stats(b200_map_t* m, int64_t out[8]) {
+  REQUIRE(m && out, "NULL argument");
+  memcpy(out, m->depth_stats, sizeof m->depth_stats);
+  out[5] = m->raycast_num;
+  return B200_OK;
+}
+
+int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, int32_t cols, const double cam_pos[3],
+                          const double cam_rot[9], int32_t on_device, int32_t* fused) {
+  REQUIRE(m && depth && cam_pos && cam_rot && rows > 0 && cols > 0, "bad argument");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_update_depth: call b200_map_set_depth_params first");
+  CK(cudaSetDevice(m->prm.device));
+  cudaStream_t st = m->stream;
+  if (fused) *fused = 0;
+  memset(m->depth_stats, 0, sizeof m->depth_stats);
+  // depthPoseCallback's gate (grid_map.cpp:676-686): a frame whose camera is outside the map is not fused
+  for (int i = 0; i < 3; ++i)
+    if (cam_pos[i] < m->d.lo[i] || cam_pos[i] > m->d.hi[i]) return B200_OK;
+  if (fused) *fused = 1;
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  DepthDev& D = m->dd;
+  const b200_depth_params_t& P = m->dprm;
+  // which pixels become rays, in the reference's order (projectDepthImage, grid_map.cpp:212-231 / :233-275)
+  int rows_s, cols_s;
+  if (P.use_depth_filter) {
+    if (!m->has_first_depth) { m->has_first_depth = true; return B200_OK; }  // :235-237: the first frame only arms the filter
+    const int mg = P.depth_filter_margin, sk = P.skip_pixel;
+    rows_s = rows - 2 * mg > 0 ? (rows - 2 * mg + sk - 1) / sk : 0;
+    cols_s = cols - 2 * mg > 0 ? (cols - 2 * mg + sk - 1) / sk : 0;
+    if (rows_s > 0 && cols_s > 0) {
+      // :258 reads the pixel `skip_pixel` after the sampled one; it must exist
+      const long long last = (long long)(mg + (rows_s - 1) * sk) * cols + mg + (long long)(cols_s - 1) * sk + sk;
+      if (last >= (long long)rows * cols)
+        return fail(B200_ERR_UNSUPPORTED, "depth filter: skip_pixel reaches past the image end (the reference reads out of bounds here)");
+    }
+  } else {
+    rows_s = rows; cols_s = cols;
+  }
+  const long long n_rays = (long long)rows_s * cols_s;
+  if (n_rays == 0) return B200_OK;  // raycastProcess :323: nothing projected, nothing happens
+  REQUIRE(n_rays < 0x7fffffff, "depth image too large");
+  const uint16_t* d_img = depth;
+  if (!on_device) {
+    if (m->depth_img.ensure((size_t)rows * cols * 2)) return fail(B200_ERR_NOMEM, "depth image staging");
+    CK(cudaMemcpyAsync(m->depth_img.p, depth, (size_t)rows * cols * 2, cudaMemcpyHostToDevice, st));
+    d_img = (const uint16_t*)m->depth_img.p;
+  }
+  if (m->depth_rays.ensure((size_t)n_rays * 40)) return fail(B200_ERR_NOMEM, "ray records");
+  D.ray_pt = (double*)m->depth_rays.p;
+  D.ray_addr = (uint32_t*)((char*)m->depth_rays.p + (size_t)n_rays * 24);
+  D.cast_id = D.ray_addr + n_rays;
+  D.path_off = D.cast_id + n_rays;
+  D.path_len = D.path_off + n_rays;
+  D.rows = rows; D.cols = cols; D.cols_s = cols_s; D.n_rays = (int)n_rays;
+  for (int i = 0; i < 3; ++i) D.cam[i] = cam_pos[i];
+  for (int i = 0; i < 9; ++i) D.R[i] = cam_rot[i];
+  // `char raycast_num_` (grid_map.h:124): 127 is followed by -128
+  const int round = (int)(signed char)(m->raycast_num + 1);
+  D.round = (int8_t)round;
+  // index box of camera +- local_update_range (:431-438)
+  for (int i = 0; i < 3; ++i) {
+    const double org = i == 0 ? m->d.ox : i == 1 ? m->d.oy : m->d.oz;
+    D.loc_min[i] = host_floor_idx(cam_pos[i] - m->prm.local_update_range[i], org, m->d.inv_res, m->N[i]);
+    D.loc_max[i] = host_floor_idx(cam_pos[i] + m->prm.local_update_range[i], org, m->d.inv_res, m->N[i]);
+  }
+  DepthCtl ctl;
+  memset(&ctl, 0, sizeof ctl);
+  for (int i = 0; i < 3; ++i) { ctl.bbox[i] = ~0ULL; ctl.bbox[i + 3] = 0ULL; }
+  CK(cudaMemcpyAsync(D.ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice, st));
+  launch_depth_project(D, m->d, d_img, st);
+  launch_depth_path_count(D, m->d, st);
+  m->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&ctl, D.ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  m->depth_stats[0] = ctl.n_valid;
+  if (ctl.n_valid == 0) {  // every sampled pixel was filtered out: proj_points_cnt == 0, raycastProcess returns at once
+    return B200_OK;
+  }
+  m->raycast_num = round;  // :328
+  if (ctl.n_path_total >= 0xffffffffULL) return fail(B200_ERR_UNSUPPORTED, "depth fusion: more than 2^32 ray steps in one frame");
+  if (m->depth_paths.ensure((size_t)ctl.n_path_total * 4 + 4)) return fail(B200_ERR_NOMEM, "ray paths");
+  D.paths = (uint32_t*)m->depth_paths.p;
+  launch_depth_path_fill(D, m->d, ctl.n_cast_rays, st);
+  m->launches++;
+  // ray-order fixed point (see depth_kernels.cu): one cooperative launch
+  {
+    const int e = launch_depth_order(D, ctl.n_cast_rays, m->sm_count, st);
+    if (e) return fail(B200_ERR_CUDA, "depth fusion: cooperative launch", (cudaError_t)e);
+    m->launches++;
+  }
+  launch_depth_count(D, ctl.n_cast_rays, st);
+  launch_depth_update(D, m->d, m->sm_count, st);
+  m->launches += 3;
+  CK(cudaGetLastError());
+  // local bounds (:421-429): end-point box, extended by the camera position and the ground height
+  double mn[3], mx[3];
+  for (int i = 0; i < 3; ++i) {
+    mn[i] = std::min(m->maxb[i], order_key_to_double(ctl.bbox[i]));      // :332-334 start values
+    mx[i] = std::max(m->minb[i], order_key_to_double(ctl.bbox[i + 3]));  // :336-338
+    mn[i] = std::min(mn[i], cam_pos[i]);
+    mx[i] = std::max(mx[i], cam_pos[i]);
+  }
+  mx[2] = std::max(mx[2], m->prm.ground_height);
+  for (int i = 0; i < 3; ++i) {
+    const double org = i == 0 ? m->d.ox : i == 1 ? m->d.oy : m->d.oz;
+    m->lb_max[i] = host_floor_idx(mx[i], org, m->d.inv_res, m->N[i]);
+    m->lb_min[i] = host_floor_idx(mn[i], org, m->d.inv_res, m->N[i]);
+  }
+  m->bounds_pending = false;
+  // clearAndInflateLocalMap (:484-624)
+  int cut_min[3], cut_max[3], cutm_min[3], cutm_max[3];
+  for (int i = 0; i < 3; ++i) {
+    cut_min[i] = std::max(std::min(m->lb_min[i] - P.local_map_margin, m->N[i] - 1), 0);
+    cut_max[i] = std::max(std::min(m->lb_max[i] + P.local_map_margin, m->N[i] - 1), 0);
+    cutm_min[i] = std::max(std::min(cut_min[i] - 5, m->N[i] - 1), 0);
+    cutm_max[i] = std::max(std::min(cut_max[i] + 5, m->N[i] - 1), 0);
+  }
+  const int inf_step = (int)std::ceil(m->prm.obstacles_inflation / m->prm.resolution);  // :583
+  const int ceil_on = P.virtual_ceil_height > -0.5;
+  const int ceil_id = (int)std::floor((P.virtual_ceil_height - m->d.oz) * m->d.inv_res);  // :621
+  launch_depth_local_map(D, m->d, m->lb_min, m->lb_max, cut_min, cut_max, cutm_min, cutm_max, inf_step, ceil_on, ceil_id, m->sm_count, st);
+  m->launches += 4;
+  CK(cudaGetLastError());
+  m->has_edt = false;
+  CK(cudaMemcpyAsync(&ctl, D.ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  m->depth_stats[1] = (int64_t)ctl.n_cast;
+  m->depth_stats[2] = (int64_t)ctl.n_steps;
+  m->depth_stats[3] = (int64_t)ctl.n_updated;
+  m->depth_stats[4] = ctl.rounds;
+  if (ctl.rounds > ctl.n_cast_rays + 3u) return fail(B200_ERR_CUDA, "depth fusion: ray-order iteration did not converge");
+  return B200_OK;
+}
+
+int b200_map_get_occupancy(b200_map_t* m, const double* pos, int64_t n, int8_t* out, int32_t on_device) {
+  REQUIRE(m, "NULL map");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_get_occupancy: call b200_map_set_depth_params first");
+  CK(cudaSetDevice(m->prm.device));
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  return per_position<int8_t>(m, pos, n, out, 1, on_device, [&](const double* p, int8_t* o) {
+    launch_depth_get_occupancy(m->d, m->dd.occ, m->dd.min_occ_log, p, n, o, m->stream);
+  });
+}
+int b200_map_download_occupancy(b200_map_t* m, double* dst) {
+  REQUIRE(m && dst, "NULL argument");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_download_occupancy: call b200_map_set_depth_params first");
+  CK(cudaSetDevice(m->prm.device));
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  const size_t nvox = (size_t)m->N[0] * m->N[1] * m->N[2];
+  CK(cudaMemcpyAsync(dst, m->dd.occ, nvox * 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+
 int b200_map_build_edt(b200_map_t* m, double d_safe) { return build_edt_impl(m, d_safe, nullptr, nullptr, 0); }
 int b200_map_build_edt_slab(b200_map_t* m, double d_safe, const int32_t* below_gap, const int32_t* above_gap, int32_t on_device) {
   return build_edt_impl(m, d_safe, below_gap, above_gap, on_device);

@@ -1,0 +1,456 @@
+// depth_kernels.cu — depth-image fusion into the log-odds grid and the inflated occupancy grid.
+//
+// Behaviour restated from the reference (not ported): grid_map.cpp:195-318 projectDepthImage, :320-456 raycastProcess,
+// :458-482 closetPointInMap, :484-624 clearAndInflateLocalMap, :173-193 setCacheOccupancy, raycast.cpp:32-49,253-346
+// (RayCaster::setInput / step).  All position arithmetic is FP64 with separately rounded operations.
+//
+// The reference processes rays ONE AFTER THE OTHER and its result depends on that order in two places:
+//   (1) only the first ray (in pixel order) that ends in a voxel is cast at all (flag_rayend_, :385-395);
+//   (2) a ray stops at the first voxel an EARLIER ray of the same frame has crossed (flag_traverse_, :408-418).
+// Both are reproduced exactly without serialising the rays.  Every ray carries its position in the reference's
+// order as an id.  (1) is an atomicMin of ids per end voxel.  For (2) let F(v) be the smallest id of a ray that
+// REACHES voxel v; ray i stops at the first voxel with F(v) < i.  F is the unique fixed point of
+//   F(v) = min { i : v on ray i's path before i's first voxel w with F(w) < i }
+// (induction over i: ray 0 is never stopped, and what ray i reaches depends only on rays < i), so iterating
+// F_{k+1} = T(F_k) from F_0 = +inf until it stops changing yields exactly the sequential result; the iterates bracket
+// it (F_1 <= F_3 <= ... <= F <= ... <= F_4 <= F_2).  Rays to one camera centre almost form a tree, so a few rounds
+// suffice (the count is reported in the stats).  Hit/miss counters are then accumulated with plain atomics by one
+// last walk under the converged F, and the per-voxel log-odds update is order-free.
+//
+// Reference quirks kept on purpose:
+//   * the zero-depth test of the filtered projection reads the NEXT sampled pixel (:258);
+//   * the two flag arrays are never cleared: they hold the `char` frame counter raycast_num_ (grid_map.h:123-124) of
+//     the last frame that set them, and the counter wraps 127 -> -128.  A voxel last flagged exactly 256 fused frames
+//     ago — or never, in frame 255, whose number -1 is the arrays' initial value — therefore looks already taken at
+//     the start of the frame: no ray is cast to it, every ray stops at it.  Kept as persistent int8 arrays here;
+//   * the counters are `short` and a voxel is queued again each time its counter wraps round to 1;
+//   * inflation range-tests only the LINEAR address (:606-611), so a cube sticking out in y or z wraps around.
+#include <cooperative_groups.h>
+#include <cstdint>
+
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace b200 {
+
+namespace {
+constexpr uint32_t kNone = 0xffffffffu;      // F / E: no ray; ray_addr: pixel produced no ray
+constexpr uint32_t kOutside = 0xfffffffeu;   // ray_addr: end point outside the buffer (never deduplicated)
+
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+// grid_map.h:400-404 + :257-265 on a world position; -1 when the linear address falls outside the buffer
+__device__ __forceinline__ long long pos_address(const MapDev& m, double x, double y, double z) {
+  const long long ix = pos_to_idx1(x, m.ox, m.inv_res), iy = pos_to_idx1(y, m.oy, m.inv_res), iz = pos_to_idx1(z, m.oz, m.inv_res);
+  const long long a = ix * m.Ny * m.Nz + iy * m.Nz + iz;
+  const long long total = (long long)m.Nx * m.Ny * m.Nz;
+  return (a < 0 || a >= total) ? -1 : a;
+}
+__device__ __forceinline__ void append(uint32_t* list, unsigned* n, uint32_t a) { list[atomicAdd(n, 1u)] = a; }
+
+// raycast.cpp:32-49
+__device__ __forceinline__ double ray_mod1(double v) { return fmod(dadd(fmod(v, 1.0), 1.0), 1.0); }
+__device__ __forceinline__ double ray_intbound(double s, double ds) {
+  if (ds < 0) { s = -s; ds = -ds; }
+  return __ddiv_rn(dsub(1.0, ray_mod1(s)), ds);
+}
+struct RayWalk {  // raycast.cpp:253-346
+  int x, y, z, ex, ey, ez, sx, sy, sz;
+  double tmx, tmy, tmz, tdx, tdy, tdz;
+  __device__ __forceinline__ void set(double ax, double ay, double az, double bx, double by, double bz) {
+    x = (int)floor(ax); y = (int)floor(ay); z = (int)floor(az);
+    ex = (int)floor(bx); ey = (int)floor(by); ez = (int)floor(bz);
+    const double dx = ex - x, dy = ey - y, dz = ez - z;
+    sx = (dx > 0) - (dx < 0); sy = (dy > 0) - (dy < 0); sz = (dz > 0) - (dz < 0);
+    tmx = ray_intbound(ax, dx); tmy = ray_intbound(ay, dy); tmz = ray_intbound(az, dz);
+    tdx = __ddiv_rn((double)sx, dx); tdy = __ddiv_rn((double)sy, dy); tdz = __ddiv_rn((double)sz, dz);
+  }
+  __device__ __forceinline__ bool step(int& ox, int& oy, int& oz) {
+    ox = x; oy = y; oz = z;
+    if (x == ex && y == ey && z == ez) return false;
+    if (tmx < tmy) {
+      if (tmx < tmz) { x += sx; tmx = dadd(tmx, tdx); } else { z += sz; tmz = dadd(tmz, tdz); }
+    } else {
+      if (tmy < tmz) { y += sy; tmy = dadd(tmy, tdy); } else { z += sz; tmz = dadd(tmz, tdz); }
+    }
+    return true;
+  }
+};
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+// projection + ray end points (projectDepthImage, first half of raycastProcess' per-point body)
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_project_kernel(DepthDev D, MapDev m, const uint16_t* __restrict__ img) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  double px = 0, py = 0, pz = 0;
+  bool valid = id < D.n_rays;
+  if (valid) {
+    int u, v;
+    double depth;
+    if (D.use_filter) {
+      v = D.margin + (id / D.cols_s) * D.skip;
+      u = D.margin + (id % D.cols_s) * D.skip;
+      const size_t at = (size_t)v * D.cols + u;
+      depth = dmul((double)img[at], D.inv_scale);
+      if (img[at + D.skip] == 0) depth = dadd(D.max_ray_length, 0.1);      // :258 (the pointer was advanced first)
+      else if (depth < D.mindist) valid = false;                          // :262
+      else if (depth > D.maxdist) depth = dadd(D.max_ray_length, 0.1);    // :266
+    } else {
+      v = id / D.cols; u = id % D.cols;
+      depth = __ddiv_rn((double)img[id], D.scale);                         // :222
+    }
+    if (valid) {
+      const double qx = __ddiv_rn(dmul(dsub((double)u, D.cx), depth), D.fx);
+      const double qy = __ddiv_rn(dmul(dsub((double)v, D.cy), depth), D.fy);
+      const double qz = depth;
+      px = dadd(dadd(dadd(dmul(D.R[0], qx), dmul(D.R[1], qy)), dmul(D.R[2], qz)), D.cam[0]);
+      py = dadd(dadd(dadd(dmul(D.R[3], qx), dmul(D.R[4], qy)), dmul(D.R[5], qz)), D.cam[1]);
+      pz = dadd(dadd(dadd(dmul(D.R[6], qx), dmul(D.R[7], qy)), dmul(D.R[8], qz)), D.cam[2]);
+    }
+  }
+  int occ = 0;
+  if (valid) {
+    const double cx = D.cam[0], cy = D.cam[1], cz = D.cam[2];
+    bool inside = is_in_map(m, px, py, pz);
+    if (!inside) {  // closetPointInMap, :458-482
+      const double diff[3] = {dsub(px, cx), dsub(py, cy), dsub(pz, cz)};
+      double min_t = 1000000;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (fabs(diff[i]) > 0) {
+          const double t1 = __ddiv_rn(dsub(D.maxb[i], D.cam[i]), diff[i]);
+          if (t1 > 0 && t1 < min_t) min_t = t1;
+          const double t2 = __ddiv_rn(dsub(D.minb[i], D.cam[i]), diff[i]);
+          if (t2 > 0 && t2 < min_t) min_t = t2;
+        }
+      const double k = dsub(min_t, 1e-3);
+      px = dadd(cx, dmul(k, diff[0])); py = dadd(cy, dmul(k, diff[1])); pz = dadd(cz, dmul(k, diff[2]));
+    }
+    const double dx = dsub(px, cx), dy = dsub(py, cy), dz = dsub(pz, cz);
+    const double len = norm3(dx, dy, dz);
+    if (len > D.max_ray_length) {  // :354-357 / :364-368
+      px = dadd(dmul(__ddiv_rn(dx, len), D.max_ray_length), cx);
+      py = dadd(dmul(__ddiv_rn(dy, len), D.max_ray_length), cy);
+      pz = dadd(dmul(__ddiv_rn(dz, len), D.max_ray_length), cz);
+    } else if (inside) {
+      occ = 1;  // :371
+    }
+  }
+  // bounding box of the (clamped) end points, :375-381
+  unsigned long long k[6];
+  k[0] = valid ? dkey(px) : ~0ULL; k[1] = valid ? dkey(py) : ~0ULL; k[2] = valid ? dkey(pz) : ~0ULL;
+  k[3] = valid ? dkey(px) : 0ULL;  k[4] = valid ? dkey(py) : 0ULL;  k[5] = valid ? dkey(pz) : 0ULL;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      k[i] = min(k[i], __shfl_xor_sync(0xffffffffu, k[i], o));
+      k[i + 3] = max(k[i + 3], __shfl_xor_sync(0xffffffffu, k[i + 3], o));
+    }
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0 && any) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { atomicMin(&D.ctl->bbox[i], k[i]); atomicMax(&D.ctl->bbox[i + 3], k[i + 3]); }
+    atomicAdd(&D.ctl->n_valid, (unsigned)__popc(any));
+  }
+  if (id >= D.n_rays) return;
+  uint32_t addr = kNone;
+  if (valid) {
+    const long long a = pos_address(m, px, py, pz);
+    if (a < 0) {
+      addr = kOutside;
+    } else {  // setCacheOccupancy, :173-193
+      addr = (uint32_t)a;
+      if (atomicAdd(&D.cnt_all[a], 1u) == 0u) append(D.touched, &D.ctl->n_touched, addr);
+      if (occ) atomicAdd(&D.cnt_hit[a], 1u);
+      atomicMin(&D.E[a], (uint32_t)id);
+    }
+    D.ray_pt[3 * (size_t)id] = px; D.ray_pt[3 * (size_t)id + 1] = py; D.ray_pt[3 * (size_t)id + 2] = pz;
+  }
+  D.ray_addr[id] = addr;
+}
+
+// --------------------------------------------------------------------------------------------------
+// ray paths.  The voxel sequence of a ray (RayCaster, raycast.cpp:253-346) depends only on its two end points, so it
+// is traced ONCE per frame into a compact list; every round of the ordering iteration and the counting pass then read
+// addresses instead of re-running the FP64 traversal (measured: 35-40 rounds per 640x480 frame, and a round of
+// dependent DDA steps costs ~50 us against ~5 us for a warp reading 32 cached voxels at a time).
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ray_is_cast(const DepthDev& D, int id) {
+  const uint32_t ea = D.ray_addr[id];
+  if (ea == kNone) return false;
+  // :385-395: the end voxel was already taken — by an earlier ray of this frame, or its flag still holds this round's number
+  return ea == kOutside || (D.flagE[ea] != D.round && D.E[ea] == (uint32_t)id);
+}
+__device__ __forceinline__ void ray_setup(const DepthDev& D, const MapDev& m, int id, RayWalk& w) {
+  const double px = D.ray_pt[3 * (size_t)id], py = D.ray_pt[3 * (size_t)id + 1], pz = D.ray_pt[3 * (size_t)id + 2];
+  w.set(__ddiv_rn(px, m.res), __ddiv_rn(py, m.res), __ddiv_rn(pz, m.res), __ddiv_rn(D.cam[0], m.res), __ddiv_rn(D.cam[1], m.res),
+        __ddiv_rn(D.cam[2], m.res));  // :397
+}
+// pass 1: which rays are cast, and how long their paths are
+__global__ void __launch_bounds__(128) depth_path_count_kernel(DepthDev D, MapDev m) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= D.n_rays || !ray_is_cast(D, id)) return;
+  RayWalk w;
+  ray_setup(D, m, id, w);
+  int ix, iy, iz;
+  unsigned steps = 0;
+  while (steps < (unsigned)D.max_steps && w.step(ix, iy, iz)) ++steps;
+  const unsigned slot = atomicAdd(&D.ctl->n_cast_rays, 1u);
+  D.cast_id[slot] = (uint32_t)id;
+  D.path_len[slot] = steps;
+  D.path_off[slot] = atomicAdd(&D.ctl->n_path_total, (unsigned long long)steps);
+}
+// pass 2: the voxel addresses (kNone where the cell centre falls outside the buffer: such a cell is stepped over, :401-404)
+__global__ void __launch_bounds__(128) depth_path_fill_kernel(DepthDev D, MapDev m) {
+  const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= D.ctl->n_cast_rays) return;
+  RayWalk w;
+  ray_setup(D, m, (int)D.cast_id[slot], w);
+  uint32_t* out = D.paths + D.path_off[slot];
+  const unsigned len = D.path_len[slot];
+  int ix, iy, iz;
+  for (unsigned k = 0; k < len && w.step(ix, iy, iz); ++k) {
+    const long long a = pos_address(m, dmul(dadd((double)ix, 0.5), m.res), dmul(dadd((double)iy, 0.5), m.res),
+                                    dmul(dadd((double)iz, 0.5), m.res));  // :401
+    out[k] = a < 0 ? kNone : (uint32_t)a;
+  }
+}
+// One cast ray handled by one warp, 32 path voxels per step.  MODE 0: a round of the ordering iteration (reads F, writes
+// Fnew); MODE 1: the counting walk under the converged F.
+template <int MODE>
+__device__ __forceinline__ void walk_path(const DepthDev& D, unsigned slot, int lane, bool first_round) {
+  const uint32_t id = D.cast_id[slot];
+  const uint32_t* path = D.paths + D.path_off[slot];
+  const unsigned len = D.path_len[slot];
+  unsigned steps = len;
+  for (unsigned base = 0; base < len; base += 32) {
+    const unsigned k = base + lane;
+    const uint32_t a = k < len ? path[k] : kNone;
+    // :410 flag_traverse_[v] == raycast_num_ at the moment ray `id` arrives
+    const bool taken = a != kNone && (D.flagT[a] == D.round || D.F[a] < id);
+    const unsigned tm = __ballot_sync(0xffffffffu, taken);
+    const int first = tm ? __ffs(tm) - 1 : 32;
+    if (MODE == 0) {
+      if (a != kNone && lane < first) {
+        const uint32_t old = atomicMin(&D.Fnew[a], id);
+        if (first_round && old == kNone) append(D.walked, &D.ctl->n_walked, a);
+      }
+    } else {
+      // :406 the voxel the ray stops at is counted too (the count comes before the stop test)
+      if (a != kNone && lane <= first && atomicAdd(&D.cnt_all[a], 1u) == 0u) append(D.touched, &D.ctl->n_touched, a);
+    }
+    if (tm) { steps = base + (unsigned)first + 1u; break; }
+  }
+  if (MODE == 1 && lane == 0) {
+    atomicAdd(&D.ctl->n_cast, 1ull);
+    atomicAdd(&D.ctl->n_steps, (unsigned long long)steps);
+  }
+}
+__global__ void __launch_bounds__(128) depth_count_kernel(DepthDev D) {
+  const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot < D.ctl->n_cast_rays) walk_path<1>(D, slot, threadIdx.x & 31, false);
+}
+// The whole fixed-point iteration in one cooperative launch: per round every cast ray walks under F into Fnew, after
+// which Fnew becomes F on the voxels the first round walked (a superset of every later round's), until a round
+// changes nothing.
+__global__ void __launch_bounds__(128) depth_order_kernel(DepthDev D) {
+  cg::grid_group grid = cg::this_grid();
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const unsigned n_cast = D.ctl->n_cast_rays;
+  unsigned round = 0;
+  for (;; ++round) {
+    for (unsigned slot = tid >> 5; slot < n_cast; slot += nthreads >> 5) walk_path<0>(D, slot, threadIdx.x & 31, round == 0);
+    if (tid == 0) D.ctl->changed[(round + 1) % 3] = 0u;  // three slots: the one read at the end of the previous round is left alone
+    grid.sync();
+    const unsigned n = D.ctl->n_walked;
+    bool any = false;
+    for (unsigned i = tid; i < n; i += nthreads) {
+      const uint32_t a = D.walked[i];
+      const uint32_t f = D.Fnew[a];
+      if (f != D.F[a]) { D.F[a] = f; any = true; }
+      D.Fnew[a] = kNone;
+    }
+    if (any) D.ctl->changed[round % 3] = 1u;
+    grid.sync();
+    if (D.ctl->changed[round % 3] == 0u || round > n_cast + 2u) break;
+  }
+  if (tid == 0) D.ctl->rounds = round + 1u;
+}
+// end of frame: the persistent flags take this frame's number, the per-frame ray ids go back to "none"
+__global__ void __launch_bounds__(256) depth_reset_kernel(DepthDev D) {
+  const unsigned n = D.ctl->n_walked, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned i = t0; i < n; i += stride) {
+    const uint32_t a = D.walked[i];
+    if (D.F[a] != kNone) D.flagT[a] = D.round;  // :416: every voxel some ray reached keeps this frame's number
+    D.F[a] = kNone; D.Fnew[a] = kNone;
+  }
+  for (unsigned i = t0; i < (unsigned)D.n_rays; i += stride) {
+    const uint32_t a = D.ray_addr[i];
+    if (a < kOutside) { D.flagE[a] = D.round; D.E[a] = kNone; }  // :393
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// log-odds update of every voxel touched this frame (raycastProcess :431-455)
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_update_kernel(DepthDev D, MapDev m) {
+  const unsigned n = D.ctl->n_touched;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const uint32_t a = D.touched[i];
+  const uint32_t n_all = D.cnt_all[a], n_hit = D.cnt_hit[a];
+  D.cnt_all[a] = 0u; D.cnt_hit[a] = 0u;
+  // the reference's counters are `short`: they hold the totals modulo 2^16, and the voxel was queued once per wrap to 1
+  const int all_s = (int)(short)(uint16_t)n_all, hit_s = (int)(short)(uint16_t)n_hit;
+  const unsigned pushes = (n_all - 1u) / 65536u + 1u;
+  const int nyz = m.Ny * m.Nz;
+  const int ix = (int)(a / (uint32_t)nyz), iy = (int)((a % (uint32_t)nyz) / (uint32_t)m.Nz), iz = (int)(a % (uint32_t)m.Nz);
+  const bool in_local = ix >= D.loc_min[0] && ix <= D.loc_max[0] && iy >= D.loc_min[1] && iy <= D.loc_max[1] &&
+                        iz >= D.loc_min[2] && iz <= D.loc_max[2];
+  double o = D.occ[a];
+  for (unsigned p = 0; p < pushes; ++p) {
+    const double upd = (p == 0 ? hit_s >= all_s - hit_s : true) ? D.prob_hit_log : D.prob_miss_log;
+    if (upd >= 0 && o >= D.clamp_max_log) continue;
+    if (upd <= 0 && o <= D.clamp_min_log) { o = D.clamp_min_log; continue; }
+    if (!in_local) o = D.clamp_min_log;
+    o = fmin(fmax(dadd(o, upd), D.clamp_min_log), D.clamp_max_log);
+  }
+  D.occ[a] = o;
+  atomicAdd(&D.ctl->n_updated, (unsigned long long)pushes);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// clearAndInflateLocalMap (:484-624)
+// --------------------------------------------------------------------------------------------------
+struct Box { int lo[3], hi[3]; };
+__device__ __forceinline__ bool box_cell(const Box& b, long long t, int& x, int& y, int& z) {
+  const int nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
+  if (nx <= 0 || ny <= 0 || nz <= 0 || t >= (long long)nx * ny * nz) return false;
+  z = b.lo[2] + (int)(t % nz);
+  y = b.lo[1] + (int)((t / nz) % ny);
+  x = b.lo[0] + (int)(t / ((long long)nz * ny));
+  return true;
+}
+// every voxel of box M outside box C becomes "unknown" (:531-579: three slab loops whose union is M \ C)
+__global__ void __launch_bounds__(256) depth_shell_kernel(DepthDev D, MapDev m, Box M, Box C) {
+  int x, y, z;
+  if (!box_cell(M, blockIdx.x * (long long)blockDim.x + threadIdx.x, x, y, z)) return;
+  const bool inside = x >= C.lo[0] && x <= C.hi[0] && y >= C.lo[1] && y <= C.hi[1] && z >= C.lo[2] && z <= C.hi[2];
+  if (!inside) D.occ[vox_addr(m, x, y, z)] = D.unknown;
+}
+__device__ __forceinline__ void set_inflate_linear(const MapDev& m, long long a) {
+  const long long total = (long long)m.Nx * m.Ny * m.Nz;
+  if (a < 0 || a >= total) return;  // :608 — the only range test there is
+  const int nyz = m.Ny * m.Nz;
+  const int x = (int)(a / nyz), y = (int)((a % nyz) / m.Nz), z = (int)(a % m.Nz);
+  atomicOr(m.occ + ((size_t)x * m.Ny + y) * m.wz + (z >> 5), 1u << (z & 31));
+}
+// occupied voxels of the local box stamp the full (2*step+1)^3 cube (:598-616, grid_map.h:412-441)
+__global__ void __launch_bounds__(256) depth_inflate_kernel(DepthDev D, MapDev m, Box L, int step) {
+  int x, y, z;
+  if (!box_cell(L, blockIdx.x * (long long)blockDim.x + threadIdx.x, x, y, z)) return;
+  if (!(D.occ[vox_addr(m, x, y, z)] > D.min_occ_log)) return;
+  for (int dx = -step; dx <= step; ++dx)
+    for (int dy = -step; dy <= step; ++dy)
+      for (int dz = -step; dz <= step; ++dz)
+        set_inflate_linear(m, (long long)(x + dx) * m.Ny * m.Nz + (long long)(y + dy) * m.Nz + (z + dz));
+}
+// virtual ceiling (:618-627)
+__global__ void __launch_bounds__(256) depth_ceiling_kernel(MapDev m, Box L, int ceil_id) {
+  const int nx = L.hi[0] - L.lo[0] + 1, ny = L.hi[1] - L.lo[1] + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (nx <= 0 || ny <= 0 || t >= (long long)nx * ny) return;
+  const int x = L.lo[0] + (int)(t / ny), y = L.lo[1] + (int)(t % ny);
+  set_inflate_linear(m, (long long)x * m.Ny * m.Nz + (long long)y * m.Nz + ceil_id);
+}
+
+// getOccupancy(Vector3d), grid_map.h:339-348
+__global__ void depth_get_occupancy_kernel(MapDev m, const double* __restrict__ occ, double min_occ_log, const double* __restrict__ pos,
+                                           long long n, int8_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+  if (!is_in_map(m, x, y, z)) { out[i] = -1; return; }
+  const int ix = pos_to_idx1(x, m.ox, m.inv_res), iy = pos_to_idx1(y, m.oy, m.inv_res), iz = pos_to_idx1(z, m.oz, m.inv_res);
+  out[i] = occ[vox_addr(m, ix, iy, iz)] > min_occ_log ? 1 : 0;
+}
+__global__ void depth_fill_kernel(double* __restrict__ p, double v, uint32_t* __restrict__ f0, uint32_t* __restrict__ f1,
+                                  uint32_t* __restrict__ f2, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = v; f0[i] = kNone; f1[i] = kNone; f2[i] = kNone;
+}
+
+// --------------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+void launch_depth_init(const DepthDev& D, double unknown, long long nvox, cudaStream_t st) {
+  depth_fill_kernel<<<blocks_for(nvox, 256), 256, 0, st>>>(D.occ, unknown, D.F, D.Fnew, D.E, nvox);
+}
+void launch_depth_project(const DepthDev& D, const MapDev& m, const uint16_t* img, cudaStream_t st) {
+  if (D.n_rays > 0) depth_project_kernel<<<blocks_for(D.n_rays, 256), 256, 0, st>>>(D, m, img);
+}
+void launch_depth_path_count(const DepthDev& D, const MapDev& m, cudaStream_t st) {
+  depth_path_count_kernel<<<blocks_for(D.n_rays, 128), 128, 0, st>>>(D, m);
+}
+void launch_depth_path_fill(const DepthDev& D, const MapDev& m, unsigned n_cast, cudaStream_t st) {
+  if (n_cast) depth_path_fill_kernel<<<blocks_for(n_cast, 128), 128, 0, st>>>(D, m);
+}
+// the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
+int launch_depth_order(const DepthDev& D, unsigned n_cast, int sm_count, cudaStream_t st) {
+  if (n_cast == 0) return 0;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_order_kernel, 128, 0);
+  if (e != cudaSuccess) return (int)e;
+  const unsigned want = blocks_for((long long)n_cast * 32, 128);  // a warp per cast ray
+  unsigned grid = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)sm_count;
+  if (grid > want) grid = want;
+  DepthDev d = D;
+  void* args[] = {&d};
+  return (int)cudaLaunchCooperativeKernel((void*)depth_order_kernel, dim3(grid), dim3(128), args, 0, st);
+}
+void launch_depth_count(const DepthDev& D, unsigned n_cast, cudaStream_t st) {
+  if (n_cast) depth_count_kernel<<<blocks_for((long long)n_cast * 32, 128), 128, 0, st>>>(D);
+}
+void launch_depth_update(const DepthDev& D, const MapDev& m, int sm_count, cudaStream_t st) {
+  depth_update_kernel<<<sm_count * 8, 256, 0, st>>>(D, m);
+  depth_reset_kernel<<<sm_count * 8, 256, 0, st>>>(D);
+}
+void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min[3], const int lb_max[3], const int cut_min[3],
+                            const int cut_max[3], const int cutm_min[3], const int cutm_max[3], int inf_step, int ceil_on, int ceil_id,
+                            int sm_count, cudaStream_t st) {
+  Box L, C, M;
+  for (int i = 0; i < 3; ++i) {
+    L.lo[i] = lb_min[i]; L.hi[i] = lb_max[i];
+    C.lo[i] = cut_min[i]; C.hi[i] = cut_max[i];
+    M.lo[i] = cutm_min[i]; M.hi[i] = cutm_max[i];
+  }
+  auto cells = [](const Box& b) {
+    long long n = 1;
+    for (int i = 0; i < 3; ++i) n *= (b.hi[i] >= b.lo[i]) ? (b.hi[i] - b.lo[i] + 1) : 0;
+    return n;
+  };
+  if (cells(M) > 0) depth_shell_kernel<<<blocks_for(cells(M), 256), 256, 0, st>>>(D, m, M, C);
+  if (cells(L) > 0) {
+    launch_clear_box(m, lb_min, lb_max, sm_count, st);  // :588-596
+    depth_inflate_kernel<<<blocks_for(cells(L), 256), 256, 0, st>>>(D, m, L, inf_step);
+    if (ceil_on) {
+      const long long cols = (long long)(L.hi[0] - L.lo[0] + 1) * (L.hi[1] - L.lo[1] + 1);
+      depth_ceiling_kernel<<<blocks_for(cols, 256), 256, 0, st>>>(m, L, ceil_id);
+    }
+  }
+}
+void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
+                                cudaStream_t st) {
+  if (n > 0) depth_get_occupancy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(m, occ, min_occ_log, pos, n, out);
+}
+
+}  // namespace b200

@@ -94,6 +94,49 @@ struct SearchParams {
 // <= 1.0 for thetastar and up to 4.4 for astar at lambda = 1 (oracle, C3 map), hence 8x for faithful astar.
 inline int open_region_factor(int algo, int faithful) { return (faithful && algo == 0) ? 8 : 2; }
 inline size_t open_region_entries(int cap, int factor) { return (size_t)factor * (size_t)cap + 32; }
+// ---- depth-image fusion (depth_kernels.cu) ----
+struct DepthCtl {                 // device-side counters of one frame
+  unsigned long long bbox[6];     // order-preserving keys: min x,y,z then max x,y,z of the ray end points
+  unsigned long long n_cast, n_steps, n_updated, n_path_total;
+  unsigned n_valid, n_touched, n_walked, rounds, n_cast_rays;
+  unsigned changed[3];
+};
+struct DepthDev {
+  // grid_map.h:60-78 (MappingParameters), logits precomputed on the host with libm like the reference
+  double fx, fy, cx, cy, scale, inv_scale, mindist, maxdist, max_ray_length;
+  double prob_hit_log, prob_miss_log, clamp_min_log, clamp_max_log, min_occ_log, unknown;
+  int use_filter, margin, skip;
+  // this frame
+  int rows, cols, cols_s, n_rays, max_steps;
+  int8_t round;                   // raycast_num_ of this frame (`char`: wraps 127 -> -128)
+  double cam[3], R[9];            // R row-major, camera -> world
+  double minb[3], maxb[3];        // map_min_boundary_ / map_max_boundary_
+  int loc_min[3], loc_max[3];     // index box of camera +- local_update_range
+  // state in HBM (per voxel unless noted)
+  double* occ;                    // occupancy_buffer_ (log-odds)
+  uint32_t *cnt_all, *cnt_hit;    // count_hit_and_miss_, count_hit_ (exact totals; the reference's shorts are their low 16 bits)
+  uint32_t *F, *Fnew, *E;         // this frame: smallest ray id reaching / ending in the voxel (0xffffffff = none)
+  int8_t *flagT, *flagE;          // flag_traverse_, flag_rayend_: raycast_num_ of the last frame that set them (never cleared)
+  uint32_t *touched, *walked;     // voxel lists: counted this frame / reached in the first round
+  double* ray_pt;                 // [n_rays][3] clamped ray end points
+  uint32_t* ray_addr;             // [n_rays] end voxel address
+  uint32_t *cast_id, *path_off, *path_len;  // [n_cast_rays] the rays that are cast: id, and their slice of `paths`
+  uint32_t* paths;                // voxel address sequences of the cast rays (0xffffffff = cell outside the buffer)
+  DepthCtl* ctl;
+};
+void launch_depth_init(const DepthDev& D, double unknown, long long nvox, cudaStream_t st);
+void launch_depth_project(const DepthDev& D, const MapDev& m, const uint16_t* img, cudaStream_t st);
+void launch_depth_path_count(const DepthDev& D, const MapDev& m, cudaStream_t st);
+void launch_depth_path_fill(const DepthDev& D, const MapDev& m, unsigned n_cast, cudaStream_t st);
+int launch_depth_order(const DepthDev& D, unsigned n_cast, int sm_count, cudaStream_t st);
+void launch_depth_count(const DepthDev& D, unsigned n_cast, cudaStream_t st);
+void launch_depth_update(const DepthDev& D, const MapDev& m, int sm_count, cudaStream_t st);
+void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min[3], const int lb_max[3], const int cut_min[3],
+                            const int cut_max[3], const int cutm_min[3], const int cutm_max[3], int inf_step, int ceil_on, int ceil_id,
+                            int sm_count, cudaStream_t st);
+void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
+                                cudaStream_t st);
+
 size_t search_slot_bytes(int cap, int open_factor, uint32_t* hcap_out);
 int search_threads_per_block(int algo);
 int search_slots_per_sm(int algo, int faithful);

@@ -104,3 +104,64 @@ def random_queries(seed, occ_fn, origin, size, n, min_dist=5.0, z_range=None, ma
         goals.append(b)
         need -= len(a)
     return np.concatenate(starts, 0), np.concatenate(goals, 0)
+
+
+# ---- depth frames: pillars + ground rendered through a pinhole camera ----
+def pillar_boxes(seed, origin, size, n_pillars):
+    """(n,6) axis-aligned boxes [x0,y0,z0,x1,y1,z1], same distributions as forest()."""
+    rng = np.random.default_rng(seed)
+    o, s = np.asarray(origin, dtype=np.float64), np.asarray(size, dtype=np.float64)
+    w = rng.uniform(0.5, 1.2, n_pillars)
+    h = rng.uniform(0.8, 3.0, n_pillars)
+    cx = rng.uniform(o[0] + 1.0, o[0] + s[0] - 1.0, n_pillars)
+    cy = rng.uniform(o[1] + 1.0, o[1] + s[1] - 1.0, n_pillars)
+    return np.stack([cx - w / 2, cy - w / 2, np.full(n_pillars, o[2]), cx + w / 2, cy + w / 2, o[2] + h], 1)
+
+
+def look_at(yaw, pitch=0.0):
+    """Camera-to-world rotation (row-major 3x3) of an optical frame (x right, y down, z forward) looking along `yaw`
+    (rad, about world z) and `pitch` (rad, positive = down), and the matching quaternion (w, x, y, z)."""
+    cyw, syw, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    fwd = np.array([cyw * cp, syw * cp, -sp])
+    right = np.array([syw, -cyw, 0.0])
+    down = np.cross(fwd, right)
+    R = np.stack([right, down, fwd], 1)
+    tr = np.trace(R)
+    if tr > 0:
+        k = np.sqrt(tr + 1.0) * 2
+        q = np.array([k / 4, (R[2, 1] - R[1, 2]) / k, (R[0, 2] - R[2, 0]) / k, (R[1, 0] - R[0, 1]) / k])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, l = (i + 1) % 3, (i + 2) % 3
+        k = np.sqrt(1.0 + R[i, i] - R[j, j] - R[l, l]) * 2
+        q = np.zeros(4)
+        q[0] = (R[l, j] - R[j, l]) / k
+        q[1 + i] = k / 4
+        q[1 + j] = (R[j, i] + R[i, j]) / k
+        q[1 + l] = (R[l, i] + R[i, l]) / k
+    return R, q / np.linalg.norm(q)
+
+
+def render_depth(boxes, ground_z, cam_pos, R, rows, cols, fx, fy, cx, cy, scale=1000.0, max_depth=20.0, dropout=0.0, seed=0):
+    """uint16 depth image (z-depth * scale, 0 = no return) of `boxes` + the plane z = ground_z."""
+    v, u = np.mgrid[0:rows, 0:cols]
+    d_cam = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u, dtype=np.float64)], -1).reshape(-1, 3)
+    d = d_cam @ np.asarray(R).T
+    o = np.asarray(cam_pos, dtype=np.float64)
+    t_best = np.full(len(d), np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = (ground_z - o[2]) / d[:, 2]
+        t_best = np.where((tg > 0) & np.isfinite(tg), tg, t_best)
+        inv = 1.0 / d
+        for b in np.asarray(boxes).reshape(-1, 6):
+            t0 = (b[:3] - o) * inv
+            t1 = (b[3:] - o) * inv
+            tn = np.nanmax(np.minimum(t0, t1), axis=1)
+            tf = np.nanmin(np.maximum(t0, t1), axis=1)
+            hit = (tf >= tn) & (tf > 0)
+            t_best = np.where(hit & (np.maximum(tn, 0) < t_best), np.maximum(tn, 0), t_best)
+    depth = np.where(np.isfinite(t_best) & (t_best < max_depth), t_best, 0.0)
+    img = np.clip(np.rint(depth * scale), 0, 65535).astype(np.uint16).reshape(rows, cols)
+    if dropout > 0:
+        img[np.random.default_rng(seed).random((rows, cols)) < dropout] = 0
+    return img

@@ -40,14 +40,35 @@ def build_world(synth):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions: NVML every ~2 ms from a thread
+    (`nvidia-smi -lms 100` as the fallback: the timed region is only ~20 ms long)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
+        self.sm, self.reasons, self.max_mhz, self.nvml, self.stop_flag = [], set(), None, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -56,11 +77,31 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                    "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,7 +116,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def run_reference(args, rank, world, out):
@@ -231,7 +272,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
     sampler.start()  # runs through warm-up, the timed region and the e2e region (the timed region alone is ~20 ms)
     gm.set_profiling(True)
     for _ in range(args.warmup):

@@ -104,6 +104,46 @@ int b200_map_device_bits(b200_map_t* map, void** dev_ptr, int64_t* n_words);
 int b200_map_export_inflate_cloud(b200_map_t* map, int32_t margin, double truncate_height, float* xyz1, int64_t cap,
                                   int64_t* n_out, int32_t on_device);
 
+/* ---- depth-image fusion: the other producer of occupancy_buffer_inflate_ -------------------------
+ * grid_map/... parameters of the depth path (grid_map.cpp:21-43, same names and defaults).  depth_filter_tolerance and
+ * min_ray_length are read by the reference but never used by live code, so they are not here. */
+typedef struct b200_depth_params {
+  double fx, fy, cx, cy;              /* 387.229248046875, 387.229248046875, 321.04638671875, 243.44969177246094 */
+  double k_depth_scaling_factor;      /* 1000.0 */
+  double depth_filter_mindist;        /* 0.2 */
+  double depth_filter_maxdist;        /* 5.0 */
+  double max_ray_length;              /* 4.5 */
+  double p_hit, p_miss, p_min, p_max, p_occ; /* 0.70 0.35 0.12 0.97 0.80 */
+  double virtual_ceil_height;         /* 2.5 (a ceiling plane is stamped when > -0.5) */
+  int32_t use_depth_filter;           /* 1 */
+  int32_t depth_filter_margin;        /* 1 */
+  int32_t skip_pixel;                 /* 2 */
+  int32_t local_map_margin;           /* 1 */
+} b200_depth_params_t;
+/* Stores the parameters and derives the log-odds constants (logit macro, grid_map.h:27; grid_map.cpp:57-62). */
+int b200_map_set_depth_params(b200_map_t* map, const b200_depth_params_t* p);
+/* One depth frame: GridMap::depthPoseCallback (grid_map.cpp:658-687: image, pose, the camera-inside-the-map gate)
+ * followed by the occupancy timer body GridMap::updateOccupancyCallback (grid_map.cpp:627-656): projectDepthImage ->
+ * raycastProcess -> clearAndInflateLocalMap.  `depth`: rows*cols uint16 (CV_16UC1), host or device memory.
+ * `cam_rot`: camera-to-world rotation, row-major 3x3 — what Eigen's camera_q_.toRotationMatrix() holds on the caller's
+ * side.  *fused = 0 when the camera is outside the map (the frame is dropped, as in the reference).
+ * Results are bit-identical to the reference's sequential loop, including its ray-order dependence (see
+ * csrc/depth_kernels.cu).  Allocates the log-odds grid, counters and flags on first use (38 bytes per voxel). */
+int b200_map_update_depth(b200_map_t* map, const uint16_t* depth, int32_t rows, int32_t cols, const double cam_pos[3],
+                          const double cam_rot[9], int32_t on_device, int32_t* fused);
+/* GridMap::getOccupancy(Vector3d) (grid_map.h:339-348): -1 outside, else occupancy_buffer_ > logit(p_occ). */
+int b200_map_get_occupancy(b200_map_t* map, const double* pos_xyz, int64_t n, int8_t* out, int32_t on_device);
+/* occupancy_buffer_ (log-odds, double per voxel, address x*Ny*Nz + y*Nz + z) to host memory. */
+int b200_map_download_occupancy(b200_map_t* map, double* dst);
+/* Counters of the last fused frame: [0] projected points, [1] rays cast, [2] voxels stepped through, [3] log-odds
+ * updates applied, [4] rounds of the ray-order fixed-point iteration, [5] raycast_num_ (int8, wraps). */
+int b200_map_depth_stats(b200_map_t* map, int64_t out[8]);
+/* Sets raycast_num_ (a `char`, grid_map.h:124; the value is reduced to int8).  It matters beyond bookkeeping: the
+ * reference never clears its per-voxel ray flags, they hold the frame number that last set them, and the number wraps
+ * every 256 fused frames — stale flags then suppress rays (see csrc/depth_kernels.cu).  Kept bit-exactly, so a
+ * restored map must restore the counter as well. */
+int b200_map_set_depth_frame_count(b200_map_t* map, int32_t raycast_num);
+
 /* NEW (not in the reference; replaces the commented-out evaluateCoarseEDT hook, AlgorithmBase.cpp:40-42):
  * exact squared Euclidean distance (voxel units, int32; 1<<29 where no obstacle exists) of every voxel to
  * the nearest inflated-occupied voxel, plus — when d_safe > 0 — the safety-cost field

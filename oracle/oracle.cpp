@@ -86,6 +86,20 @@ struct OMap {
   // new functionality (not in the reference): squared EDT + quantised cost field
   std::vector<int32_t> dist2;
   std::vector<uint16_t> costq;
+  // depth-image fusion state (grid_map.h:89-135 MappingData), allocated by the first depth frame
+  struct DepthParams {  // same layout as b200_depth_params_t
+    double fx, fy, cx, cy, k_depth_scaling_factor, depth_filter_mindist, depth_filter_maxdist, max_ray_length;
+    double p_hit, p_miss, p_min, p_max, p_occ, virtual_ceil_height;
+    int32_t use_depth_filter, depth_filter_margin, skip_pixel, local_map_margin;
+  } dp;
+  bool dp_set = false;
+  double prob_hit_log, prob_miss_log, clamp_min_log, clamp_max_log, min_occupancy_log, unknown_flag;
+  std::vector<double> occ;              // occupancy_buffer_ (log-odds)
+  std::vector<short> cnt_all, cnt_hit;  // count_hit_and_miss_, count_hit_
+  std::vector<char> flag_rayend, flag_traverse;
+  signed char raycast_num = 0;  // grid_map.h:124 `char raycast_num_`: wraps 127 -> -128, so flags alias every 256 fused frames
+  bool has_first_depth = false, local_updated = false;
+  int64_t depth_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [0] projected points, [1] rays cast, [2] ray steps, [3] voxels updated
   int64_t nvox() const { return (int64_t)N[0] * N[1] * N[2]; }
 };
 
@@ -235,6 +249,267 @@ static bool fast_los(const OMap& m, const V3& start, const V3& end, int64_t* nsa
 // ------------------------------------------------------------------------------------------
 // New functionality (not in the reference): exact squared EDT, cost field
 // ------------------------------------------------------------------------------------------
+// ===================================================================================================
+// Depth-image fusion: projectDepthImage -> raycastProcess -> clearAndInflateLocalMap,
+// restated sequentially in the reference's order, quirks included.
+// ===================================================================================================
+// grid_map.cpp:34-41,57-62 + grid_map.h:27 (logit is a macro over libm's log)
+static void depth_set_params(OMap& m, const OMap::DepthParams& p) {
+  m.dp = p;
+  m.dp_set = true;
+  m.prob_hit_log = std::log(p.p_hit / (1 - p.p_hit));
+  m.prob_miss_log = std::log(p.p_miss / (1 - p.p_miss));
+  m.clamp_min_log = std::log(p.p_min / (1 - p.p_min));
+  m.clamp_max_log = std::log(p.p_max / (1 - p.p_max));
+  m.min_occupancy_log = std::log(p.p_occ / (1 - p.p_occ));
+  m.unknown_flag = 0.01;
+}
+// grid_map.cpp:77-85: buffers and their initial values
+static void depth_alloc(OMap& m) {
+  if (!m.occ.empty()) return;
+  const size_t n = (size_t)m.nvox();
+  m.occ.assign(n, m.clamp_min_log - m.unknown_flag);
+  m.cnt_all.assign(n, 0);
+  m.cnt_hit.assign(n, 0);
+  m.flag_rayend.assign(n, (char)-1);
+  m.flag_traverse.assign(n, (char)-1);
+}
+// camera_r * p + camera_pos with the product evaluated row by row as (r0*x + r1*y) + r2*z (the header stand-in's
+// order, oracle/shim/shim_eigen.h operator*; Eigen itself is not in this image: unpinned)
+static inline V3 cam_to_world(const double R[9], const V3& p, const V3& t) {
+  return {((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + t.x, ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + t.y,
+          ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + t.z};
+}
+// grid_map.cpp:195-318 projectDepthImage.  Returns the projected points in the reference's order.
+static void depth_project(OMap& m, const uint16_t* img, int rows, int cols, const V3& cam, const double R[9], std::vector<V3>& out) {
+  const OMap::DepthParams& p = m.dp;
+  out.clear();
+  if (!p.use_depth_filter) {  // :212-231
+    for (int v = 0; v < rows; ++v)
+      for (int u = 0; u < cols; ++u) {
+        const double depth = img[(size_t)v * cols + u] / p.k_depth_scaling_factor;
+        V3 q{(u - p.cx) * depth / p.fx, (v - p.cy) * depth / p.fy, depth};
+        out.push_back(cam_to_world(R, q, cam));
+      }
+    return;
+  }
+  if (!m.has_first_depth) { m.has_first_depth = true; return; }  // :235-237: the first filtered frame projects nothing
+  const double inv_factor = 1.0 / p.k_depth_scaling_factor;
+  for (int v = p.depth_filter_margin; v < rows - p.depth_filter_margin; v += p.skip_pixel) {
+    size_t at = (size_t)v * cols + p.depth_filter_margin;
+    for (int u = p.depth_filter_margin; u < cols - p.depth_filter_margin; u += p.skip_pixel) {
+      double depth = img[at] * inv_factor;
+      at += p.skip_pixel;
+      // :258-269 — the zero test reads the pixel the pointer was just advanced TO, not the one whose depth was taken
+      if (img[at] == 0) depth = p.max_ray_length + 0.1;
+      else if (depth < p.depth_filter_mindist) continue;
+      else if (depth > p.depth_filter_maxdist) depth = p.max_ray_length + 0.1;
+      V3 q{(u - p.cx) * depth / p.fx, (v - p.cy) * depth / p.fy, depth};
+      out.push_back(cam_to_world(R, q, cam));
+    }
+  }
+}
+// grid_map.cpp:458-482 closetPointInMap
+static V3 closest_point_in_map(const OMap& m, const V3& pt, const V3& cam) {
+  const double diff[3] = {pt.x - cam.x, pt.y - cam.y, pt.z - cam.z};
+  const double max_tc[3] = {m.maxb.x - cam.x, m.maxb.y - cam.y, m.maxb.z - cam.z};
+  const double min_tc[3] = {m.minb.x - cam.x, m.minb.y - cam.y, m.minb.z - cam.z};
+  double min_t = 1000000;
+  for (int i = 0; i < 3; ++i)
+    if (std::fabs(diff[i]) > 0) {
+      const double t1 = max_tc[i] / diff[i];
+      if (t1 > 0 && t1 < min_t) min_t = t1;
+      const double t2 = min_tc[i] / diff[i];
+      if (t2 > 0 && t2 < min_t) min_t = t2;
+    }
+  const double k = min_t - 1e-3;
+  return {cam.x + k * diff[0], cam.y + k * diff[1], cam.z + k * diff[2]};
+}
+// raycast.cpp:32-49 signum / mod / intbound
+static inline int ray_signum(int x) { return x == 0 ? 0 : x < 0 ? -1 : 1; }
+static inline double ray_mod(double v, double mod) { return std::fmod(std::fmod(v, mod) + mod, mod); }
+static double ray_intbound(double s, double ds) {
+  if (ds < 0) return ray_intbound(-s, -ds);
+  s = ray_mod(s, 1);
+  return (1 - s) / ds;
+}
+// raycast.cpp:253-346 RayCaster::setInput / step
+struct RayWalk {
+  int x, y, z, ex, ey, ez, sx, sy, sz;
+  double tmx, tmy, tmz, tdx, tdy, tdz;
+  void set(const V3& a, const V3& b) {
+    x = (int)std::floor(a.x); y = (int)std::floor(a.y); z = (int)std::floor(a.z);
+    ex = (int)std::floor(b.x); ey = (int)std::floor(b.y); ez = (int)std::floor(b.z);
+    const double dx = ex - x, dy = ey - y, dz = ez - z;
+    sx = ray_signum((int)dx); sy = ray_signum((int)dy); sz = ray_signum((int)dz);
+    tmx = ray_intbound(a.x, dx); tmy = ray_intbound(a.y, dy); tmz = ray_intbound(a.z, dz);
+    tdx = ((double)sx) / dx; tdy = ((double)sy) / dy; tdz = ((double)sz) / dz;
+  }
+  bool step(int& ox, int& oy, int& oz) {
+    ox = x; oy = y; oz = z;
+    if (x == ex && y == ey && z == ez) return false;
+    if (tmx < tmy) {
+      if (tmx < tmz) { x += sx; tmx += tdx; } else { z += sz; tmz += tdz; }
+    } else {
+      if (tmy < tmz) { y += sy; tmy += tdy; } else { z += sz; tmz += tdz; }
+    }
+    return true;
+  }
+};
+// grid_map.cpp:173-193 setCacheOccupancy (no bounds test in the reference: callers keep `pos` inside the map; here an
+// address outside the buffer is skipped and reported as -1 instead of corrupting memory)
+static int64_t set_cache_occupancy(OMap& m, const V3& pos, int occ, std::vector<int64_t>& queue) {
+  int id[3];
+  pos_to_index(m, pos, id);
+  const int64_t a = to_address(m, id[0], id[1], id[2]);
+  if (a < 0 || a >= m.nvox()) return -1;
+  m.cnt_all[a] = (short)(m.cnt_all[a] + 1);
+  if (m.cnt_all[a] == 1) queue.push_back(a);
+  if (occ == 1) m.cnt_hit[a] = (short)(m.cnt_hit[a] + 1);
+  return a;
+}
+// grid_map.cpp:356,366: (pt - cam) / length * max_ray_length + cam, component-wise, left to right
+static inline V3 shorten_ray(const V3& pt, const V3& cam, double length, double maxlen) {
+  return {(pt.x - cam.x) / length * maxlen + cam.x, (pt.y - cam.y) / length * maxlen + cam.y, (pt.z - cam.z) / length * maxlen + cam.z};
+}
+// grid_map.cpp:320-456 raycastProcess
+static void depth_raycast(OMap& m, const std::vector<V3>& pts, const V3& cam) {
+  if (pts.empty()) return;
+  m.raycast_num = (signed char)(m.raycast_num + 1);
+  const double maxlen = m.dp.max_ray_length;
+  double min_x = m.maxb.x, min_y = m.maxb.y, min_z = m.maxb.z, max_x = m.minb.x, max_y = m.minb.y, max_z = m.minb.z;
+  std::vector<int64_t> queue;
+  RayWalk rc;
+  for (const V3& p0 : pts) {
+    V3 pt = p0;
+    int64_t vox;
+    if (!is_in_map(m, pt)) {
+      pt = closest_point_in_map(m, pt, cam);
+      const double length = norm(pt - cam);
+      if (length > maxlen) pt = shorten_ray(pt, cam, length, maxlen);
+      vox = set_cache_occupancy(m, pt, 0, queue);
+    } else {
+      const double length = norm(pt - cam);
+      if (length > maxlen) {
+        pt = shorten_ray(pt, cam, length, maxlen);
+        vox = set_cache_occupancy(m, pt, 0, queue);
+      } else {
+        vox = set_cache_occupancy(m, pt, 1, queue);
+      }
+    }
+    max_x = std::max(max_x, pt.x); max_y = std::max(max_y, pt.y); max_z = std::max(max_z, pt.z);
+    min_x = std::min(min_x, pt.x); min_y = std::min(min_y, pt.y); min_z = std::min(min_z, pt.z);
+    if (vox >= 0) {  // :385-395 one ray per end voxel and round (flags persist across frames: a voxel whose flag still
+                     // holds this round's number from 256 frames ago — or the initial -1 in round 255 — looks taken)
+      if (m.flag_rayend[vox] == (char)m.raycast_num) continue;
+      m.flag_rayend[vox] = (char)m.raycast_num;
+    }
+    m.depth_stats[1]++;
+    rc.set(V3{pt.x / m.res, pt.y / m.res, pt.z / m.res}, V3{cam.x / m.res, cam.y / m.res, cam.z / m.res});  // :397
+    int ix, iy, iz;
+    // a ray between two points of the map takes at most N0+N1+N2 steps; the cap only guards a walk that misses its end
+    // cell (the reference would run on, out of bounds)
+    for (int steps = 0, cap = m.N[0] + m.N[1] + m.N[2] + 4; steps < cap && rc.step(ix, iy, iz); ++steps) {
+      const V3 tmp{(ix + 0.5) * m.res, (iy + 0.5) * m.res, (iz + 0.5) * m.res};
+      m.depth_stats[2]++;
+      const int64_t v = set_cache_occupancy(m, tmp, 0, queue);
+      if (v >= 0) {  // :408-418 stop at a voxel another ray of this round already crossed
+        if (m.flag_traverse[v] == (char)m.raycast_num) break;
+        m.flag_traverse[v] = (char)m.raycast_num;
+      }
+    }
+  }
+  min_x = std::min(min_x, cam.x); min_y = std::min(min_y, cam.y); min_z = std::min(min_z, cam.z);
+  max_x = std::max(max_x, cam.x); max_y = std::max(max_y, cam.y); max_z = std::max(max_z, cam.z);
+  max_z = std::max(max_z, m.ground_height);
+  pos_to_index(m, V3{max_x, max_y, max_z}, m.lb_max);
+  pos_to_index(m, V3{min_x, min_y, min_z}, m.lb_min);
+  bound_index(m, m.lb_min);
+  bound_index(m, m.lb_max);
+  m.local_updated = true;
+  // :431-455 log-odds update of every voxel touched this round
+  int min_id[3], max_id[3];
+  pos_to_index(m, cam - m.range, min_id);
+  pos_to_index(m, cam + m.range, max_id);
+  bound_index(m, min_id);
+  bound_index(m, max_id);
+  const int64_t nyz = (int64_t)m.N[1] * m.N[2];
+  for (size_t qi = 0; qi < queue.size(); ++qi) {
+    const int64_t a = queue[qi];
+    const int idx[3] = {(int)(a / nyz), (int)((a % nyz) / m.N[2]), (int)(a % m.N[2])};
+    const double upd = m.cnt_hit[a] >= m.cnt_all[a] - m.cnt_hit[a] ? m.prob_hit_log : m.prob_miss_log;
+    m.cnt_hit[a] = m.cnt_all[a] = 0;
+    m.depth_stats[3]++;
+    if (upd >= 0 && m.occ[a] >= m.clamp_max_log) continue;
+    if (upd <= 0 && m.occ[a] <= m.clamp_min_log) { m.occ[a] = m.clamp_min_log; continue; }
+    const bool in_local = idx[0] >= min_id[0] && idx[0] <= max_id[0] && idx[1] >= min_id[1] && idx[1] <= max_id[1] &&
+                          idx[2] >= min_id[2] && idx[2] <= max_id[2];
+    if (!in_local) m.occ[a] = m.clamp_min_log;
+    m.occ[a] = std::min(std::max(m.occ[a] + upd, m.clamp_min_log), m.clamp_max_log);
+  }
+}
+// grid_map.cpp:484-624 clearAndInflateLocalMap
+static void depth_clear_and_inflate(OMap& m) {
+  const int vec_margin = 5, lm = m.dp.local_map_margin;
+  int min_cut[3], max_cut[3], min_cut_m[3], max_cut_m[3];
+  for (int i = 0; i < 3; ++i) { min_cut[i] = m.lb_min[i] - lm; max_cut[i] = m.lb_max[i] + lm; }
+  bound_index(m, min_cut);
+  bound_index(m, max_cut);
+  for (int i = 0; i < 3; ++i) { min_cut_m[i] = min_cut[i] - vec_margin; max_cut_m[i] = max_cut[i] + vec_margin; }
+  bound_index(m, min_cut_m);
+  bound_index(m, max_cut_m);
+  // :531-579 the three slab loops together write every voxel of box M that lies outside box C
+  const double unknown = m.clamp_min_log - m.unknown_flag;
+  for (int x = min_cut_m[0]; x <= max_cut_m[0]; ++x)
+    for (int y = min_cut_m[1]; y <= max_cut_m[1]; ++y)
+      for (int z = min_cut_m[2]; z <= max_cut_m[2]; ++z) {
+        const bool inside = x >= min_cut[0] && x <= max_cut[0] && y >= min_cut[1] && y <= max_cut[1] && z >= min_cut[2] && z <= max_cut[2];
+        if (!inside) m.occ[to_address(m, x, y, z)] = unknown;
+      }
+  // :583-596
+  const int step = (int)std::ceil(m.inflation / m.res);
+  for (int x = m.lb_min[0]; x <= m.lb_max[0]; ++x)
+    for (int y = m.lb_min[1]; y <= m.lb_max[1]; ++y)
+      for (int z = m.lb_min[2]; z <= m.lb_max[2]; ++z) m.inflate[to_address(m, x, y, z)] = 0;
+  // :598-616 + grid_map.h:412-441 inflatePoint: the full (2*step+1)^3 cube, and only the LINEAR address is range-tested,
+  // so a cube sticking out in y or z wraps into the neighbouring row/column
+  const int64_t total = m.nvox();
+  for (int x = m.lb_min[0]; x <= m.lb_max[0]; ++x)
+    for (int y = m.lb_min[1]; y <= m.lb_max[1]; ++y)
+      for (int z = m.lb_min[2]; z <= m.lb_max[2]; ++z) {
+        if (!(m.occ[to_address(m, x, y, z)] > m.min_occupancy_log)) continue;
+        for (int dx = -step; dx <= step; ++dx)
+          for (int dy = -step; dy <= step; ++dy)
+            for (int dz = -step; dz <= step; ++dz) {
+              const int64_t a = to_address(m, x + dx, y + dy, z + dz);
+              if (a < 0 || a >= total) continue;
+              m.inflate[a] = 1;
+            }
+      }
+  // :618-627 virtual ceiling (no range test in the reference; an address outside the buffer is skipped here)
+  if (m.dp.virtual_ceil_height > -0.5) {
+    const int ceil_id = (int)std::floor((m.dp.virtual_ceil_height - m.origin.z) * m.res_inv);
+    for (int x = m.lb_min[0]; x <= m.lb_max[0]; ++x)
+      for (int y = m.lb_min[1]; y <= m.lb_max[1]; ++y) {
+        const int64_t a = to_address(m, x, y, ceil_id);
+        if (a >= 0 && a < total) m.inflate[a] = 1;
+      }
+  }
+}
+// depthPoseCallback's gate (grid_map.cpp:676-686) + updateOccupancyCallback (grid_map.cpp:629-656)
+static int depth_update(OMap& m, const uint16_t* img, int rows, int cols, const V3& cam, const double R[9]) {
+  if (!is_in_map(m, cam)) return 0;
+  depth_alloc(m);
+  std::vector<V3> pts;
+  depth_project(m, img, rows, cols, cam, R, pts);
+  m.depth_stats[0] = (int64_t)pts.size();
+  m.depth_stats[1] = m.depth_stats[2] = m.depth_stats[3] = 0;
+  depth_raycast(m, pts, cam);
+  if (m.local_updated) depth_clear_and_inflate(m);
+  m.local_updated = false;
+  return 1;
+}
+
 static const int32_t kDistInf = 1 << 29;  // "no obstacle anywhere on this line" sentinel
 
 // Brute force: d2[v] = min over occupied u of |v-u|^2 in voxel units (for tiny grids).
@@ -865,6 +1140,32 @@ void orc_map_local_bounds(void* h, int mn[3], int mx[3]) {
 }
 int64_t orc_map_export_inflate_cloud(void* h, int margin, double truncate_height, float* out, int64_t cap) {
   return export_inflate_cloud(*(OMap*)h, margin, truncate_height, out, cap);
+}
+void orc_map_set_depth_params(void* h, const void* p) { depth_set_params(*(OMap*)h, *(const OMap::DepthParams*)p); }
+int orc_map_update_depth(void* h, const uint16_t* img, int rows, int cols, const double cam[3], const double R[9]) {
+  OMap& m = *(OMap*)h;
+  if (!m.dp_set) return -1;
+  return depth_update(m, img, rows, cols, V3{cam[0], cam[1], cam[2]}, R);
+}
+void orc_map_download_occupancy(void* h, double* dst) {
+  OMap& m = *(OMap*)h;
+  depth_alloc(m);
+  memcpy(dst, m.occ.data(), m.occ.size() * sizeof(double));
+}
+void orc_map_set_raycast_num(void* h, int v) { ((OMap*)h)->raycast_num = (signed char)v; }
+int orc_map_raycast_num(void* h) { return ((OMap*)h)->raycast_num; }
+void orc_map_depth_stats(void* h, int64_t out[8]) { memcpy(out, ((OMap*)h)->depth_stats, sizeof(int64_t) * 8); }
+// grid_map.h:339-348 getOccupancy(Vector3d)
+void orc_map_get_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
+  OMap& m = *(OMap*)h;
+  depth_alloc(m);
+  for (int64_t i = 0; i < n; ++i) {
+    const V3 p{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    if (!is_in_map(m, p)) { out[i] = -1; continue; }
+    int id[3];
+    pos_to_index(m, p, id);
+    out[i] = m.occ[to_address(m, id[0], id[1], id[2])] > m.min_occupancy_log ? 1 : 0;
+  }
 }
 void orc_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   OMap* m = (OMap*)h;

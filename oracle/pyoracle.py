@@ -32,6 +32,32 @@ RESULT_DTYPE = np.dtype([("solved", "i4"), ("status", "i4"), ("n_path", "i4"), (
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 
+class DepthParams(C.Structure):
+    """Same layout as b200_depth_params_t (include/b200_planner.h); defaults = grid_map.cpp:22-49."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k_depth_scaling_factor", C.c_double), ("depth_filter_mindist", C.c_double),
+                ("depth_filter_maxdist", C.c_double), ("max_ray_length", C.c_double),
+                ("p_hit", C.c_double), ("p_miss", C.c_double), ("p_min", C.c_double), ("p_max", C.c_double),
+                ("p_occ", C.c_double), ("virtual_ceil_height", C.c_double),
+                ("use_depth_filter", C.c_int32), ("depth_filter_margin", C.c_int32), ("skip_pixel", C.c_int32),
+                ("local_map_margin", C.c_int32)]
+
+
+DEPTH_DEFAULTS = dict(fx=387.229248046875, fy=387.229248046875, cx=321.04638671875, cy=243.44969177246094,
+                      k_depth_scaling_factor=1000.0, depth_filter_mindist=0.2, depth_filter_maxdist=5.0, max_ray_length=4.5,
+                      p_hit=0.70, p_miss=0.35, p_min=0.12, p_max=0.97, p_occ=0.80, virtual_ceil_height=2.5,
+                      use_depth_filter=1, depth_filter_margin=1, skip_pixel=2, local_map_margin=1)
+
+
+def depth_params(**kw):
+    d = dict(DEPTH_DEFAULTS)
+    d.update(kw)
+    p = DepthParams()
+    for k, v in d.items():
+        setattr(p, k, v)
+    return p
+
+
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE, "CXX=g++"])
 
@@ -70,6 +96,15 @@ def lib():
         L.orc_planner_find_paths.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp,
                                              vp, vp, vp, i64, vp, vp, i64, C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_map_set_depth_params.argtypes = [vp, vp]
+        L.orc_map_update_depth.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp]
+        L.orc_map_update_depth.restype = C.c_int
+        L.orc_map_download_occupancy.argtypes = [vp, vp]
+        L.orc_map_set_raycast_num.argtypes = [vp, C.c_int]
+        L.orc_map_raycast_num.argtypes = [vp]
+        L.orc_map_raycast_num.restype = C.c_int
+        L.orc_map_depth_stats.argtypes = [vp, vp]
+        L.orc_map_get_occupancy.argtypes = [vp, vp, i64, vp]
         _LIB = L
     return _LIB
 
@@ -129,6 +164,42 @@ class OracleMap:
         out = np.empty((cap, 4), dtype=np.float32)
         n = lib().orc_map_export_inflate_cloud(self.h, margin, truncate_height, _ptr(out), cap)
         return out[: min(n, cap)].copy(), n
+
+    # ---- depth-image fusion (grid_map.cpp:195-687) ----
+    def set_depth_params(self, **kw):
+        self._dp = depth_params(**kw)
+        lib().orc_map_set_depth_params(self.h, C.byref(self._dp))
+
+    def update_depth(self, depth, cam_pos, cam_rot):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        rot = np.ascontiguousarray(cam_rot, dtype=np.float64).reshape(9)
+        r = lib().orc_map_update_depth(self.h, _ptr(depth), depth.shape[0], depth.shape[1], _d3(cam_pos),
+                                       rot.ctypes.data_as(C.POINTER(C.c_double)))
+        if r < 0:
+            raise RuntimeError("set_depth_params first")
+        return bool(r)
+
+    def occupancy(self):
+        out = np.empty(self.dims, dtype=np.float64)
+        lib().orc_map_download_occupancy(self.h, _ptr(out))
+        return out
+
+    def set_raycast_num(self, v):
+        lib().orc_map_set_raycast_num(self.h, int(v))
+
+    def raycast_num(self):
+        return lib().orc_map_raycast_num(self.h)
+
+    def depth_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        lib().orc_map_depth_stats(self.h, _ptr(out))
+        return out
+
+    def get_occupancy(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        lib().orc_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

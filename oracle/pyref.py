@@ -43,6 +43,15 @@ def lib():
         L.ref_pos_to_index.argtypes = [vp, vp, i64, vp]
         L.ref_los_batch.argtypes = [vp, vp, vp, i64, vp]
         L.ref_set_param.argtypes = [C.c_char_p, C.c_double]
+        L.ref_map_update_depth.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, dp]
+        L.ref_map_update_depth.restype = C.c_int
+        L.ref_map_download_occupancy.argtypes = [vp, vp]
+        L.ref_map_raycast_num.argtypes = [vp]
+        L.ref_map_raycast_num.restype = C.c_int
+        L.ref_map_proj_points.argtypes = [vp]
+        L.ref_map_proj_points.restype = C.c_int
+        L.ref_map_set_raycast_num.argtypes = [vp, C.c_int]
+        L.ref_map_get_occupancy.argtypes = [vp, vp, i64, vp]
         L.ref_planner_create.restype = vp
         L.ref_planner_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, vp]
         L.ref_planner_destroy.argtypes = [vp]
@@ -56,7 +65,11 @@ def lib():
 class RefMap:
     """The reference's GridMap (initMap + odomCallback + cloudCallback); origin is always (-sx/2,-sy/2,ground_height)."""
 
-    def __init__(self, size, resolution, obstacles_inflation=0.099, local_update_range=(1e9, 1e9, 1e9), ground_height=-0.01):
+    def __init__(self, size, resolution, obstacles_inflation=0.099, local_update_range=(1e9, 1e9, 1e9), ground_height=-0.01,
+                 depth=None):
+        """depth: dict of grid_map/* depth-fusion params (names as in oracle.pyoracle.DEPTH_DEFAULTS), set before initMap."""
+        for k, v in (depth or {}).items():
+            lib().ref_set_param(("grid_map/" + k).encode(), float(v))
         self.h = lib().ref_map_create(_d3(size), resolution, obstacles_inflation, _d3(local_update_range), ground_height)
         d = (C.c_int * 3)()
         lib().ref_map_dims(self.h, d)
@@ -101,6 +114,35 @@ class RefMap:
         out = np.empty((cap, 4), dtype=np.float32)
         n = lib().ref_map_publish_inflate(self.h, 1 if all_info else 0, _ptr(out), cap)
         return out[:n].copy()
+
+    def update_depth(self, depth, cam_pos, quat_wxyz):
+        """depthPoseCallback + updateOccupancyCallback. Returns (fused, rotation 3x3 the reference derived)."""
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        rot = np.zeros(9)
+        q = (C.c_double * 4)(*[float(x) for x in quat_wxyz])
+        r = lib().ref_map_update_depth(self.h, _ptr(depth), depth.shape[0], depth.shape[1], _d3(cam_pos), q,
+                                       rot.ctypes.data_as(C.POINTER(C.c_double)))
+        return bool(r), rot.reshape(3, 3)
+
+    def occupancy(self):
+        out = np.empty(self.dims, dtype=np.float64)
+        lib().ref_map_download_occupancy(self.h, _ptr(out))
+        return out
+
+    def raycast_num(self):
+        return lib().ref_map_raycast_num(self.h)
+
+    def set_raycast_num(self, v):
+        lib().ref_map_set_raycast_num(self.h, int(v))
+
+    def proj_points(self):
+        return lib().ref_map_proj_points(self.h)
+
+    def get_occupancy(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.int8)
+        lib().ref_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
+        return out
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

@@ -135,6 +135,44 @@ int64_t ref_map_publish_inflate(void* h, int all_info, float* out, int64_t cap) 
   std::memcpy(out, shim::last_cloud_blob().data(), (size_t)std::min<int64_t>(n, cap) * 16);
   return n;
 }
+// One depth frame through the reference's own callbacks: depthPoseCallback (image copy, pose, the in-map gate,
+// grid_map.cpp:658-687) then the occupancy timer body updateOccupancyCallback (projectDepthImage -> raycastProcess
+// -> clearAndInflateLocalMap, grid_map.cpp:627-656).  Returns 1 if the frame was fused (camera inside the map).
+// rot_out (row-major 3x3) = the rotation the reference derived from the quaternion, for the caller to hand to the
+// implementations under test (their boundary takes the matrix).
+int ref_map_update_depth(void* h, const uint16_t* depth, int rows, int cols, const double cam_pos[3], const double quat_wxyz[4],
+                         double rot_out[9]) {
+  Silence s;
+  GridMap& g = *((RefMap*)h)->gm;
+  auto img = std::make_shared<sensor_msgs::Image>();
+  img->height = (uint32_t)rows; img->width = (uint32_t)cols;
+  img->encoding = sensor_msgs::image_encodings::TYPE_16UC1;
+  img->data.resize((size_t)rows * cols * 2);
+  std::memcpy(img->data.data(), depth, img->data.size());
+  auto pose = std::make_shared<geometry_msgs::PoseStamped>();
+  pose->pose.position.x = cam_pos[0]; pose->pose.position.y = cam_pos[1]; pose->pose.position.z = cam_pos[2];
+  pose->pose.orientation.w = quat_wxyz[0]; pose->pose.orientation.x = quat_wxyz[1];
+  pose->pose.orientation.y = quat_wxyz[2]; pose->pose.orientation.z = quat_wxyz[3];
+  g.depthPoseCallback(img, pose);
+  if (rot_out) {
+    const Eigen::Matrix3d r = g.md_.camera_q_.toRotationMatrix();
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) rot_out[3 * i + j] = r(i, j);
+  }
+  const int fused = g.md_.occ_need_update_ ? 1 : 0;
+  g.updateOccupancyCallback(ros::TimerEvent());
+  return fused;
+}
+void ref_map_download_occupancy(void* h, double* dst) {
+  const auto& b = ((RefMap*)h)->gm->md_.occupancy_buffer_;
+  std::memcpy(dst, b.data(), b.size() * sizeof(double));
+}
+int ref_map_raycast_num(void* h) { return ((RefMap*)h)->gm->md_.raycast_num_; }
+int ref_map_proj_points(void* h) { return ((RefMap*)h)->gm->md_.proj_points_cnt; }
+void ref_map_set_raycast_num(void* h, int v) { ((RefMap*)h)->gm->md_.raycast_num_ = v; }
+void ref_map_get_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
+  GridMap& g = *((RefMap*)h)->gm;
+  for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)g.getOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+}
 void ref_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   GridMap& g = *((RefMap*)h)->gm;
   for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)g.getInflateOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));

@@ -120,7 +120,16 @@ class Mat {
 namespace cv_bridge {
 struct CvImage { cv::Mat image; };
 typedef std::shared_ptr<CvImage> CvImagePtr;
-inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr&, const std::string&) { return std::make_shared<CvImage>(); }
+// what cv_bridge::toCvCopy does for a 16UC1 image: a deep copy of the payload, rows = height, cols = width
+inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr& img, const std::string&) {
+  auto p = std::make_shared<CvImage>();
+  if (img) {
+    p->image.rows = (int)img->height;
+    p->image.cols = (int)img->width;
+    p->image.buf = std::make_shared<std::vector<uint8_t>>(img->data);
+  }
+  return p;
+}
 }
 
 namespace pcl {

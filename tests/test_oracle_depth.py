@@ -1,0 +1,78 @@
+"""Depth-image fusion: the oracle's restatement against the reference's own code — the committed
+golden vectors everywhere, and the live reference build where /root/reference exists."""
+import numpy as np
+import pytest
+
+from depth_util import GOLDEN, SCENARIOS, replay, scenario
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_oracle_depth_fusion_is_the_reference(po, golden, name):
+    sc = scenario(golden, name)
+    om = po.OracleMap(tuple(golden["origin"]), tuple(golden["size"]), float(golden["res"]), sc["inflation"], sc["range"],
+                      float(golden["origin"][2]))
+    om.set_depth_params(**sc["params"])
+    replay(sc, om.update_depth, om.occupancy, om.inflate, om.local_bounds, om.dims, om.set_raycast_num)
+    assert om.raycast_num() == sc["frames_after"]
+    st = om.depth_stats()
+    assert st[0] == sc["proj"][-1]
+    if name == "count_wrap":
+        # more log-odds updates than voxels touched: a `short` counter wrapped past 1 again and re-queued its voxel
+        assert int((sc["img"][0] == 0).sum()) > 65536
+        fresh = po.OracleMap(tuple(golden["origin"]), tuple(golden["size"]), float(golden["res"]), sc["inflation"], sc["range"],
+                             float(golden["origin"][2]))
+        fresh.set_depth_params(**sc["params"])
+        fresh.update_depth(sc["img"][0], sc["pos"][0], sc["rot"][0])
+        occ = fresh.occupancy()
+        assert fresh.depth_stats()[3] > int((occ != occ.min()).sum())
+    # a camera outside the map drops the frame (grid_map.cpp:676-686)
+    before = om.occupancy()
+    assert not om.update_depth(sc["img"][0], (0.0, 0.0, float(golden["size"][2]) + 1.0), sc["rot"][0])
+    assert np.array_equal(before, om.occupancy())
+
+
+def test_get_occupancy_matches_threshold(po, golden):
+    sc = scenario(golden, "filter")
+    om = po.OracleMap(tuple(golden["origin"]), tuple(golden["size"]), float(golden["res"]), sc["inflation"], sc["range"],
+                      float(golden["origin"][2]))
+    om.set_depth_params(**sc["params"])
+    for f in range(len(sc["pos"])):
+        om.update_depth(sc["img"][f], sc["pos"][f], sc["rot"][f])
+    occ = om.occupancy()
+    idx = np.argwhere(occ > np.log(0.8 / 0.2))
+    assert len(idx) > 50
+    pos = (idx + 0.5) * float(golden["res"]) + golden["origin"]
+    assert (om.get_occupancy(pos) == 1).all()
+    assert (om.get_occupancy(pos + [0, 0, 100.0]) == -1).all()
+
+
+def test_oracle_depth_vs_live_reference(po, synth):
+    pr = pytest.importorskip("oracle.pyref")
+    if not pr.available():
+        pytest.skip("reference sources not present")
+    size, res, gh = (8.0, 6.0, 2.5), 0.1, -0.01
+    origin = (-4.0, -3.0, gh)
+    dp = dict(po.DEPTH_DEFAULTS)
+    dp.update(fx=60.5, fy=60.5, cx=50.2, cy=38.1, depth_filter_margin=2, skip_pixel=3, local_map_margin=2, virtual_ceil_height=2.2,
+              max_ray_length=3.5)
+    rm = pr.RefMap(size, res, 0.099, (3.0, 3.0, 2.0), gh, depth=dp)
+    om = po.OracleMap(origin, size, res, 0.099, (3.0, 3.0, 2.0), gh)
+    om.set_depth_params(**dp)
+    boxes = synth.pillar_boxes(5, origin, size, 12)
+    rng = np.random.default_rng(9)
+    for f in range(7):
+        pos = (rng.uniform(-3.5, 3.5), rng.uniform(-2.5, 2.5), rng.uniform(0.3, 2.0))
+        R, q = synth.look_at(rng.uniform(0, 6.28), rng.uniform(-0.4, 0.6))
+        img = synth.render_depth(boxes, gh, pos, R, 76, 100, dp["fx"], dp["fy"], dp["cx"], dp["cy"], dropout=0.05, seed=f)
+        fused, Rref = rm.update_depth(img, pos, q)
+        assert om.update_depth(img, pos, Rref) == fused
+        assert np.array_equal(rm.occupancy(), om.occupancy())
+        assert np.array_equal(rm.inflate(), om.inflate())
+        assert rm.proj_points() == om.depth_stats()[0]
+        if rm.proj_points():
+            assert rm.local_bounds() == om.local_bounds()
