@@ -7,8 +7,8 @@
 // What is mirrored: initMap (geometry + parameters of the cloud path), cloudCallback, odomCallback
 // (camera position), resetBuffer (x2), posToIndex, indexToPos, toAddress, isInMap (x2), boundIndex,
 // getInflateOccupancy, setOccupied, getRegion, getResolution, getOrigin, odomValid, plus the new
-// buildDistanceField / getDistance2.  The depth-image path and the rviz publishers stay in the reference
-// (SURVEY.md §8f).
+// buildDistanceField / getDistance2, and the depth-image path (depthPoseCallback = the reference's callback plus its
+// occupancy timer body; getOccupancy, isKnownOccupied, hasDepthObservation).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -98,10 +98,33 @@ class GridMap {
     prm_.size[0] = x_size; prm_.size[1] = y_size; prm_.size[2] = z_size;
     prm_.device = device;
     prm_.reserved = 0;
+    // depth-fusion parameters (grid_map.cpp:21-43), same keys and defaults
+    bool use_filter;
+    nh.param("grid_map/fx", dprm_.fx, 387.229248046875);
+    nh.param("grid_map/fy", dprm_.fy, 387.229248046875);
+    nh.param("grid_map/cx", dprm_.cx, 321.04638671875);
+    nh.param("grid_map/cy", dprm_.cy, 243.44969177246094);
+    nh.param("grid_map/use_depth_filter", use_filter, true);
+    dprm_.use_depth_filter = use_filter ? 1 : 0;
+    nh.param("grid_map/depth_filter_maxdist", dprm_.depth_filter_maxdist, 5.0);
+    nh.param("grid_map/depth_filter_mindist", dprm_.depth_filter_mindist, 0.2);
+    nh.param("grid_map/depth_filter_margin", dprm_.depth_filter_margin, (int32_t)1);
+    nh.param("grid_map/k_depth_scaling_factor", dprm_.k_depth_scaling_factor, 1000.0);
+    nh.param("grid_map/skip_pixel", dprm_.skip_pixel, (int32_t)2);
+    nh.param("grid_map/p_hit", dprm_.p_hit, 0.70);
+    nh.param("grid_map/p_miss", dprm_.p_miss, 0.35);
+    nh.param("grid_map/p_min", dprm_.p_min, 0.12);
+    nh.param("grid_map/p_max", dprm_.p_max, 0.97);
+    nh.param("grid_map/p_occ", dprm_.p_occ, 0.80);
+    nh.param("grid_map/max_ray_length", dprm_.max_ray_length, 4.5);
+    nh.param("grid_map/virtual_ceil_height", dprm_.virtual_ceil_height, 2.5);
+    nh.param("grid_map/local_map_margin", dprm_.local_map_margin, (int32_t)1);
     create();
+    b200_check(b200_map_set_depth_params(h_, &dprm_), "initMap (depth parameters)");
   }
   // explicit-origin variant (the C-ABI does not force the centred origin)
   void initMap(const b200_map_params_t& p) { prm_ = p; create(); }
+  void setDepthParams(const b200_depth_params_t& d) { dprm_ = d; b200_check(b200_map_set_depth_params(h_, &dprm_), "setDepthParams"); }
 
   // odomCallback (grid_map.cpp:699-709)
   void odomCallback(const Vec3d& position) { camera_pos_ = position; has_odom_ = true; }
@@ -122,6 +145,56 @@ class GridMap {
     odomCallback(Vec3d(odom->pose.pose.position.x, odom->pose.pose.position.y, odom->pose.pose.position.z));
   }
 #endif
+
+  // depthPoseCallback (grid_map.cpp:658-687) + the 20 Hz occupancy timer body updateOccupancyCallback (:627-656) in one
+  // call: a CV_16UC1 image (a 32FC1 image is converted by the caller with k_depth_scaling_factor, :665-668), the camera
+  // position and orientation quaternion (w, x, y, z).  The rotation matrix is formed here with the textbook
+  // unit-quaternion formula; with Eigen present pass camera_q.toRotationMatrix() to the matrix overload instead.
+  bool depthPoseCallback(const uint16_t* depth, int rows, int cols, const Vec3d& pos, double qw, double qx, double qy, double qz) {
+    const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw),     2 * (qx * qz + qy * qw),
+                         2 * (qx * qy + qz * qw),     1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                         2 * (qx * qz - qy * qw),     2 * (qy * qz + qx * qw),     1 - 2 * (qx * qx + qy * qy)};
+    return depthPoseCallback(depth, rows, cols, pos, R);
+  }
+  bool depthPoseCallback(const uint16_t* depth, int rows, int cols, const Vec3d& pos, const double cam_rot_row_major[9]) {
+    camera_pos_ = pos;
+    const double cam[3] = {pos(0), pos(1), pos(2)};
+    int32_t fused = 0;
+    b200_check(b200_map_update_depth(h_, depth, rows, cols, cam, cam_rot_row_major, 0, &fused), "depthPoseCallback");
+    if (fused) { has_odom_ = true; has_depth_ = true; }  // :676-681
+    return fused != 0;
+  }
+#ifdef B200_WITH_ROS
+  void depthPoseCallback(const sensor_msgs::ImageConstPtr& img, const geometry_msgs::PoseStampedConstPtr& pose) {
+    cv_bridge::CvImagePtr cv_ptr = cv_bridge::toCvCopy(img, img->encoding);
+    if (img->encoding == sensor_msgs::image_encodings::TYPE_32FC1) (cv_ptr->image).convertTo(cv_ptr->image, CV_16UC1, dprm_.k_depth_scaling_factor);
+    const auto& o = pose->pose.orientation;
+    depthPoseCallback(cv_ptr->image.ptr<uint16_t>(0), cv_ptr->image.rows, cv_ptr->image.cols,
+                      Vec3d(pose->pose.position.x, pose->pose.position.y, pose->pose.position.z), o.w, o.x, o.y, o.z);
+  }
+#endif
+  // grid_map.h:339-348 / :276-311 — single reads of occupancy_buffer_ (log-odds) and the inflated grid
+  inline int getOccupancy(Vec3d pos) const {
+    int8_t v = 0;
+    const double p[3] = {pos(0), pos(1), pos(2)};
+    b200_check(b200_map_get_occupancy(h_, p, 1, &v, 0), "getOccupancy");
+    return (int)v;
+  }
+  inline int getOccupancy(Vec3i id) const {
+    if (id(0) < 0 || id(0) >= n_[0] || id(1) < 0 || id(1) >= n_[1] || id(2) < 0 || id(2) >= n_[2]) return -1;
+    Vec3d pos;
+    indexToPos(id, pos);
+    return getOccupancy(pos);
+  }
+  inline bool isKnownOccupied(const Vec3i& id) const {
+    Vec3i id1 = id;
+    boundIndex(id1);
+    Vec3d pos;
+    indexToPos(id1, pos);
+    return getInflateOccupancy(pos) == 1;
+  }
+  bool hasDepthObservation() const { return has_depth_; }
+  const b200_depth_params_t& depthParams() const { return dprm_; }
 
   void resetBuffer() { b200_check(b200_map_reset(h_), "resetBuffer"); }
   void resetBuffer(Vec3d min_pos, Vec3d max_pos) {
@@ -207,11 +280,12 @@ class GridMap {
     for (int i = 0; i < 3; ++i) n_[i] = n[i];
   }
   b200_map_params_t prm_{};
+  b200_depth_params_t dprm_{};
   b200_map_t* h_ = nullptr;
   int n_[3] = {0, 0, 0};
   double res_inv_ = 0;
   Vec3d camera_pos_;
-  bool has_odom_ = false, has_cloud_ = false;
+  bool has_odom_ = false, has_cloud_ = false, has_depth_ = false;
 };
 
 }  // namespace b200host

@@ -33,6 +33,27 @@ int main(int argc, char** argv) {
     else if (name == "lazythetastar") algorithm.reset(new Planners::LazyThetaStar());
     else if (name == "costastar") algorithm.reset(new Planners::CostAStar());
     else if (name == "costlazythetastar") algorithm.reset(new Planners::CostLazyThetaStar());
+    else if (name == "depth") {
+      // depth-image path: a wall 2 m in front of a camera at (0,0,1) looking along +x, seen in 6 frames
+      GridMap::Ptr gm(new GridMap);
+      gm->initMap(nh);
+      const int rows = 120, cols = 160;
+      b200_depth_params_t dp = gm->depthParams();
+      dp.fx = dp.fy = 96.8; dp.cx = 80.3; dp.cy = 60.9;
+      gm->setDepthParams(dp);
+      std::vector<uint16_t> img((size_t)rows * cols, 2000);
+      // optical frame (x right, y down, z forward) looking along world +x: q = (0.5, -0.5, 0.5, -0.5)
+      int fused = 0;
+      for (int f = 0; f < 6; ++f) fused += gm->depthPoseCallback(img.data(), rows, cols, Vec3d(0.0, 0.0, 1.0), 0.5, -0.5, 0.5, -0.5) ? 1 : 0;
+      int64_t st[8];
+      b200_map_depth_stats(gm->handle(), st);
+      std::printf("{\"mode\": \"depth\", \"fused\": %d, \"wall_occupancy\": %d, \"wall_inflated\": %d, \"free_occupancy\": %d, "
+                  "\"outside\": %d, \"projected\": %lld, \"rays_cast\": %lld, \"ray_steps\": %lld, \"updates\": %lld, \"has_depth\": %d}\n",
+                  fused, gm->getOccupancy(Vec3d(2.02, 0.0, 1.0)), gm->getInflateOccupancy(Vec3d(2.02, 0.0, 1.0)),
+                  gm->getOccupancy(Vec3d(1.0, 0.0, 1.0)), gm->getOccupancy(Vec3d(100.0, 0.0, 1.0)), (long long)st[0], (long long)st[1],
+                  (long long)st[2], (long long)st[3], gm->hasDepthObservation() ? 1 : 0);
+      return 0;
+    }
     else algorithm.reset(new Planners::AStar());
     algorithm->setCostFactor(2.0f);
     algorithm->setParam(nh);

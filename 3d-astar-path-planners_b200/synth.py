@@ -152,14 +152,23 @@ def render_depth(boxes, ground_z, cam_pos, R, rows, cols, fx, fy, cx, cy, scale=
     with np.errstate(divide="ignore", invalid="ignore"):
         tg = (ground_z - o[2]) / d[:, 2]
         t_best = np.where((tg > 0) & np.isfinite(tg), tg, t_best)
-        inv = 1.0 / d
+        inv = 1.0 / np.where(d == 0.0, 1e-300, d)
+        reach = max_depth * float(np.linalg.norm(d_cam, axis=1).max())  # z-depth < max_depth => range < reach
+        fwd = np.asarray(R)[:, 2]
         for b in np.asarray(boxes).reshape(-1, 6):
+            if np.linalg.norm(np.maximum(np.maximum(b[:3] - o, o - b[3:]), 0.0)) > reach:
+                continue  # cannot produce a return within max_depth
+            corners = np.array([[b[i], b[1 + j], b[2 + k]] for i in (0, 3) for j in (0, 3) for k in (0, 3)])
+            if ((corners - o) @ fwd).max() <= 0:
+                continue  # entirely behind the camera
             t0 = (b[:3] - o) * inv
             t1 = (b[3:] - o) * inv
-            tn = np.nanmax(np.minimum(t0, t1), axis=1)
-            tf = np.nanmin(np.maximum(t0, t1), axis=1)
+            lo, hi = np.minimum(t0, t1), np.maximum(t0, t1)
+            tn = np.maximum(np.maximum(lo[:, 0], lo[:, 1]), lo[:, 2])
+            tf = np.minimum(np.minimum(hi[:, 0], hi[:, 1]), hi[:, 2])
             hit = (tf >= tn) & (tf > 0)
-            t_best = np.where(hit & (np.maximum(tn, 0) < t_best), np.maximum(tn, 0), t_best)
+            tn = np.maximum(tn, 0)
+            t_best = np.where(hit & (tn < t_best), tn, t_best)
     depth = np.where(np.isfinite(t_best) & (t_best < max_depth), t_best, 0.0)
     img = np.clip(np.rint(depth * scale), 0, 65535).astype(np.uint16).reshape(rows, cols)
     if dropout > 0:

@@ -422,6 +422,45 @@ def main():
         except Exception as e:  # never let the extra take the headline down
             extra["edt_slab_c5"] = {"error": repr(e)[:200]}
 
+    # ---- extra (rank 0, N = 1): the depth-image fusion path — 640x480 frames with the reference's default
+    # intrinsics into a second C2-sized map, host image in, fused grids resident; the sequential CPU restatement beside it
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            from oracle import pyoracle as po
+            rng_ = (5.5, 5.5, 4.5)
+            gd = b200.GridMap(c["size"], c["resolution"], origin=c["origin"], local_update_range=rng_, ground_height=c["origin"][2],
+                              device=local_rank)
+            gd.set_depth_params()
+            od = None if args.no_cpu else po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=rng_,
+                                                       ground_height=c["origin"][2])
+            if od is not None:
+                od.set_depth_params()
+            dpp = b200.DEPTH_DEFAULTS
+            boxes = synth.pillar_boxes(c["seed"], c["origin"], c["size"], c["n_pillars"])
+            tg, tc, st = [], [], {}
+            for f in range(7):
+                pos = np.array([-3.0 + 0.12 * f, 2.0 - 0.05 * f, 1.2])
+                R, _ = synth.look_at(0.7 + 0.03 * f, 0.15)
+                img = synth.render_depth(boxes, c["origin"][2], pos, R, 480, 640, dpp["fx"], dpp["fy"], dpp["cx"], dpp["cy"],
+                                         max_depth=8.0, dropout=0.02, seed=f)
+                gd.sync()
+                t0 = time.perf_counter()
+                gd.depthPoseCallback(img, pos, R)
+                gd.sync()
+                tg.append((time.perf_counter() - t0) * 1e3)
+                if od is not None:
+                    t0 = time.perf_counter()
+                    od.update_depth(img, pos, R)
+                    tc.append((time.perf_counter() - t0) * 1e3)
+                st = gd.depth_stats()
+            extra["depth_fusion"] = {"frame": "640x480 CV_16UC1, reference default intrinsics and filter (skip_pixel 2)",
+                                     "gpu_ms_per_frame_e2e": float(np.median(tg[2:])), "frames": len(tg),
+                                     "cpu_sequential_ms_per_frame": float(np.median(tc[2:])) if tc else None,
+                                     "last_frame": st, "h2d_bytes_per_frame": 480 * 640 * 2}
+            gd.close()
+        except Exception as e:  # never let the extra take the headline down
+            extra["depth_fusion"] = {"error": repr(e)[:200]}
+
     # ---- cpu_baseline: the oracle on this box's host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

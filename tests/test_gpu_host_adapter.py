@@ -44,3 +44,28 @@ def test_cpp_adapter_matches_ctypes_path(b200, algo):
     assert np.array_equal(np.array(d["goal_coords"]), r["goal_coords"])
     assert d["collide_wall"] == 1 and d["collide_outside"] == 1 and d["total_cost1"] == 0
     assert d["time_spent_us"] > 0
+
+
+def test_cpp_adapter_depth_path(b200, po):
+    """GridMap::depthPoseCallback of the C++ adapter: a wall seen in 6 identical frames, against the oracle."""
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(EXE)])
+    out = subprocess.run([EXE, "depth"], capture_output=True, text=True, timeout=120)
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert "error" not in d, d
+    om = po.OracleMap((-6.4, -6.4, -0.01), (12.8, 12.8, 3.2), 0.1, 0.099, (100, 100, 100), -0.01)
+    om.set_depth_params(fx=96.8, fy=96.8, cx=80.3, cy=60.9)
+    qw, qx, qy, qz = 0.5, -0.5, 0.5, -0.5
+    R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                  [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                  [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+    img = np.full((120, 160), 2000, dtype=np.uint16)
+    fused = sum(int(om.update_depth(img, (0.0, 0.0, 1.0), R)) for _ in range(6))
+    st = om.depth_stats()
+    want = dict(fused=fused, wall_occupancy=int(om.get_occupancy([(2.02, 0.0, 1.0)])[0]),
+                wall_inflated=int(om.get_inflate_occupancy([(2.02, 0.0, 1.0)])[0]),
+                free_occupancy=int(om.get_occupancy([(1.0, 0.0, 1.0)])[0]), outside=-1, projected=int(st[0]), rays_cast=int(st[1]),
+                ray_steps=int(st[2]), updates=int(st[3]), has_depth=1)
+    assert want["wall_occupancy"] == 1 and want["wall_inflated"] == 1 and want["free_occupancy"] == 0
+    for k, v in want.items():
+        assert d[k] == v, (k, d[k], v)
