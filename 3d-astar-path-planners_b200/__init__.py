@@ -223,7 +223,7 @@ class GridMap:
         else:
             _ck(lib().b200_map_clear_box(self.h, _d3(min_pos), _d3(max_pos)))
 
-    # ---- depth-image fusion (grid_map.cpp:195-687) ----
+    # ---- depth-image fusion (grid_map.cpp:173-697) ----
     def set_depth_params(self, **kw):
         """grid_map/* depth parameters by the reference's names; unspecified ones take its defaults."""
         d = dict(DEPTH_DEFAULTS)
@@ -235,7 +235,7 @@ class GridMap:
         self.depth_params = d
 
     def depthPoseCallback(self, depth, cam_pos, cam_rot):
-        """depthPoseCallback + updateOccupancyCallback (grid_map.cpp:627-687) for one CV_16UC1 frame (numpy uint16
+        """depthPoseCallback + updateOccupancyCallback (grid_map.cpp:635-697) for one CV_16UC1 frame (numpy uint16
         (rows, cols) or a CUDA tensor); cam_rot = camera-to-world rotation (3x3). Returns False if the frame was dropped."""
         rot = (C.c_double * 9)(*[float(x) for x in np.asarray(cam_rot, dtype=np.float64).reshape(9)])
         fused = C.c_int32(0)

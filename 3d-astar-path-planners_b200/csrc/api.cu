@@ -481,7 +481,7 @@ int b200_map_set_depth_params(b200_map_t* m, const b200_depth_params_t* p) {
   DepthDev& D = m->dd;
   D.fx = p->fx; D.fy = p->fy; D.cx = p->cx; D.cy = p->cy;
   D.scale = p->k_depth_scaling_factor;
-  D.inv_scale = 1.0 / p->k_depth_scaling_factor;  // grid_map.cpp:243
+  D.inv_scale = 1.0 / p->k_depth_scaling_factor;  // grid_map.cpp:245
   D.mindist = p->depth_filter_mindist; D.maxdist = p->depth_filter_maxdist; D.max_ray_length = p->max_ray_length;
   // grid_map.h:27 `#define logit(x) (log((x) / (1 - (x))))` with the host's libm, exactly like the reference (:57-62)
   D.prob_hit_log = std::log(p->p_hit / (1 - p->p_hit));
@@ -519,7 +519,7 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   cudaStream_t st = m->stream;
   if (fused) *fused = 0;
   memset(m->depth_stats, 0, sizeof m->depth_stats);
-  // depthPoseCallback's gate (grid_map.cpp:676-686): a frame whose camera is outside the map is not fused
+  // depthPoseCallback's gate (grid_map.cpp:688-697): a frame whose camera is outside the map is not fused
   for (int i = 0; i < 3; ++i)
     if (cam_pos[i] < m->d.lo[i] || cam_pos[i] > m->d.hi[i]) return B200_OK;
   if (fused) *fused = 1;
@@ -530,12 +530,12 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   // which pixels become rays, in the reference's order (projectDepthImage, grid_map.cpp:212-231 / :233-275)
   int rows_s, cols_s;
   if (P.use_depth_filter) {
-    if (!m->has_first_depth) { m->has_first_depth = true; return B200_OK; }  // :235-237: the first frame only arms the filter
+    if (!m->has_first_depth) { m->has_first_depth = true; return B200_OK; }  // :236-239: the first frame only arms the filter
     const int mg = P.depth_filter_margin, sk = P.skip_pixel;
     rows_s = rows - 2 * mg > 0 ? (rows - 2 * mg + sk - 1) / sk : 0;
     cols_s = cols - 2 * mg > 0 ? (cols - 2 * mg + sk - 1) / sk : 0;
     if (rows_s > 0 && cols_s > 0) {
-      // :258 reads the pixel `skip_pixel` after the sampled one; it must exist
+       // :260 reads the pixel `skip_pixel` after the sampled one; it must exist
       const long long last = (long long)(mg + (rows_s - 1) * sk) * cols + mg + (long long)(cols_s - 1) * sk + sk;
       if (last >= (long long)rows * cols)
         return fail(B200_ERR_UNSUPPORTED, "depth filter: skip_pixel reaches past the image end (the reference reads out of bounds here)");
@@ -544,7 +544,7 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
     rows_s = rows; cols_s = cols;
   }
   const long long n_rays = (long long)rows_s * cols_s;
-  if (n_rays == 0) return B200_OK;  // raycastProcess :323: nothing projected, nothing happens
+  if (n_rays == 0) return B200_OK;  // raycastProcess :320: nothing projected, nothing happens
   REQUIRE(n_rays < 0x7fffffff, "depth image too large");
   const uint16_t* d_img = depth;
   if (!on_device) {
@@ -564,7 +564,7 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   // `char raycast_num_` (grid_map.h:124): 127 is followed by -128
   const int round = (int)(signed char)(m->raycast_num + 1);
   D.round = (int8_t)round;
-  // index box of camera +- local_update_range (:431-438)
+  // index box of camera +- local_update_range (:439-446)
   for (int i = 0; i < 3; ++i) {
     const double org = i == 0 ? m->d.ox : i == 1 ? m->d.oy : m->d.oz;
     D.loc_min[i] = host_floor_idx(cam_pos[i] - m->prm.local_update_range[i], org, m->d.inv_res, m->N[i]);
@@ -584,7 +584,7 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   if (ctl.n_valid == 0) {  // every sampled pixel was filtered out: proj_points_cnt == 0, raycastProcess returns at once
     return B200_OK;
   }
-  m->raycast_num = round;  // :328
+  m->raycast_num = round;  // :325
   if (ctl.n_path_total >= 0xffffffffULL) return fail(B200_ERR_UNSUPPORTED, "depth fusion: more than 2^32 ray steps in one frame");
   if (m->depth_paths.ensure((size_t)ctl.n_path_total * 4 + 4)) return fail(B200_ERR_NOMEM, "ray paths");
   D.paths = (uint32_t*)m->depth_paths.p;
@@ -600,11 +600,11 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   launch_depth_update(D, m->d, m->sm_count, st);
   m->launches += 3;
   CK(cudaGetLastError());
-  // local bounds (:421-429): end-point box, extended by the camera position and the ground height
+  // local bounds (:421-435): end-point box, extended by the camera position and the ground height
   double mn[3], mx[3];
   for (int i = 0; i < 3; ++i) {
     mn[i] = std::min(m->maxb[i], order_key_to_double(ctl.bbox[i]));      // :332-334 start values
-    mx[i] = std::max(m->minb[i], order_key_to_double(ctl.bbox[i + 3]));  // :336-338
+    mx[i] = std::max(m->minb[i], order_key_to_double(ctl.bbox[i + 3]));  // :335-337
     mn[i] = std::min(mn[i], cam_pos[i]);
     mx[i] = std::max(mx[i], cam_pos[i]);
   }
@@ -615,7 +615,7 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
     m->lb_min[i] = host_floor_idx(mn[i], org, m->d.inv_res, m->N[i]);
   }
   m->bounds_pending = false;
-  // clearAndInflateLocalMap (:484-624)
+  // clearAndInflateLocalMap (:509-627)
   int cut_min[3], cut_max[3], cutm_min[3], cutm_max[3];
   for (int i = 0; i < 3; ++i) {
     cut_min[i] = std::max(std::min(m->lb_min[i] - P.local_map_margin, m->N[i] - 1), 0);
@@ -623,9 +623,9 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
     cutm_min[i] = std::max(std::min(cut_min[i] - 5, m->N[i] - 1), 0);
     cutm_max[i] = std::max(std::min(cut_max[i] + 5, m->N[i] - 1), 0);
   }
-  const int inf_step = (int)std::ceil(m->prm.obstacles_inflation / m->prm.resolution);  // :583
+  const int inf_step = (int)std::ceil(m->prm.obstacles_inflation / m->prm.resolution);  // :581
   const int ceil_on = P.virtual_ceil_height > -0.5;
-  const int ceil_id = (int)std::floor((P.virtual_ceil_height - m->d.oz) * m->d.inv_res);  // :621
+  const int ceil_id = (int)std::floor((P.virtual_ceil_height - m->d.oz) * m->d.inv_res);  // :620
   launch_depth_local_map(D, m->d, m->lb_min, m->lb_max, cut_min, cut_max, cutm_min, cutm_max, inf_step, ceil_on, ceil_id, m->sm_count, st);
   m->launches += 4;
   CK(cudaGetLastError());

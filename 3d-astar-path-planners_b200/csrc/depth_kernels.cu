@@ -1,7 +1,7 @@
 // depth_kernels.cu — depth-image fusion into the log-odds grid and the inflated occupancy grid.
 //
-// Behaviour restated from the reference (not ported): grid_map.cpp:195-318 projectDepthImage, :320-456 raycastProcess,
-// :458-482 closetPointInMap, :484-624 clearAndInflateLocalMap, :173-193 setCacheOccupancy, raycast.cpp:32-49,253-346
+// Behaviour restated from the reference (not ported): grid_map.cpp:195-315 projectDepthImage, :317-482 raycastProcess,
+// :484-507 closetPointInMap, :509-627 clearAndInflateLocalMap, :173-193 setCacheOccupancy, raycast.cpp:32-49,253-346
 // (RayCaster::setInput / step).  All position arithmetic is FP64 with separately rounded operations.
 //
 // The reference processes rays ONE AFTER THE OTHER and its result depends on that order in two places:
@@ -18,13 +18,13 @@
 // last walk under the converged F, and the per-voxel log-odds update is order-free.
 //
 // Reference quirks kept on purpose:
-//   * the zero-depth test of the filtered projection reads the NEXT sampled pixel (:258);
+//   * the zero-depth test of the filtered projection reads the NEXT sampled pixel (:260);
 //   * the two flag arrays are never cleared: they hold the `char` frame counter raycast_num_ (grid_map.h:123-124) of
 //     the last frame that set them, and the counter wraps 127 -> -128.  A voxel last flagged exactly 256 fused frames
 //     ago — or never, in frame 255, whose number -1 is the arrays' initial value — therefore looks already taken at
 //     the start of the frame: no ray is cast to it, every ray stops at it.  Kept as persistent int8 arrays here;
 //   * the counters are `short` and a voxel is queued again each time its counter wraps round to 1;
-//   * inflation range-tests only the LINEAR address (:606-611), so a cube sticking out in y or z wraps around.
+//   * inflation range-tests only the LINEAR address (:608), so a cube sticking out in y or z wraps around.
 #include <cooperative_groups.h>
 #include <cstdint>
 
@@ -96,12 +96,12 @@ __global__ void __launch_bounds__(256) depth_project_kernel(DepthDev D, MapDev m
       u = D.margin + (id % D.cols_s) * D.skip;
       const size_t at = (size_t)v * D.cols + u;
       depth = dmul((double)img[at], D.inv_scale);
-      if (img[at + D.skip] == 0) depth = dadd(D.max_ray_length, 0.1);      // :258 (the pointer was advanced first)
-      else if (depth < D.mindist) valid = false;                          // :262
-      else if (depth > D.maxdist) depth = dadd(D.max_ray_length, 0.1);    // :266
+      if (img[at + D.skip] == 0) depth = dadd(D.max_ray_length, 0.1);      // :260 (the pointer was advanced first)
+      else if (depth < D.mindist) valid = false;                          // :264
+      else if (depth > D.maxdist) depth = dadd(D.max_ray_length, 0.1);    // :268
     } else {
       v = id / D.cols; u = id % D.cols;
-      depth = __ddiv_rn((double)img[id], D.scale);                         // :222
+      depth = __ddiv_rn((double)img[id], D.scale);                         // :221
     }
     if (valid) {
       const double qx = __ddiv_rn(dmul(dsub((double)u, D.cx), depth), D.fx);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) depth_project_kernel(DepthDev D, MapDev m
   if (valid) {
     const double cx = D.cam[0], cy = D.cam[1], cz = D.cam[2];
     bool inside = is_in_map(m, px, py, pz);
-    if (!inside) {  // closetPointInMap, :458-482
+    if (!inside) {  // closetPointInMap, :484-507
       const double diff[3] = {dsub(px, cx), dsub(py, cy), dsub(pz, cz)};
       double min_t = 1000000;
 #pragma unroll
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) depth_project_kernel(DepthDev D, MapDev m
     }
     const double dx = dsub(px, cx), dy = dsub(py, cy), dz = dsub(pz, cz);
     const double len = norm3(dx, dy, dz);
-    if (len > D.max_ray_length) {  // :354-357 / :364-368
+    if (len > D.max_ray_length) {  // :353-357 / :364-367
       px = dadd(dmul(__ddiv_rn(dx, len), D.max_ray_length), cx);
       py = dadd(dmul(__ddiv_rn(dy, len), D.max_ray_length), cy);
       pz = dadd(dmul(__ddiv_rn(dz, len), D.max_ray_length), cz);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) depth_reset_kernel(DepthDev D) {
 }
 
 // --------------------------------------------------------------------------------------------------
-// log-odds update of every voxel touched this frame (raycastProcess :431-455)
+// log-odds update of every voxel touched this frame (raycastProcess :448-481)
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) depth_update_kernel(DepthDev D, MapDev m) {
   const unsigned n = D.ctl->n_touched;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) depth_update_kernel(DepthDev D, MapDev m)
 }
 
 // --------------------------------------------------------------------------------------------------
-// clearAndInflateLocalMap (:484-624)
+// clearAndInflateLocalMap (:509-627)
 // --------------------------------------------------------------------------------------------------
 struct Box { int lo[3], hi[3]; };
 __device__ __forceinline__ bool box_cell(const Box& b, long long t, int& x, int& y, int& z) {
@@ -337,7 +337,7 @@ __device__ __forceinline__ bool box_cell(const Box& b, long long t, int& x, int&
   x = b.lo[0] + (int)(t / ((long long)nz * ny));
   return true;
 }
-// every voxel of box M outside box C becomes "unknown" (:531-579: three slab loops whose union is M \ C)
+// every voxel of box M outside box C becomes "unknown" (:529-579: three slab loops whose union is M \ C)
 __global__ void __launch_bounds__(256) depth_shell_kernel(DepthDev D, MapDev m, Box M, Box C) {
   int x, y, z;
   if (!box_cell(M, blockIdx.x * (long long)blockDim.x + threadIdx.x, x, y, z)) return;
@@ -351,7 +351,7 @@ __device__ __forceinline__ void set_inflate_linear(const MapDev& m, long long a)
   const int x = (int)(a / nyz), y = (int)((a % nyz) / m.Nz), z = (int)(a % m.Nz);
   atomicOr(m.occ + ((size_t)x * m.Ny + y) * m.wz + (z >> 5), 1u << (z & 31));
 }
-// occupied voxels of the local box stamp the full (2*step+1)^3 cube (:598-616, grid_map.h:412-441)
+// occupied voxels of the local box stamp the full (2*step+1)^3 cube (:595-616, grid_map.h:412-441)
 __global__ void __launch_bounds__(256) depth_inflate_kernel(DepthDev D, MapDev m, Box L, int step) {
   int x, y, z;
   if (!box_cell(L, blockIdx.x * (long long)blockDim.x + threadIdx.x, x, y, z)) return;
@@ -440,7 +440,7 @@ void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min
   };
   if (cells(M) > 0) depth_shell_kernel<<<blocks_for(cells(M), 256), 256, 0, st>>>(D, m, M, C);
   if (cells(L) > 0) {
-    launch_clear_box(m, lb_min, lb_max, sm_count, st);  // :588-596
+    launch_clear_box(m, lb_min, lb_max, sm_count, st);  // :587-593
     depth_inflate_kernel<<<blocks_for(cells(L), 256), 256, 0, st>>>(D, m, L, inf_step);
     if (ceil_on) {
       const long long cols = (long long)(L.hi[0] - L.lo[0] + 1) * (L.hi[1] - L.lo[1] + 1);

@@ -146,8 +146,8 @@ class GridMap {
   }
 #endif
 
-  // depthPoseCallback (grid_map.cpp:658-687) + the 20 Hz occupancy timer body updateOccupancyCallback (:627-656) in one
-  // call: a CV_16UC1 image (a 32FC1 image is converted by the caller with k_depth_scaling_factor, :665-668), the camera
+  // depthPoseCallback (grid_map.cpp:668-697) + the 20 Hz occupancy timer body updateOccupancyCallback (:635-666) in one
+  // call: a CV_16UC1 image (a 32FC1 image is converted by the caller with k_depth_scaling_factor, :674-677), the camera
   // position and orientation quaternion (w, x, y, z).  The rotation matrix is formed here with the textbook
   // unit-quaternion formula; with Eigen present pass camera_q.toRotationMatrix() to the matrix overload instead.
   bool depthPoseCallback(const uint16_t* depth, int rows, int cols, const Vec3d& pos, double qw, double qx, double qy, double qz) {
@@ -161,7 +161,7 @@ class GridMap {
     const double cam[3] = {pos(0), pos(1), pos(2)};
     int32_t fused = 0;
     b200_check(b200_map_update_depth(h_, depth, rows, cols, cam, cam_rot_row_major, 0, &fused), "depthPoseCallback");
-    if (fused) { has_odom_ = true; has_depth_ = true; }  // :676-681
+    if (fused) { has_odom_ = true; has_depth_ = true; }  // :688-693
     return fused != 0;
   }
 #ifdef B200_WITH_ROS

@@ -122,8 +122,8 @@ typedef struct b200_depth_params {
 } b200_depth_params_t;
 /* Stores the parameters and derives the log-odds constants (logit macro, grid_map.h:27; grid_map.cpp:57-62). */
 int b200_map_set_depth_params(b200_map_t* map, const b200_depth_params_t* p);
-/* One depth frame: GridMap::depthPoseCallback (grid_map.cpp:658-687: image, pose, the camera-inside-the-map gate)
- * followed by the occupancy timer body GridMap::updateOccupancyCallback (grid_map.cpp:627-656): projectDepthImage ->
+/* One depth frame: GridMap::depthPoseCallback (grid_map.cpp:668-697: image, pose, the camera-inside-the-map gate)
+ * followed by the occupancy timer body GridMap::updateOccupancyCallback (grid_map.cpp:635-666): projectDepthImage ->
  * raycastProcess -> clearAndInflateLocalMap.  `depth`: rows*cols uint16 (CV_16UC1), host or device memory.
  * `cam_rot`: camera-to-world rotation, row-major 3x3 — what Eigen's camera_q_.toRotationMatrix() holds on the caller's
  * side.  *fused = 0 when the camera is outside the map (the frame is dropped, as in the reference).

@@ -264,7 +264,7 @@ static void depth_set_params(OMap& m, const OMap::DepthParams& p) {
   m.min_occupancy_log = std::log(p.p_occ / (1 - p.p_occ));
   m.unknown_flag = 0.01;
 }
-// grid_map.cpp:77-85: buffers and their initial values
+// grid_map.cpp:77-86: buffers and their initial values
 static void depth_alloc(OMap& m) {
   if (!m.occ.empty()) return;
   const size_t n = (size_t)m.nvox();
@@ -280,7 +280,7 @@ static inline V3 cam_to_world(const double R[9], const V3& p, const V3& t) {
   return {((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + t.x, ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + t.y,
           ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + t.z};
 }
-// grid_map.cpp:195-318 projectDepthImage.  Returns the projected points in the reference's order.
+// grid_map.cpp:195-315 projectDepthImage.  Returns the projected points in the reference's order.
 static void depth_project(OMap& m, const uint16_t* img, int rows, int cols, const V3& cam, const double R[9], std::vector<V3>& out) {
   const OMap::DepthParams& p = m.dp;
   out.clear();
@@ -293,14 +293,14 @@ static void depth_project(OMap& m, const uint16_t* img, int rows, int cols, cons
       }
     return;
   }
-  if (!m.has_first_depth) { m.has_first_depth = true; return; }  // :235-237: the first filtered frame projects nothing
+  if (!m.has_first_depth) { m.has_first_depth = true; return; }  // :236-239: the first filtered frame projects nothing
   const double inv_factor = 1.0 / p.k_depth_scaling_factor;
   for (int v = p.depth_filter_margin; v < rows - p.depth_filter_margin; v += p.skip_pixel) {
     size_t at = (size_t)v * cols + p.depth_filter_margin;
     for (int u = p.depth_filter_margin; u < cols - p.depth_filter_margin; u += p.skip_pixel) {
       double depth = img[at] * inv_factor;
       at += p.skip_pixel;
-      // :258-269 — the zero test reads the pixel the pointer was just advanced TO, not the one whose depth was taken
+      // :258-271 — the zero test reads the pixel the pointer was just advanced TO, not the one whose depth was taken
       if (img[at] == 0) depth = p.max_ray_length + 0.1;
       else if (depth < p.depth_filter_mindist) continue;
       else if (depth > p.depth_filter_maxdist) depth = p.max_ray_length + 0.1;
@@ -309,7 +309,7 @@ static void depth_project(OMap& m, const uint16_t* img, int rows, int cols, cons
     }
   }
 }
-// grid_map.cpp:458-482 closetPointInMap
+// grid_map.cpp:484-507 closetPointInMap
 static V3 closest_point_in_map(const OMap& m, const V3& pt, const V3& cam) {
   const double diff[3] = {pt.x - cam.x, pt.y - cam.y, pt.z - cam.z};
   const double max_tc[3] = {m.maxb.x - cam.x, m.maxb.y - cam.y, m.maxb.z - cam.z};
@@ -372,7 +372,7 @@ static int64_t set_cache_occupancy(OMap& m, const V3& pos, int occ, std::vector<
 static inline V3 shorten_ray(const V3& pt, const V3& cam, double length, double maxlen) {
   return {(pt.x - cam.x) / length * maxlen + cam.x, (pt.y - cam.y) / length * maxlen + cam.y, (pt.z - cam.z) / length * maxlen + cam.z};
 }
-// grid_map.cpp:320-456 raycastProcess
+// grid_map.cpp:317-482 raycastProcess
 static void depth_raycast(OMap& m, const std::vector<V3>& pts, const V3& cam) {
   if (pts.empty()) return;
   m.raycast_num = (signed char)(m.raycast_num + 1);
@@ -427,7 +427,7 @@ static void depth_raycast(OMap& m, const std::vector<V3>& pts, const V3& cam) {
   bound_index(m, m.lb_min);
   bound_index(m, m.lb_max);
   m.local_updated = true;
-  // :431-455 log-odds update of every voxel touched this round
+  // :448-481 log-odds update of every voxel touched this round
   int min_id[3], max_id[3];
   pos_to_index(m, cam - m.range, min_id);
   pos_to_index(m, cam + m.range, max_id);
@@ -448,7 +448,7 @@ static void depth_raycast(OMap& m, const std::vector<V3>& pts, const V3& cam) {
     m.occ[a] = std::min(std::max(m.occ[a] + upd, m.clamp_min_log), m.clamp_max_log);
   }
 }
-// grid_map.cpp:484-624 clearAndInflateLocalMap
+// grid_map.cpp:509-627 clearAndInflateLocalMap
 static void depth_clear_and_inflate(OMap& m) {
   const int vec_margin = 5, lm = m.dp.local_map_margin;
   int min_cut[3], max_cut[3], min_cut_m[3], max_cut_m[3];
@@ -458,7 +458,7 @@ static void depth_clear_and_inflate(OMap& m) {
   for (int i = 0; i < 3; ++i) { min_cut_m[i] = min_cut[i] - vec_margin; max_cut_m[i] = max_cut[i] + vec_margin; }
   bound_index(m, min_cut_m);
   bound_index(m, max_cut_m);
-  // :531-579 the three slab loops together write every voxel of box M that lies outside box C
+  // :529-579 the three slab loops together write every voxel of box M that lies outside box C
   const double unknown = m.clamp_min_log - m.unknown_flag;
   for (int x = min_cut_m[0]; x <= max_cut_m[0]; ++x)
     for (int y = min_cut_m[1]; y <= max_cut_m[1]; ++y)
@@ -466,12 +466,12 @@ static void depth_clear_and_inflate(OMap& m) {
         const bool inside = x >= min_cut[0] && x <= max_cut[0] && y >= min_cut[1] && y <= max_cut[1] && z >= min_cut[2] && z <= max_cut[2];
         if (!inside) m.occ[to_address(m, x, y, z)] = unknown;
       }
-  // :583-596
+  // :581-593
   const int step = (int)std::ceil(m.inflation / m.res);
   for (int x = m.lb_min[0]; x <= m.lb_max[0]; ++x)
     for (int y = m.lb_min[1]; y <= m.lb_max[1]; ++y)
       for (int z = m.lb_min[2]; z <= m.lb_max[2]; ++z) m.inflate[to_address(m, x, y, z)] = 0;
-  // :598-616 + grid_map.h:412-441 inflatePoint: the full (2*step+1)^3 cube, and only the LINEAR address is range-tested,
+  // :595-616 + grid_map.h:412-441 inflatePoint: the full (2*step+1)^3 cube, and only the LINEAR address is range-tested,
   // so a cube sticking out in y or z wraps into the neighbouring row/column
   const int64_t total = m.nvox();
   for (int x = m.lb_min[0]; x <= m.lb_max[0]; ++x)
@@ -496,7 +496,7 @@ static void depth_clear_and_inflate(OMap& m) {
       }
   }
 }
-// depthPoseCallback's gate (grid_map.cpp:676-686) + updateOccupancyCallback (grid_map.cpp:629-656)
+// depthPoseCallback's gate (grid_map.cpp:688-697) + updateOccupancyCallback (grid_map.cpp:635-666)
 static int depth_update(OMap& m, const uint16_t* img, int rows, int cols, const V3& cam, const double R[9]) {
   if (!is_in_map(m, cam)) return 0;
   depth_alloc(m);

@@ -165,7 +165,7 @@ class OracleMap:
         n = lib().orc_map_export_inflate_cloud(self.h, margin, truncate_height, _ptr(out), cap)
         return out[: min(n, cap)].copy(), n
 
-    # ---- depth-image fusion (grid_map.cpp:195-687) ----
+    # ---- depth-image fusion (grid_map.cpp:173-697) ----
     def set_depth_params(self, **kw):
         self._dp = depth_params(**kw)
         lib().orc_map_set_depth_params(self.h, C.byref(self._dp))

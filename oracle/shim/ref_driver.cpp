@@ -136,8 +136,8 @@ int64_t ref_map_publish_inflate(void* h, int all_info, float* out, int64_t cap) 
   return n;
 }
 // One depth frame through the reference's own callbacks: depthPoseCallback (image copy, pose, the in-map gate,
-// grid_map.cpp:658-687) then the occupancy timer body updateOccupancyCallback (projectDepthImage -> raycastProcess
-// -> clearAndInflateLocalMap, grid_map.cpp:627-656).  Returns 1 if the frame was fused (camera inside the map).
+// grid_map.cpp:668-697) then the occupancy timer body updateOccupancyCallback (projectDepthImage -> raycastProcess
+// -> clearAndInflateLocalMap, grid_map.cpp:635-666).  Returns 1 if the frame was fused (camera inside the map).
 // rot_out (row-major 3x3) = the rotation the reference derived from the quaternion, for the caller to hand to the
 // implementations under test (their boundary takes the matrix).
 int ref_map_update_depth(void* h, const uint16_t* depth, int rows, int cols, const double cam_pos[3], const double quat_wxyz[4],

@@ -100,7 +100,7 @@ def main():
         out[f"{name}/occ_final_values"], inv = np.unique(occ, return_inverse=True)
         assert len(out[f"{name}/occ_final_values"]) < 65536
         out[f"{name}/occ_final_index"] = inv.astype(np.uint16).reshape(occ.shape)
-        # a camera outside the map: the frame is dropped (grid_map.cpp:676-686)
+        # a camera outside the map: the frame is dropped (grid_map.cpp:688-697)
         fused, _ = rm.update_depth(frames[0][2], (0.0, 0.0, SIZE[2] + 1.0), frames[0][1])
         assert not fused and sha(rm.occupancy()) == occ_sha[-1]
         print(name, "frames", len(frames), "proj", proj, "occupied", int((occ > np.log(0.8 / 0.2)).sum()), "inflated",

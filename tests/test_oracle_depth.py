@@ -30,7 +30,7 @@ def test_oracle_depth_fusion_is_the_reference(po, golden, name):
         fresh.update_depth(sc["img"][0], sc["pos"][0], sc["rot"][0])
         occ = fresh.occupancy()
         assert fresh.depth_stats()[3] > int((occ != occ.min()).sum())
-    # a camera outside the map drops the frame (grid_map.cpp:676-686)
+    # a camera outside the map drops the frame (grid_map.cpp:688-697)
     before = om.occupancy()
     assert not om.update_depth(sc["img"][0], (0.0, 0.0, float(golden["size"][2]) + 1.0), sc["rot"][0])
     assert np.array_equal(before, om.occupancy())
