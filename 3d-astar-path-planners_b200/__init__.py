@@ -93,6 +93,7 @@ ABI = [
     ("b200_map_update_depth", C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _i32, C.POINTER(_i32)]),
     ("b200_map_get_occupancy", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
     ("b200_map_download_occupancy", C.c_int, [_vp, _vp]),
+    ("b200_map_export_occupancy_cloud", C.c_int, [_vp, _i32, _i32, _dbl, _vp, _i64, C.POINTER(_i64), _i32]),
     ("b200_map_depth_stats", C.c_int, [_vp, C.POINTER(_i64)]),
     ("b200_map_set_depth_frame_count", C.c_int, [_vp, _i32]),
     ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
@@ -259,6 +260,22 @@ class GridMap:
         out = np.empty(self.dims, dtype=np.float64)
         _ck(lib().b200_map_download_occupancy(self.h, _ptr(out)))
         return out
+
+    def _publish_occupancy(self, which, margin, truncate_height):
+        n = C.c_int64(0)
+        _ck(lib().b200_map_export_occupancy_cloud(self.h, which, margin, truncate_height, None, 0, C.byref(n), 0))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            _ck(lib().b200_map_export_occupancy_cloud(self.h, which, margin, truncate_height, _ptr(out), n.value, C.byref(n), 0))
+        return out
+
+    def publishMap(self, visualization_truncate_height=2.4):
+        """publishMap (grid_map.cpp:806-849): occupied voxels (log-odds) of the local box as PointXYZ records (n,4)."""
+        return self._publish_occupancy(0, int(self.depth_params["local_map_margin"]) // 2, visualization_truncate_height)
+
+    def publishUnknown(self, visualization_truncate_height=2.4):
+        """publishUnknown (grid_map.cpp:902-939)."""
+        return self._publish_occupancy(1, 0, visualization_truncate_height)
 
     def depth_stats(self):
         out = (C.c_int64 * 8)()

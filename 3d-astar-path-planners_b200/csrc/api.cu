@@ -767,6 +767,49 @@ int b200_map_export_inflate_cloud(b200_map_t* m, int32_t margin, double truncate
   return B200_OK;
 }
 
+int b200_map_export_occupancy_cloud(b200_map_t* m, int32_t which, int32_t margin, double truncate_height, float* xyz1, int64_t cap,
+                                    int64_t* n_out, int32_t on_device) {
+  REQUIRE(m && n_out && cap >= 0 && (cap == 0 || xyz1) && margin >= 0 && (which == 0 || which == 1), "bad argument");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_export_occupancy_cloud: call b200_map_set_depth_params first");
+  CK(cudaSetDevice(m->prm.device));
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  int32_t lo[3], hi[3];
+  rc = b200_map_local_bounds(m, lo, hi);
+  if (rc) return rc;
+  int a[3], b[3];
+  for (int i = 0; i < 3; ++i) {  // grid_map.cpp:813-821 / :907-911: box +- margin, then boundIndex
+    a[i] = std::max(std::min(lo[i] - margin, m->N[i] - 1), 0);
+    b[i] = std::max(std::min(hi[i] + margin, m->N[i] - 1), 0);
+  }
+  *n_out = 0;
+  if (a[0] > b[0] || a[1] > b[1] || a[2] > b[2]) return B200_OK;
+  const long long cols = (long long)(b[0] - a[0] + 1) * (b[1] - a[1] + 1);
+  const size_t temp_bytes = export_scan_temp_bytes(cols + 1);
+  const size_t ints = (size_t)(cols + 1) * 4;
+  if (m->stage_aux.ensure(2 * ints + temp_bytes + 256)) return fail(B200_ERR_NOMEM, "export scratch");
+  int* counts = (int*)m->stage_aux.p;
+  int* offsets = counts + (cols + 1);
+  void* temp = (char*)m->stage_aux.p + ((2 * ints + 255) & ~(size_t)255);
+  float4* d_out = (float4*)xyz1;
+  if (!on_device && cap > 0) {
+    if (m->stage_out.ensure((size_t)cap * 16)) return fail(B200_ERR_NOMEM, "export staging");
+    d_out = (float4*)m->stage_out.p;
+  }
+  launch_depth_publish(m->dd, m->d, which, a, b, truncate_height, counts, offsets, temp, temp_bytes, cap > 0 ? d_out : nullptr, cap, m->stream);
+  m->launches += 3;
+  CK(cudaGetLastError());
+  int total = 0;
+  CK(cudaMemcpyAsync(&total, offsets + cols, 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  *n_out = total;
+  if (!on_device && cap > 0 && total > 0) {
+    CK(cudaMemcpyAsync(xyz1, d_out, (size_t)std::min<int64_t>(total, cap) * 16, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  return B200_OK;
+}
+
 int b200_map_set_profiling(b200_map_t* m, int32_t enable) {
   REQUIRE(m, "NULL map");
   m->profiling = enable != 0;

@@ -370,6 +370,39 @@ __global__ void __launch_bounds__(256) depth_ceiling_kernel(MapDev m, Box L, int
   set_inflate_linear(m, (long long)x * m.Ny * m.Nz + (long long)y * m.Nz + ceil_id);
 }
 
+// publishMap (grid_map.cpp:806-849, WHICH 0: occupancy_buffer_ >= logit(p_occ)) and publishUnknown (:902-939, WHICH 1:
+// occupancy_buffer_ < clamp_min - 1e-3): voxel centres of the box, x -> y -> z order, not above the truncate height.
+// Thread per (x,y) column; `out == nullptr` counts, otherwise writes from the column's scanned offset.
+template <int WHICH>
+__device__ __forceinline__ bool publish_keep(const DepthDev& D, double o) {
+  return WHICH == 0 ? !(o < D.min_occ_log) : (o < dsub(D.clamp_min_log, 1e-3));
+}
+template <int WHICH>
+__global__ void __launch_bounds__(256) depth_publish_kernel(DepthDev D, MapDev m, Box B, double truncate, int* __restrict__ counts,
+                                                            const int* __restrict__ offsets, float4* __restrict__ out, long long cap) {
+  const int ny = B.hi[1] - B.lo[1] + 1;
+  const long long cols = (long long)(B.hi[0] - B.lo[0] + 1) * ny;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= cols) return;
+  const int x = B.lo[0] + (int)(i / ny), y = B.lo[1] + (int)(i % ny);
+  const double* col = D.occ + vox_addr(m, x, y, 0);
+  const float px = __double2float_rn(dadd(dmul(dadd((double)x, 0.5), m.res), m.ox));  // indexToPos, grid_map.h:406-410
+  const float py = __double2float_rn(dadd(dmul(dadd((double)y, 0.5), m.res), m.oy));
+  long long o = out ? offsets[i] : 0;
+  int n = 0;
+  for (int z = B.lo[2]; z <= B.hi[2]; ++z) {
+    if (!publish_keep<WHICH>(D, col[z])) continue;
+    const double pz = dadd(dmul(dadd((double)z, 0.5), m.res), m.oz);
+    if (pz > truncate) continue;
+    if (out) {
+      if (o < cap) out[o] = make_float4(px, py, __double2float_rn(pz), 1.0f);  // pcl::PointXYZ: data[3] = 1
+      ++o;
+    }
+    ++n;
+  }
+  if (!out) counts[i] = n;
+}
+
 // getOccupancy(Vector3d), grid_map.h:339-348
 __global__ void depth_get_occupancy_kernel(MapDev m, const double* __restrict__ occ, double min_occ_log, const double* __restrict__ pos,
                                            long long n, int8_t* __restrict__ out) {
@@ -447,6 +480,21 @@ void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min
       depth_ceiling_kernel<<<blocks_for(cols, 256), 256, 0, st>>>(m, L, ceil_id);
     }
   }
+}
+// counts/offsets: cols + 1 ints each; temp: export_scan_temp_bytes(cols + 1) bytes
+void launch_depth_publish(const DepthDev& D, const MapDev& m, int which, const int a[3], const int b[3], double truncate, int* counts,
+                          int* offsets, void* temp, size_t temp_bytes, float4* out, long long cap, cudaStream_t st) {
+  Box B;
+  for (int i = 0; i < 3; ++i) { B.lo[i] = a[i]; B.hi[i] = b[i]; }
+  const long long cols = (long long)(b[0] - a[0] + 1) * (b[1] - a[1] + 1);
+  const unsigned g = blocks_for(cols, 256);
+  cudaMemsetAsync(counts + cols, 0, sizeof(int), st);
+  if (which == 0) depth_publish_kernel<0><<<g, 256, 0, st>>>(D, m, B, truncate, counts, nullptr, nullptr, 0);
+  else depth_publish_kernel<1><<<g, 256, 0, st>>>(D, m, B, truncate, counts, nullptr, nullptr, 0);
+  launch_exclusive_scan(temp, temp_bytes, counts, offsets, cols + 1, st);
+  if (!out) return;  // count only
+  if (which == 0) depth_publish_kernel<0><<<g, 256, 0, st>>>(D, m, B, truncate, nullptr, offsets, out, cap);
+  else depth_publish_kernel<1><<<g, 256, 0, st>>>(D, m, B, truncate, nullptr, offsets, out, cap);
 }
 void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
                                 cudaStream_t st) {

@@ -134,6 +134,9 @@ void launch_depth_update(const DepthDev& D, const MapDev& m, int sm_count, cudaS
 void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min[3], const int lb_max[3], const int cut_min[3],
                             const int cut_max[3], const int cutm_min[3], const int cutm_max[3], int inf_step, int ceil_on, int ceil_id,
                             int sm_count, cudaStream_t st);
+void launch_exclusive_scan(void* temp, size_t temp_bytes, const int* in, int* out, long long n, cudaStream_t st);  // map_kernels.cu (CUB)
+void launch_depth_publish(const DepthDev& D, const MapDev& m, int which, const int a[3], const int b[3], double truncate, int* counts,
+                          int* offsets, void* temp, size_t temp_bytes, float4* out, long long cap, cudaStream_t st);
 void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
                                 cudaStream_t st);
 

@@ -264,6 +264,9 @@ size_t export_scan_temp_bytes(long long cols) {
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (int)cols);
   return bytes;
 }
+void launch_exclusive_scan(void* temp, size_t temp_bytes, const int* in, int* out, long long n, cudaStream_t st) {
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, st);
+}
 // counts/offsets: cols + 1 ints each (the extra element receives the total); temp: export_scan_temp_bytes(cols + 1)
 void launch_export(const MapDev& m, const int a[3], const int b[3], double truncate, int* counts, int* offsets, void* temp,
                    size_t temp_bytes, float4* out, long long cap, cudaStream_t st) {

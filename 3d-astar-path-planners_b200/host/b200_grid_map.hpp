@@ -264,6 +264,13 @@ class GridMap {
     if (n) b200_check(b200_map_export_inflate_cloud(h_, all_info ? local_map_margin : 0, visualization_truncate_height, pts.data(), n, &n, 0), "publishMapInflate");
     return pts;
   }
+  // publishMap (grid_map.cpp:806-849) / publishUnknown (:902-939): the PointXYZ records of the clouds the reference publishes
+  std::vector<float> publishMap(double visualization_truncate_height = 2.4) const {
+    return exportOccupancy(0, dprm_.local_map_margin / 2, visualization_truncate_height);
+  }
+  std::vector<float> publishUnknown(double visualization_truncate_height = 2.4) const {
+    return exportOccupancy(1, 0, visualization_truncate_height);
+  }
   // new: exact squared EDT + safety cost field (replaces the commented-out evaluateCoarseEDT hook)
   void buildDistanceField(double d_safe) { b200_check(b200_map_build_edt(h_, d_safe), "build_edt"); }
 
@@ -271,6 +278,13 @@ class GridMap {
   const int* voxelNum() const { return n_; }
 
  private:
+  std::vector<float> exportOccupancy(int which, int margin, double truncate) const {
+    int64_t n = 0;
+    b200_check(b200_map_export_occupancy_cloud(h_, which, margin, truncate, nullptr, 0, &n, 0), "publishMap");
+    std::vector<float> pts((size_t)n * 4);
+    if (n) b200_check(b200_map_export_occupancy_cloud(h_, which, margin, truncate, pts.data(), n, &n, 0), "publishMap");
+    return pts;
+  }
   void create() {
     if (h_) { b200_map_destroy(h_); h_ = nullptr; }
     res_inv_ = 1 / prm_.resolution;

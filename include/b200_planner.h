@@ -135,6 +135,12 @@ int b200_map_update_depth(b200_map_t* map, const uint16_t* depth, int32_t rows, 
 int b200_map_get_occupancy(b200_map_t* map, const double* pos_xyz, int64_t n, int8_t* out, int32_t on_device);
 /* occupancy_buffer_ (log-odds, double per voxel, address x*Ny*Nz + y*Nz + z) to host memory. */
 int b200_map_download_occupancy(b200_map_t* map, double* dst);
+/* GridMap::publishMap (grid_map.cpp:806-849; which = 0: voxels whose log-odds are not below logit(p_occ), box = local
+ * bounds +- margin with margin = local_map_margin / 2) and GridMap::publishUnknown (:902-939; which = 1: log-odds below
+ * clamp_min - 1e-3, margin 0): voxel centres in x -> y -> z order, not above `truncate_height`, as 16-byte PointXYZ
+ * records (float x, y, z, 1.0f).  *n_out = number of points (may exceed cap; only cap are written). */
+int b200_map_export_occupancy_cloud(b200_map_t* map, int32_t which, int32_t margin, double truncate_height, float* xyz1,
+                                    int64_t cap, int64_t* n_out, int32_t on_device);
 /* Counters of the last fused frame: [0] projected points, [1] rays cast, [2] voxels stepped through, [3] log-odds
  * updates applied, [4] rounds of the ray-order fixed-point iteration, [5] raycast_num_ (int8, wraps). */
 int b200_map_depth_stats(b200_map_t* map, int64_t out[8]);

@@ -496,6 +496,26 @@ static void depth_clear_and_inflate(OMap& m) {
       }
   }
 }
+// publishMap (grid_map.cpp:806-849; which 0) / publishUnknown (:902-939; which 1): PointXYZ records (x, y, z, 1.0f)
+static int64_t export_occupancy_cloud(OMap& m, int which, int margin, double truncate_height, float* out, int64_t cap) {
+  depth_alloc(m);
+  int a[3], b[3];
+  for (int i = 0; i < 3; ++i) { a[i] = m.lb_min[i] - margin; b[i] = m.lb_max[i] + margin; }
+  bound_index(m, a);
+  bound_index(m, b);
+  int64_t n = 0;
+  for (int x = a[0]; x <= b[0]; ++x)
+    for (int y = a[1]; y <= b[1]; ++y)
+      for (int z = a[2]; z <= b[2]; ++z) {
+        const double o = m.occ[to_address(m, x, y, z)];
+        if (which == 0 ? (o < m.min_occupancy_log) : !(o < m.clamp_min_log - 1e-3)) continue;
+        const double px = (x + 0.5) * m.res + m.origin.x, py = (y + 0.5) * m.res + m.origin.y, pz = (z + 0.5) * m.res + m.origin.z;
+        if (pz > truncate_height) continue;
+        if (n < cap) { out[4 * n] = (float)px; out[4 * n + 1] = (float)py; out[4 * n + 2] = (float)pz; out[4 * n + 3] = 1.0f; }
+        ++n;
+      }
+  return n;
+}
 // depthPoseCallback's gate (grid_map.cpp:688-697) + updateOccupancyCallback (grid_map.cpp:635-666)
 static int depth_update(OMap& m, const uint16_t* img, int rows, int cols, const V3& cam, const double R[9]) {
   if (!is_in_map(m, cam)) return 0;
@@ -1166,6 +1186,9 @@ void orc_map_get_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
     pos_to_index(m, p, id);
     out[i] = m.occ[to_address(m, id[0], id[1], id[2])] > m.min_occupancy_log ? 1 : 0;
   }
+}
+int64_t orc_map_export_occupancy_cloud(void* h, int which, int margin, double truncate_height, float* out, int64_t cap) {
+  return export_occupancy_cloud(*(OMap*)h, which, margin, truncate_height, out, cap);
 }
 void orc_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   OMap* m = (OMap*)h;

@@ -105,6 +105,8 @@ def lib():
         L.orc_map_raycast_num.restype = C.c_int
         L.orc_map_depth_stats.argtypes = [vp, vp]
         L.orc_map_get_occupancy.argtypes = [vp, vp, i64, vp]
+        L.orc_map_export_occupancy_cloud.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, i64]
+        L.orc_map_export_occupancy_cloud.restype = i64
         _LIB = L
     return _LIB
 
@@ -194,6 +196,13 @@ class OracleMap:
         out = np.zeros(8, dtype=np.int64)
         lib().orc_map_depth_stats(self.h, _ptr(out))
         return out
+
+    def export_occupancy_cloud(self, which, margin=0, truncate_height=2.4):
+        """publishMap (which=0, margin = local_map_margin // 2) / publishUnknown (which=1) -> (n,4) float32."""
+        cap = int(np.prod(self.dims))
+        out = np.empty((cap, 4), dtype=np.float32)
+        n = lib().orc_map_export_occupancy_cloud(self.h, which, margin, truncate_height, _ptr(out), cap)
+        return out[:n].copy()
 
     def get_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

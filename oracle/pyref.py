@@ -52,6 +52,8 @@ def lib():
         L.ref_map_proj_points.restype = C.c_int
         L.ref_map_set_raycast_num.argtypes = [vp, C.c_int]
         L.ref_map_get_occupancy.argtypes = [vp, vp, i64, vp]
+        L.ref_map_publish_occupancy.argtypes = [vp, C.c_int, vp, i64]
+        L.ref_map_publish_occupancy.restype = i64
         L.ref_planner_create.restype = vp
         L.ref_planner_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, vp]
         L.ref_planner_destroy.argtypes = [vp]
@@ -128,6 +130,13 @@ class RefMap:
         out = np.empty(self.dims, dtype=np.float64)
         lib().ref_map_download_occupancy(self.h, _ptr(out))
         return out
+
+    def publish_occupancy(self, which):
+        """publishMap (which=0) / publishUnknown (which=1): the PointXYZ records the reference published, (n,4) float32."""
+        cap = int(np.prod(self.dims))
+        out = np.empty((cap, 4), dtype=np.float32)
+        n = lib().ref_map_publish_occupancy(self.h, which, _ptr(out), cap)
+        return out[:n].copy()
 
     def raycast_num(self):
         return lib().ref_map_raycast_num(self.h)

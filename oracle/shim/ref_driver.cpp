@@ -135,6 +135,17 @@ int64_t ref_map_publish_inflate(void* h, int all_info, float* out, int64_t cap) 
   std::memcpy(out, shim::last_cloud_blob().data(), (size_t)std::min<int64_t>(n, cap) * 16);
   return n;
 }
+// GridMap::publishMap (grid_map.cpp:806-849, which = 0, one fake subscriber) / publishUnknown (:902-939, which = 1)
+int64_t ref_map_publish_occupancy(void* h, int which, float* out, int64_t cap) {
+  GridMap& g = *((RefMap*)h)->gm;
+  shim::fake_subscribers() = 1;
+  shim::last_cloud_blob().clear();
+  if (which == 0) g.publishMap(); else g.publishUnknown();
+  shim::fake_subscribers() = 0;
+  const int64_t n = (int64_t)(shim::last_cloud_blob().size() / 16);
+  std::memcpy(out, shim::last_cloud_blob().data(), (size_t)std::min<int64_t>(n, cap) * 16);
+  return n;
+}
 // One depth frame through the reference's own callbacks: depthPoseCallback (image copy, pose, the in-map gate,
 // grid_map.cpp:668-697) then the occupancy timer body updateOccupancyCallback (projectDepthImage -> raycastProcess
 // -> clearAndInflateLocalMap, grid_map.cpp:635-666).  Returns 1 if the frame was fused (camera inside the map).

@@ -23,7 +23,15 @@ def scenario(g, name):
                 pos=g[f"{name}/pos"], rot=g[f"{name}/rot"], img=g[f"{name}/img"], occ_sha=g[f"{name}/occ_sha"],
                 inflate_bits=g[f"{name}/inflate_bits"], bounds=g[f"{name}/bounds"], proj=g[f"{name}/proj"],
                 frames_after=int(g[f"{name}/frames_after"]), rewind=int(g[f"{name}/rewind"]),
+                pub_map_sha=str(g[f"{name}/pub_map_sha"]), pub_unknown_sha=str(g[f"{name}/pub_unknown_sha"]),
+                pub_counts=tuple(int(x) for x in g[f"{name}/pub_counts"]),
                 occ_final=g[f"{name}/occ_final_values"][g[f"{name}/occ_final_index"]])
+
+
+def check_publishers(sc, pub_map, pub_unknown):
+    """pub_map / pub_unknown: (n,4) float32 PointXYZ records of publishMap / publishUnknown after the last frame."""
+    assert (len(pub_map), len(pub_unknown)) == sc["pub_counts"]
+    assert sha(pub_map) == sc["pub_map_sha"] and sha(pub_unknown) == sc["pub_unknown_sha"]
 
 
 def replay(sc, update, occupancy, inflate, bounds, dims, set_frame_count):

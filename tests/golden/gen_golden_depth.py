@@ -96,6 +96,9 @@ def main():
         out[f"{name}/bounds"] = np.array(bounds)
         out[f"{name}/proj"] = np.array(proj)
         out[f"{name}/frames_after"] = np.array(rm.raycast_num())
+        pm, pu = rm.publish_occupancy(0), rm.publish_occupancy(1)  # publishMap / publishUnknown (grid_map.cpp:806-849, :902-939)
+        out[f"{name}/pub_map_sha"], out[f"{name}/pub_unknown_sha"] = np.array(sha(pm)), np.array(sha(pu))
+        out[f"{name}/pub_counts"] = np.array([len(pm), len(pu)])
         occ = rm.occupancy()
         out[f"{name}/occ_final_values"], inv = np.unique(occ, return_inverse=True)
         assert len(out[f"{name}/occ_final_values"]) < 65536

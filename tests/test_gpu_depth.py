@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from depth_util import GOLDEN, SCENARIOS, replay, scenario
+from depth_util import GOLDEN, SCENARIOS, check_publishers, replay, scenario
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,7 @@ def test_depth_fusion_is_bit_identical_to_the_reference(b200, golden, name):
     replay(sc, gm.depthPoseCallback, gm.occupancy, gm.inflate, gm.local_bounds, gm.dims, gm.set_depth_frame_count)
     st = gm.depth_stats()
     assert st["projected"] == sc["proj"][-1] and st["frames"] == sc["frames_after"]
+    check_publishers(sc, gm.publishMap(), gm.publishUnknown())
     before = gm.occupancy()
     assert not gm.depthPoseCallback(sc["img"][0], (0.0, 0.0, float(golden["size"][2]) + 1.0), sc["rot"][0])  # camera outside: dropped
     assert np.array_equal(before, gm.occupancy())
@@ -65,6 +66,11 @@ def test_large_frames_match_the_oracle(b200, po, synth):
     pos = (idx + 0.5) * c["resolution"] + np.array(c["origin"])
     q = np.concatenate([pos, pos + [0.0, 0.0, 50.0], r.uniform(-12, 12, (2000, 3))])
     assert np.array_equal(gm.getOccupancy(q), om.get_occupancy(q))
+    # publishMap / publishUnknown blobs (grid_map.cpp:806-849, :902-939)
+    pm, pu = gm.publishMap(), gm.publishUnknown()
+    assert len(pm) > 500 and len(pu) > 1000
+    assert np.array_equal(pm, om.export_occupancy_cloud(0, dp["local_map_margin"] // 2))
+    assert np.array_equal(pu, om.export_occupancy_cloud(1, 0))
     pl = b200.Planner("thetastar", resolution=c["resolution"], allocate_num=200000)
     pl.setGridMap(gm)
     op = po.OraclePlanner("thetastar", om, c["resolution"], 5.0, 200000, po.FAITHFUL)

@@ -3,7 +3,7 @@ golden vectors everywhere, and the live reference build where /root/reference ex
 import numpy as np
 import pytest
 
-from depth_util import GOLDEN, SCENARIOS, replay, scenario
+from depth_util import GOLDEN, SCENARIOS, check_publishers, replay, scenario
 
 
 @pytest.fixture(scope="module")
@@ -19,6 +19,7 @@ def test_oracle_depth_fusion_is_the_reference(po, golden, name):
     om.set_depth_params(**sc["params"])
     replay(sc, om.update_depth, om.occupancy, om.inflate, om.local_bounds, om.dims, om.set_raycast_num)
     assert om.raycast_num() == sc["frames_after"]
+    check_publishers(sc, om.export_occupancy_cloud(0, sc["params"]["local_map_margin"] // 2), om.export_occupancy_cloud(1, 0))
     st = om.depth_stats()
     assert st[0] == sc["proj"][-1]
     if name == "count_wrap":
@@ -66,8 +67,13 @@ def test_oracle_depth_vs_live_reference(po, synth):
     boxes = synth.pillar_boxes(5, origin, size, 12)
     rng = np.random.default_rng(9)
     for f in range(7):
-        pos = (rng.uniform(-3.5, 3.5), rng.uniform(-2.5, 2.5), rng.uniform(0.3, 2.0))
-        R, q = synth.look_at(rng.uniform(0, 6.28), rng.uniform(-0.4, 0.6))
+        # frames 0-4: a slowly moving camera (surfaces seen repeatedly become occupied); 5-6: somewhere else entirely
+        if f < 5:
+            pos = (-2.0 + 0.08 * f + rng.uniform(-0.02, 0.02), 1.0 + rng.uniform(-0.02, 0.02), 1.1)
+            R, q = synth.look_at(-0.6 + 0.03 * f, 0.2)
+        else:
+            pos = (rng.uniform(-3.5, 3.5), rng.uniform(-2.5, 2.5), rng.uniform(0.3, 2.0))
+            R, q = synth.look_at(rng.uniform(0, 6.28), rng.uniform(-0.4, 0.6))
         img = synth.render_depth(boxes, gh, pos, R, 76, 100, dp["fx"], dp["fy"], dp["cx"], dp["cy"], dropout=0.05, seed=f)
         fused, Rref = rm.update_depth(img, pos, q)
         assert om.update_depth(img, pos, Rref) == fused
@@ -76,3 +82,8 @@ def test_oracle_depth_vs_live_reference(po, synth):
         assert rm.proj_points() == om.depth_stats()[0]
         if rm.proj_points():
             assert rm.local_bounds() == om.local_bounds()
+            # the two raw-occupancy publishers (grid_map.cpp:806-849, :902-939)
+            assert np.array_equal(rm.publish_occupancy(0), om.export_occupancy_cloud(0, dp["local_map_margin"] // 2))
+            assert np.array_equal(rm.publish_occupancy(1), om.export_occupancy_cloud(1, 0))
+        if f == 4:
+            assert len(om.export_occupancy_cloud(0, 1)) > 20 and len(om.export_occupancy_cloud(1, 0)) > 1000
