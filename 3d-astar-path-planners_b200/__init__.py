@@ -92,6 +92,7 @@ ABI = [
     ("b200_map_set_depth_params", C.c_int, [_vp, C.POINTER(DepthParams)]),
     ("b200_map_update_depth", C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _i32, C.POINTER(_i32)]),
     ("b200_map_get_occupancy", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
+    ("b200_map_get_log_odds", C.c_int, [_vp, _vp, _i64, _vp, _i32]),
     ("b200_map_download_occupancy", C.c_int, [_vp, _vp]),
     ("b200_map_export_occupancy_cloud", C.c_int, [_vp, _i32, _i32, _dbl, _vp, _i64, C.POINTER(_i64), _i32]),
     ("b200_map_depth_stats", C.c_int, [_vp, C.POINTER(_i64)]),
@@ -103,6 +104,7 @@ ABI = [
     ("b200_map_download_costq", C.c_int, [_vp, _vp]),
     ("b200_map_download_cost", C.c_int, [_vp, _vp]),
     ("b200_los_batch", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
+    ("b200_los_batch_dda", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
     ("b200_map_set_profiling", C.c_int, [_vp, _i32]),
     ("b200_map_get_stage_ms", C.c_int, [_vp, C.POINTER(_dbl)]),
     ("b200_planner_create", C.c_int, [C.c_char_p, C.POINTER(PlannerParams), _pp]),
@@ -255,6 +257,18 @@ class GridMap:
         _ck(lib().b200_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out), 0))
         return out
 
+    def log_odds(self, pos):
+        """occupancy_buffer_ at the (clamped) voxel of each position."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.float64)
+        _ck(lib().b200_map_get_log_odds(self.h, _ptr(pos), len(pos), _ptr(out), 0))
+        return out
+
+    def isUnknown(self, pos):
+        """isUnknown(Vector3d) (grid_map.h:276-289)."""
+        p = self.depth_params
+        return self.log_odds(pos) < np.log(p["p_min"] / (1 - p["p_min"])) - 1e-3
+
     def occupancy(self):
         """occupancy_buffer_ (log-odds) as a (Nx,Ny,Nz) float64 array."""
         out = np.empty(self.dims, dtype=np.float64)
@@ -389,6 +403,18 @@ class GridMap:
         ns = np.empty(len(s), dtype=np.int32)
         _ck(lib().b200_los_batch(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(ns), 0))
         return (vis, ns) if return_samples else vis
+
+    def los_batch_dda(self, starts, ends, return_cells=False, vis_out=None, cells_out=None):
+        """Voxel-traversal (Amanatides-Woo, raycast.cpp:253-346) line of sight for n segments."""
+        if _is_dev(starts):
+            _ck(lib().b200_los_batch_dda(self.h, _ptr(starts), _ptr(ends), starts.shape[0], _ptr(vis_out), _ptr(cells_out), 1))
+            return vis_out
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        e = np.ascontiguousarray(ends, dtype=np.float64).reshape(-1, 3)
+        vis = np.empty(len(s), dtype=np.uint8)
+        nc = np.empty(len(s), dtype=np.int32)
+        _ck(lib().b200_los_batch_dda(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(nc), 0))
+        return (vis, nc) if return_cells else vis
 
     def set_stream(self, cuda_stream_ptr):
         _ck(lib().b200_map_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

@@ -650,6 +650,16 @@ int b200_map_get_occupancy(b200_map_t* m, const double* pos, int64_t n, int8_t* 
     launch_depth_get_occupancy(m->d, m->dd.occ, m->dd.min_occ_log, p, n, o, m->stream);
   });
 }
+int b200_map_get_log_odds(b200_map_t* m, const double* pos, int64_t n, double* out, int32_t on_device) {
+  REQUIRE(m, "NULL map");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_get_log_odds: call b200_map_set_depth_params first");
+  CK(cudaSetDevice(m->prm.device));
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  return per_position<double>(m, pos, n, out, 1, on_device, [&](const double* p, double* o) {
+    launch_depth_get_log_odds(m->d, m->dd.occ, p, n, o, m->stream);
+  });
+}
 int b200_map_download_occupancy(b200_map_t* m, double* dst) {
   REQUIRE(m && dst, "NULL argument");
   if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_download_occupancy: call b200_map_set_depth_params first");
@@ -723,6 +733,31 @@ int b200_los_batch(b200_map_t* m, const double* s, const double* e, int64_t n, u
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(vis, m->stage_out.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
   if (ns) CK(cudaMemcpyAsync(ns, m->stage_aux.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+
+int b200_los_batch_dda(b200_map_t* m, const double* s, const double* e, int64_t n, uint8_t* vis, int32_t* nc, int32_t on_device) {
+  REQUIRE(m && n >= 0 && (n == 0 || (s && e && vis)), "bad argument");
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  if (on_device) {
+    launch_los_dda(m->d, s, e, n, vis, nc, m->stream);
+    m->launches++;
+    CK(cudaGetLastError());
+    return B200_OK;
+  }
+  if (m->stage_in.ensure((size_t)n * 48) || m->stage_out.ensure((size_t)n) || m->stage_aux.ensure((size_t)n * 4))
+    return fail(B200_ERR_NOMEM, "los staging");
+  double* ds = (double*)m->stage_in.p;
+  double* de = ds + 3 * n;
+  CK(cudaMemcpyAsync(ds, s, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  CK(cudaMemcpyAsync(de, e, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  launch_los_dda(m->d, ds, de, n, (uint8_t*)m->stage_out.p, (int32_t*)m->stage_aux.p, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vis, m->stage_out.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+  if (nc) CK(cudaMemcpyAsync(nc, m->stage_aux.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   return B200_OK;
 }

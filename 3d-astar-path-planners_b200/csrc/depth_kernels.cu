@@ -403,6 +403,36 @@ __global__ void __launch_bounds__(256) depth_publish_kernel(DepthDev D, MapDev m
   if (!out) counts[i] = n;
 }
 
+// ---- 3-D DDA line of sight (ours — the reference's planners use the sampled fastLOS) ----------
+// visible iff both end points are inside the map and no voxel the reference's RayCaster (raycast.cpp:253-346) visits
+// between them — start and end voxel included — is occupied in the inflated grid.  The traversal runs on
+// map-relative voxel coordinates (pos - origin) * res_inv.  It is a serial FP64 recurrence, so one THREAD walks one
+// segment (a warp takes 32 segments); splitting a segment over lanes would restart the recurrence at interior
+// points and could visit different voxels on grazing rays.
+__global__ void __launch_bounds__(128) los_dda_kernel(MapDev m, const double* __restrict__ s, const double* __restrict__ e, long long n,
+                                                      int max_steps, uint8_t* __restrict__ vis, int32_t* __restrict__ ncells) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sx = s[3 * i], sy = s[3 * i + 1], sz = s[3 * i + 2], ex = e[3 * i], ey = e[3 * i + 1], ez = e[3 * i + 2];
+  int cells = 0;
+  bool ok = is_in_map(m, sx, sy, sz) && is_in_map(m, ex, ey, ez);
+  if (ok) {
+    RayWalk w;
+    w.set(dmul(dsub(sx, m.ox), m.inv_res), dmul(dsub(sy, m.oy), m.inv_res), dmul(dsub(sz, m.oz), m.inv_res),
+          dmul(dsub(ex, m.ox), m.inv_res), dmul(dsub(ey, m.oy), m.inv_res), dmul(dsub(ez, m.oz), m.inv_res));
+    for (;;) {
+      int ix, iy, iz;
+      const bool more = w.step(ix, iy, iz);
+      ++cells;
+      if (ix < 0 || iy < 0 || iz < 0 || ix >= m.Nx || iy >= m.Ny || iz >= m.Nz || occ_bit(m, ix, iy, iz)) { ok = false; break; }
+      if (!more) break;
+      if (cells > max_steps) { ok = false; break; }  // a walk that misses its end cell counts as blocked
+    }
+  }
+  vis[i] = ok ? 1 : 0;
+  if (ncells) ncells[i] = cells;
+}
+
 // getOccupancy(Vector3d), grid_map.h:339-348
 __global__ void depth_get_occupancy_kernel(MapDev m, const double* __restrict__ occ, double min_occ_log, const double* __restrict__ pos,
                                            long long n, int8_t* __restrict__ out) {
@@ -412,6 +442,16 @@ __global__ void depth_get_occupancy_kernel(MapDev m, const double* __restrict__ 
   if (!is_in_map(m, x, y, z)) { out[i] = -1; return; }
   const int ix = pos_to_idx1(x, m.ox, m.inv_res), iy = pos_to_idx1(y, m.oy, m.inv_res), iz = pos_to_idx1(z, m.oz, m.inv_res);
   out[i] = occ[vox_addr(m, ix, iy, iz)] > min_occ_log ? 1 : 0;
+}
+// occupancy_buffer_[toAddress(boundIndex(posToIndex(pos)))] — the read behind isUnknown / isKnownFree (grid_map.h:276-300)
+__global__ void depth_get_log_odds_kernel(MapDev m, const double* __restrict__ occ, const double* __restrict__ pos, long long n,
+                                          double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ix = min(max(pos_to_idx1(pos[3 * i], m.ox, m.inv_res), 0), m.Nx - 1);
+  const int iy = min(max(pos_to_idx1(pos[3 * i + 1], m.oy, m.inv_res), 0), m.Ny - 1);
+  const int iz = min(max(pos_to_idx1(pos[3 * i + 2], m.oz, m.inv_res), 0), m.Nz - 1);
+  out[i] = occ[vox_addr(m, ix, iy, iz)];
 }
 __global__ void depth_fill_kernel(double* __restrict__ p, double v, uint32_t* __restrict__ f0, uint32_t* __restrict__ f1,
                                   uint32_t* __restrict__ f2, long long n) {
@@ -495,6 +535,12 @@ void launch_depth_publish(const DepthDev& D, const MapDev& m, int which, const i
   if (!out) return;  // count only
   if (which == 0) depth_publish_kernel<0><<<g, 256, 0, st>>>(D, m, B, truncate, nullptr, offsets, out, cap);
   else depth_publish_kernel<1><<<g, 256, 0, st>>>(D, m, B, truncate, nullptr, offsets, out, cap);
+}
+void launch_los_dda(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* ncells, cudaStream_t st) {
+  if (n > 0) los_dda_kernel<<<blocks_for(n, 128), 128, 0, st>>>(m, s, e, n, m.Nx + m.Ny + m.Nz + 4, vis, ncells);
+}
+void launch_depth_get_log_odds(const MapDev& m, const double* occ, const double* pos, long long n, double* out, cudaStream_t st) {
+  if (n > 0) depth_get_log_odds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(m, occ, pos, n, out);
 }
 void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
                                 cudaStream_t st) {

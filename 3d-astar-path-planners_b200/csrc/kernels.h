@@ -137,6 +137,8 @@ void launch_depth_local_map(const DepthDev& D, const MapDev& m, const int lb_min
 void launch_exclusive_scan(void* temp, size_t temp_bytes, const int* in, int* out, long long n, cudaStream_t st);  // map_kernels.cu (CUB)
 void launch_depth_publish(const DepthDev& D, const MapDev& m, int which, const int a[3], const int b[3], double truncate, int* counts,
                           int* offsets, void* temp, size_t temp_bytes, float4* out, long long cap, cudaStream_t st);
+void launch_los_dda(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* ncells, cudaStream_t st);
+void launch_depth_get_log_odds(const MapDev& m, const double* occ, const double* pos, long long n, double* out, cudaStream_t st);
 void launch_depth_get_occupancy(const MapDev& m, const double* occ, double min_occ_log, const double* pos, long long n, int8_t* out,
                                 cudaStream_t st);
 

@@ -186,6 +186,28 @@ class GridMap {
     indexToPos(id, pos);
     return getOccupancy(pos);
   }
+  // grid_map.h:276-300 — isUnknown / isKnownFree read the raw log-odds of the (clamped) voxel
+  inline double logOdds(const Vec3d& pos) const {
+    double v = 0;
+    const double p[3] = {pos(0), pos(1), pos(2)};
+    b200_check(b200_map_get_log_odds(h_, p, 1, &v, 0), "log odds");
+    return v;
+  }
+  inline bool isUnknown(const Vec3d& pos) const { return logOdds(pos) < clampMinLog() - 1e-3; }
+  inline bool isUnknown(const Vec3i& id) const {
+    Vec3i id1 = id;
+    boundIndex(id1);
+    Vec3d pos;
+    indexToPos(id1, pos);
+    return isUnknown(pos);
+  }
+  inline bool isKnownFree(const Vec3i& id) const {
+    Vec3i id1 = id;
+    boundIndex(id1);
+    Vec3d pos;
+    indexToPos(id1, pos);
+    return logOdds(pos) >= clampMinLog() && getInflateOccupancy(pos) == 0;
+  }
   inline bool isKnownOccupied(const Vec3i& id) const {
     Vec3i id1 = id;
     boundIndex(id1);
@@ -195,6 +217,7 @@ class GridMap {
   }
   bool hasDepthObservation() const { return has_depth_; }
   const b200_depth_params_t& depthParams() const { return dprm_; }
+  double clampMinLog() const { return std::log(dprm_.p_min / (1 - dprm_.p_min)); }  // grid_map.h:27, grid_map.cpp:59
 
   void resetBuffer() { b200_check(b200_map_reset(h_), "resetBuffer"); }
   void resetBuffer(Vec3d min_pos, Vec3d max_pos) {

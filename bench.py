@@ -379,6 +379,19 @@ def main():
         extra["fastlos_segments_per_s"] = float(t[1]) / (los_ms * 1e-3)
         extra["fastlos_samples_per_s"] = float(t[2]) / (los_ms * 1e-3)
         extra["fastlos_visible_frac"] = float(vis.float().mean().item())
+        # the same segments through the voxel-traversal line of sight (rank-local number)
+        vis2 = torch.empty(nseg, dtype=torch.uint8, device=dev)
+        ncell = torch.empty(nseg, dtype=torch.int32, device=dev)
+        gm.los_batch_dda(da, db, vis_out=vis2, cells_out=ncell)
+        torch.cuda.synchronize()
+        a.record()
+        gm.los_batch_dda(da, db, vis_out=vis2, cells_out=ncell)
+        b.record()
+        torch.cuda.synchronize()
+        dda_ms = a.elapsed_time(b)
+        extra["ddalos_segments_per_s_per_gpu"] = nseg / (dda_ms * 1e-3)
+        extra["ddalos_cells_per_s_per_gpu"] = float(ncell.sum().item()) / (dda_ms * 1e-3)
+        extra["ddalos_agrees_with_fastlos_frac"] = float((vis2 == vis).float().mean().item())
         for algo, sem, nq in QUERY_ALGOS:
             # every rank draws the same global batch and takes its contiguous shard (map replicated, no collective)
             s, g = synth.random_queries(6, occ, c["origin"], c["size"], nq * world, min_dist=5.0, z_range=(0.3, 3.0))

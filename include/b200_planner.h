@@ -133,6 +133,10 @@ int b200_map_update_depth(b200_map_t* map, const uint16_t* depth, int32_t rows, 
                           const double cam_rot[9], int32_t on_device, int32_t* fused);
 /* GridMap::getOccupancy(Vector3d) (grid_map.h:339-348): -1 outside, else occupancy_buffer_ > logit(p_occ). */
 int b200_map_get_occupancy(b200_map_t* map, const double* pos_xyz, int64_t n, int8_t* out, int32_t on_device);
+/* The raw log-odds of the voxel holding each position, index clamped into the map (posToIndex + boundIndex): the read
+ * behind GridMap::isUnknown (value < logit(p_min) - 1e-3) and isKnownFree (value >= logit(p_min) and the inflated voxel
+ * is free), grid_map.h:276-300. */
+int b200_map_get_log_odds(b200_map_t* map, const double* pos_xyz, int64_t n, double* out, int32_t on_device);
 /* occupancy_buffer_ (log-odds, double per voxel, address x*Ny*Nz + y*Nz + z) to host memory. */
 int b200_map_download_occupancy(b200_map_t* map, double* dst);
 /* GridMap::publishMap (grid_map.cpp:806-849; which = 0: voxels whose log-odds are not below logit(p_occ), box = local
@@ -173,6 +177,15 @@ int b200_map_download_cost(b200_map_t* map, float* dst);
  * n_samples (optional, may be NULL) = samples the reference loop evaluates. */
 int b200_los_batch(b200_map_t* map, const double* seg_start_xyz, const double* seg_end_xyz, int64_t n,
                    uint8_t* visible, int32_t* n_samples, int32_t on_device);
+
+/* NEW (SURVEY Appendix D "3-D DDA LoS"; not what the reference's planners call): exact voxel-traversal line of sight.
+ * visible[i] = 1 iff both end points are inside the map and no voxel visited by the reference's Amanatides-Woo
+ * RayCaster (src/plan_env/raycast.cpp:253-346; start and end voxel included) between them is occupied in the inflated
+ * grid.  The walk runs on map-relative voxel coordinates (pos - origin) * res_inv.  Its booleans differ from fastLOS on
+ * grazing rays (a sampled march skips corner voxels), so the planners keep fastLOS.  n_cells (optional) = voxels
+ * examined. */
+int b200_los_batch_dda(b200_map_t* map, const double* seg_start_xyz, const double* seg_end_xyz, int64_t n,
+                       uint8_t* visible, int32_t* n_cells, int32_t on_device);
 
 /* Per-stage device times (ms, CUDA events on the map's stream) of the last update_cloud / build_edt when
  * profiling is enabled: [0] clear, [1] scatter, [2] edt z, [3] scan y, [4] band crossovers y,

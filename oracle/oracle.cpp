@@ -356,6 +356,25 @@ struct RayWalk {
     return true;
   }
 };
+// 3-D DDA line of sight (ours): visible iff both end points are inside the map and no voxel the
+// RayCaster walk visits between them (start and end voxel included) is occupied in the inflated grid; the walk runs on
+// map-relative voxel coordinates (pos - origin) * res_inv.
+static bool dda_los(const OMap& m, const V3& s, const V3& e, int* ncells) {
+  *ncells = 0;
+  if (!is_in_map(m, s) || !is_in_map(m, e)) return false;
+  RayWalk rc;
+  rc.set(V3{(s.x - m.origin.x) * m.res_inv, (s.y - m.origin.y) * m.res_inv, (s.z - m.origin.z) * m.res_inv},
+         V3{(e.x - m.origin.x) * m.res_inv, (e.y - m.origin.y) * m.res_inv, (e.z - m.origin.z) * m.res_inv});
+  const int cap = m.N[0] + m.N[1] + m.N[2] + 4;
+  for (;;) {
+    int id[3];
+    const bool more = rc.step(id[0], id[1], id[2]);
+    ++*ncells;
+    if (!is_in_map_idx(m, id) || m.inflate[to_address(m, id[0], id[1], id[2])]) return false;
+    if (!more) return true;
+    if (*ncells > cap) return false;
+  }
+}
 // grid_map.cpp:173-193 setCacheOccupancy (no bounds test in the reference: callers keep `pos` inside the map; here an
 // address outside the buffer is skipped and reported as -1 instead of corrupting memory)
 static int64_t set_cache_occupancy(OMap& m, const V3& pos, int occ, std::vector<int64_t>& queue) {
@@ -1189,6 +1208,26 @@ void orc_map_get_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
 }
 int64_t orc_map_export_occupancy_cloud(void* h, int which, int margin, double truncate_height, float* out, int64_t cap) {
   return export_occupancy_cloud(*(OMap*)h, which, margin, truncate_height, out, cap);
+}
+void orc_los_batch_dda(void* h, const double* s, const double* e, int64_t n, uint8_t* vis, int32_t* ncells) {
+  const OMap& m = *(OMap*)h;
+  for (int64_t i = 0; i < n; ++i) {
+    int nc = 0;
+    vis[i] = dda_los(m, V3{s[3 * i], s[3 * i + 1], s[3 * i + 2]}, V3{e[3 * i], e[3 * i + 1], e[3 * i + 2]}, &nc) ? 1 : 0;
+    if (ncells) ncells[i] = nc;
+  }
+}
+// the voxel sequence of one walk (lattice coordinates in, integer cells out), for pinning against the reference's RayCaster
+int64_t orc_ray_cells(const double a[3], const double b[3], int32_t* out, int64_t cap) {
+  RayWalk rc;
+  rc.set(V3{a[0], a[1], a[2]}, V3{b[0], b[1], b[2]});
+  int64_t n = 0;
+  int x, y, z;
+  while (n < 1000000 && rc.step(x, y, z)) {
+    if (n < cap) { out[3 * n] = x; out[3 * n + 1] = y; out[3 * n + 2] = z; }
+    ++n;
+  }
+  return n;
 }
 void orc_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t* out) {
   OMap* m = (OMap*)h;

@@ -107,6 +107,9 @@ def lib():
         L.orc_map_get_occupancy.argtypes = [vp, vp, i64, vp]
         L.orc_map_export_occupancy_cloud.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, i64]
         L.orc_map_export_occupancy_cloud.restype = i64
+        L.orc_los_batch_dda.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.orc_ray_cells.argtypes = [dp, dp, vp, i64]
+        L.orc_ray_cells.restype = i64
         _LIB = L
     return _LIB
 
@@ -236,6 +239,14 @@ class OracleMap:
         lib().orc_los_batch(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(ns), nthreads)
         return (vis, ns) if return_samples else vis
 
+    def los_batch_dda(self, starts, ends, return_cells=False):
+        s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        e = np.ascontiguousarray(ends, dtype=np.float64).reshape(-1, 3)
+        vis = np.empty(len(s), dtype=np.uint8)
+        nc = np.empty(len(s), dtype=np.int32)
+        lib().orc_los_batch_dda(self.h, _ptr(s), _ptr(e), len(s), _ptr(vis), _ptr(nc))
+        return (vis, nc) if return_cells else vis
+
     def edt_brute(self):
         out = np.empty(self.dims, dtype=np.int32)
         lib().orc_edt_brute(self.h, _ptr(out))
@@ -248,6 +259,13 @@ class OracleMap:
         lib().orc_map_build_edt(self.h, d_safe, _ptr(d2), _ptr(cq) if cq is not None else None,
                                 _ptr(cf) if cf is not None else None, nthreads)
         return (d2, cq, cf) if want_cost else (d2, cq)
+
+
+def ray_cells(a, b, cap=4096):
+    """Voxel sequence of the RayCaster restatement between two lattice points (raycast.cpp:253-346)."""
+    out = np.empty((cap, 3), dtype=np.int32)
+    n = lib().orc_ray_cells(_d3(a), _d3(b), _ptr(out), cap)
+    return out[: min(n, cap)].copy()
 
 
 def los_dk(n):

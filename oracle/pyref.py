@@ -54,6 +54,8 @@ def lib():
         L.ref_map_get_occupancy.argtypes = [vp, vp, i64, vp]
         L.ref_map_publish_occupancy.argtypes = [vp, C.c_int, vp, i64]
         L.ref_map_publish_occupancy.restype = i64
+        L.ref_ray_cells.argtypes = [dp, dp, vp, i64]
+        L.ref_ray_cells.restype = i64
         L.ref_planner_create.restype = vp
         L.ref_planner_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, vp]
         L.ref_planner_destroy.argtypes = [vp]
@@ -62,6 +64,13 @@ def lib():
         L.ref_planner_find_path.argtypes = [vp, dp, dp, C.POINTER(Result), vp, i64]
         _LIB = L
     return _LIB
+
+
+def ray_cells(a, b, cap=4096):
+    """Cells the reference's own RayCaster::step returns between two lattice points (raycast.cpp:253-346)."""
+    out = np.empty((cap, 3), dtype=np.int32)
+    n = lib().ref_ray_cells(_d3(a), _d3(b), _ptr(out), cap)
+    return out[: min(n, cap)].copy()
 
 
 class RefMap:

@@ -135,6 +135,18 @@ int64_t ref_map_publish_inflate(void* h, int all_info, float* out, int64_t cap) 
   std::memcpy(out, shim::last_cloud_blob().data(), (size_t)std::min<int64_t>(n, cap) * 16);
   return n;
 }
+// the reference's own RayCaster (raycast.cpp:253-346): cells returned by step() until it reports the end
+int64_t ref_ray_cells(const double a[3], const double b[3], int32_t* out, int64_t cap) {
+  RayCaster rc;
+  rc.setInput(Eigen::Vector3d(a[0], a[1], a[2]), Eigen::Vector3d(b[0], b[1], b[2]));
+  Eigen::Vector3d p;
+  int64_t n = 0;
+  while (n < 1000000 && rc.step(p)) {
+    if (n < cap) { out[3 * n] = (int32_t)p(0); out[3 * n + 1] = (int32_t)p(1); out[3 * n + 2] = (int32_t)p(2); }
+    ++n;
+  }
+  return n;
+}
 // GridMap::publishMap (grid_map.cpp:806-849, which = 0, one fake subscriber) / publishUnknown (:902-939, which = 1)
 int64_t ref_map_publish_occupancy(void* h, int which, float* out, int64_t cap) {
   GridMap& g = *((RefMap*)h)->gm;

@@ -66,6 +66,10 @@ def test_large_frames_match_the_oracle(b200, po, synth):
     pos = (idx + 0.5) * c["resolution"] + np.array(c["origin"])
     q = np.concatenate([pos, pos + [0.0, 0.0, 50.0], r.uniform(-12, 12, (2000, 3))])
     assert np.array_equal(gm.getOccupancy(q), om.get_occupancy(q))
+    inside = q[gm.isInMap(q)]
+    ii = gm.posToIndex(inside)
+    assert np.array_equal(gm.log_odds(inside), occ[ii[:, 0], ii[:, 1], ii[:, 2]])
+    assert gm.isUnknown(inside).sum() > 0 and (~gm.isUnknown(inside)).sum() > 0
     # publishMap / publishUnknown blobs (grid_map.cpp:806-849, :902-939)
     pm, pu = gm.publishMap(), gm.publishUnknown()
     assert len(pm) > 500 and len(pu) > 1000

@@ -47,3 +47,23 @@ def test_dk_sequence_is_not_k_times_step(po):
     dk = po.los_dk(1200)
     assert dk[0] == 0.0 and dk[1] == 0.05
     assert (dk != np.arange(1200) * 0.05).sum() > 1000   # repeated addition drifts
+
+
+def test_dda_line_of_sight_matches_oracle(b200, po, synth):
+    """b200_los_batch_dda against the oracle's RayCaster restatement: booleans and voxel counts."""
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    r = np.random.default_rng(11)
+    o, s = np.array(c["origin"]), np.array(c["size"])
+    a = o - 0.2 + r.random((20000, 3)) * (s + 0.4)
+    b = a + r.normal(0, 2.0, a.shape)
+    b[:2000] = a[:2000]                                  # degenerate
+    b[2000:4000, 1:] = a[2000:4000, 1:]                  # axis-aligned
+    a[4000:6000] = np.round(a[4000:6000] / 0.1) * 0.1    # on voxel boundaries
+    vg, ng = gm.los_batch_dda(a, b, return_cells=True)
+    vo, no = om.los_batch_dda(a, b, return_cells=True)
+    assert np.array_equal(vg, vo) and np.array_equal(ng, no)
+    assert 0.05 < vg.mean() < 0.95
+    # fastLOS and the traversal agree on most segments, not all (a sampled march can step over a corner voxel)
+    vf = gm.los_batch(a, b)
+    agree = (vf == vg).mean()
+    assert agree > 0.9, agree

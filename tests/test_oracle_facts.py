@@ -136,3 +136,23 @@ def test_cost_planners_prefer_clearance(po, synth):
         r1, p1 = po.OraclePlanner("cost" + base, m, 0.1, 5.0, 200000, cost_weight=5.0).find_path(s, g)
         assert r0["solved"] and r1["solved"]
         assert r1["g_final"] > r0["g_final"]                # cost term adds to g
+
+
+def test_dda_line_of_sight_facts(po, synth):
+    """The voxel-traversal LoS: never more permissive than 'every voxel on the exact path is free',
+    blocked by a one-voxel wall a coarse sampled march could straddle, and symmetric in nothing it should not be."""
+    om = po.OracleMap((-3.2, -3.2, -0.01), (6.4, 6.4, 3.2), 0.1, obstacles_inflation=0.0, local_update_range=(1e3, 1e3, 1e3))
+    grid = np.zeros(om.dims, dtype=np.uint8)
+    grid[40, :, :] = 1   # a one-voxel-thick wall at x index 40
+    grid[40, 30, 10] = 0  # with a single-voxel hole
+    om.set_inflate(grid)
+    c = lambda i, j, k: ((i + 0.5) * 0.1 - 3.2, (j + 0.5) * 0.1 - 3.2, (k + 0.5) * 0.1 - 0.01)
+    vis, cells = om.los_batch_dda([c(20, 30, 10), c(20, 31, 10), c(20, 30, 10), c(20, 30, 10), (100.0, 0.0, 1.0)],
+                                  [c(60, 30, 10), c(60, 31, 10), c(30, 50, 20), c(20, 30, 10), c(20, 30, 10)], return_cells=True)
+    assert vis.tolist() == [1, 0, 1, 1, 0]
+    assert cells[0] == 41 and cells[3] == 1 and cells[4] == 0  # straight along x: 41 voxels; same voxel: 1; outside: none
+    # a voxel on the path blocks, whichever end it is at
+    grid[20, 30, 10] = 1
+    om.set_inflate(grid)
+    assert om.los_batch_dda([c(20, 30, 10)], [c(30, 30, 10)]).tolist() == [0]
+    assert om.los_batch_dda([c(30, 30, 10)], [c(20, 30, 10)]).tolist() == [0]

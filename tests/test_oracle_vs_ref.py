@@ -61,3 +61,23 @@ def test_map_publisher_matches_reference(po, synth):
             mine, n = om.export_inflate_cloud(1 if all_info else 0, 2.4)
             assert n == len(ref) and n > 1000
             assert np.array_equal(ref.view(np.uint32), mine.view(np.uint32))
+
+
+def test_voxel_traversal_matches_the_reference_raycaster(po):
+    """The RayCaster restatement (used by depth fusion and by the DDA line of sight) against the reference's own
+    RayCaster::setInput/step (raycast.cpp:253-346): identical cell sequences, including axis-aligned, degenerate and
+    negative-coordinate rays."""
+    pr = pytest.importorskip("oracle.pyref")
+    if not pr.available():
+        pytest.skip("reference sources not present")
+    r = np.random.default_rng(3)
+    a = r.uniform(-40, 40, (400, 3))
+    b = r.uniform(-40, 40, (400, 3))
+    a[:40, 0] = b[:40, 0]                    # no motion along x
+    a[40:60, 1:] = b[40:60, 1:]              # axis-aligned
+    a[60:70] = b[60:70]                      # same point
+    a[70:100] = np.floor(a[70:100])          # starts exactly on lattice planes
+    b[100:130] = np.floor(b[100:130]) + 0.5  # ends at cell centres
+    for i in range(len(a)):
+        got, want = po.ray_cells(a[i], b[i]), pr.ray_cells(a[i], b[i])
+        assert np.array_equal(got, want), (i, a[i], b[i], len(got), len(want))
