@@ -584,9 +584,17 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   if (ctl.n_valid == 0) {  // every sampled pixel was filtered out: proj_points_cnt == 0, raycastProcess returns at once
     return B200_OK;
   }
+  // a frame that cannot be completed must not leave its end-point counters and ray ids behind
+  auto abandon = [&](int code, const char* what) {
+    const size_t nvox = (size_t)m->N[0] * m->N[1] * m->N[2];
+    cudaMemsetAsync(D.cnt_all, 0, nvox * 8, st);
+    cudaMemsetAsync(D.F, 0xff, nvox * 12, st);  // F, Fnew, E are adjacent
+    cudaStreamSynchronize(st);
+    return fail(code, what);
+  };
+  if (ctl.n_path_total >= 0xffffffffULL) return abandon(B200_ERR_UNSUPPORTED, "depth fusion: more than 2^32 ray steps in one frame");
+  if (m->depth_paths.ensure((size_t)ctl.n_path_total * 4 + 4)) return abandon(B200_ERR_NOMEM, "ray paths");
   m->raycast_num = round;  // :325
-  if (ctl.n_path_total >= 0xffffffffULL) return fail(B200_ERR_UNSUPPORTED, "depth fusion: more than 2^32 ray steps in one frame");
-  if (m->depth_paths.ensure((size_t)ctl.n_path_total * 4 + 4)) return fail(B200_ERR_NOMEM, "ray paths");
   D.paths = (uint32_t*)m->depth_paths.p;
   launch_depth_path_fill(D, m->d, ctl.n_cast_rays, st);
   m->launches++;

@@ -40,9 +40,10 @@ def test_struct_layouts(b200, tmp_path):
     # compile a C (not C++) program against the header: proves it is a plain C header and gives the true layout
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200_planner.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b200_map_params_t), sizeof(b200_planner_params_t),'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200_map_params_t), sizeof(b200_planner_params_t),'
                    'sizeof(b200_path_result_t), offsetof(b200_path_result_t, g_final), offsetof(b200_path_result_t, goal_coords),'
-                   'offsetof(b200_map_params_t, device));return 0;}\n')
+                   'offsetof(b200_map_params_t, device), sizeof(b200_depth_params_t), offsetof(b200_depth_params_t, use_depth_filter));'
+                   'return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
@@ -52,6 +53,10 @@ def test_struct_layouts(b200, tmp_path):
     assert sizes[3] == b200.RESULT_DTYPE.fields["g_final"][1]
     assert sizes[4] == b200.RESULT_DTYPE.fields["goal_coords"][1]
     assert sizes[5] == b200.MapParams.device.offset
+    assert sizes[6] == C.sizeof(b200.DepthParams) == 128
+    assert sizes[7] == b200.DepthParams.use_depth_filter.offset == 112
+    from oracle import pyoracle as po  # the oracle mirrors the same struct (test infrastructure talking to test infrastructure)
+    assert C.sizeof(po.DepthParams) == 128 and [f[0] for f in po.DepthParams._fields_] == [f[0] for f in b200.DepthParams._fields_]
     hdr = open(HEADER).read()
     for field in ("solved", "status", "n_path", "path_offset", "g_final", "path_length", "explored_nodes", "iter_num",
                   "los_checks", "los_samples", "goal_coords", "start_coords", "time_us"):
