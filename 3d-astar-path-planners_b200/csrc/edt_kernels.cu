@@ -341,7 +341,10 @@ __global__ void __launch_bounds__(128) edt_cross_kernel(const uint2* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // fill
 // ---------------------------------------------------------------------------------------------------
-constexpr int SPT = 8;
+// sites per fill thread.  The binary search for a thread's first site is what loads L2 (its probes hit a different
+// 32-byte sector per lane), so more sites per search help until too few threads are left: with the kernels capped at
+// 32 registers, 8 / 12 / 16 sites give fill_y 108 / 101 / 108 us and fill_x 121 / 115 / 114 us at C2.
+constexpr int SPT = 12;
 template <class Emit>
 __device__ __forceinline__ void envelope_fill(const LineBands& L, int u0, const Emit& emit) {
   if (u0 >= L.n) return;
@@ -363,7 +366,7 @@ __device__ __forceinline__ void envelope_fill(const LineBands& L, int u0, const 
         tnext = L.n;
         if (k < q) { en = __ldg(ep + L.stride); tnext = (int)(en.x >> 16); }
       }
-      while (u >= tnext) {  // t is strictly increasing: at most one step per site on average
+      if (u >= tnext) {  // t is strictly increasing and sites are consecutive integers: at most one new entry per site
         ++k;
         ep += L.stride;
         e = en;
@@ -387,7 +390,7 @@ __device__ __forceinline__ LineBands load_bands(const uint2* st_line, size_t str
   return L;
 }
 
-__global__ void __launch_bounds__(128) edt_fill_y_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts,
+__global__ void __launch_bounds__(128, 16) edt_fill_y_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts,
                                                          const int4* __restrict__ cross, int nb, int32_t* __restrict__ out) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (l >= (long long)m.Nx * m.Nz) return;
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(128) edt_fill_y_kernel(MapDev m, const uint2* 
   envelope_fill(L, u0, [&](int j, int32_t v) { o[(size_t)j * stride] = v; });
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 16)  // 32 registers: the fills are latency-bound and want all 64 warps (36 registers cost 12 %)
 edt_fill_x_kernel(MapDev m, const uint2* __restrict__ st, const int* __restrict__ counts, const int4* __restrict__ cross, int nb,
                   int32_t* __restrict__ out, uint16_t* __restrict__ costq, const uint16_t* __restrict__ lut, int lut_n) {
   const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
