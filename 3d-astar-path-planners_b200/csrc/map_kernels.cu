@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(256) clear_box_kernel(MapDev m, int ax, int ay
 // space (pt + k*res, then floor — grid_map.cpp:765-777), which is not the same as voxelise-then-dilate
 // for lattice-aligned points.  The three z cells of a column almost always share a
 // 32-bit word, so a column costs one OR.  A word that already holds the bits is skipped after a plain
-// load; the remaining ORs are warp-aggregated (__match_any_sync on the word address, __reduce_or_sync on
-// the masks, one atomicOr per distinct word per warp).
+// load; the remaining ORs go through or_aggregated below (one atomicOr for the whole warp when every voting
+// lane targets the same word, otherwise one per lane).
 // bounds[0..2] = running min, bounds[3..5] = running max of every generated position (:769-775), kept
 // as order-preserving int64 keys so atomicMin/atomicMax apply.
 // ---------------------------------------------------------------------------------------------------
