@@ -114,6 +114,7 @@ ABI = [
     ("b200_planner_detect_collision", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i32)]),
     ("b200_planner_find_path", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _i64]),
     ("b200_planner_find_paths", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32]),
+    ("b200_planner_get_visited_nodes", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     ("b200_planner_last_launches", C.c_int, [_vp, C.POINTER(_i32)]),
     ("b200_last_error", C.c_char_p, []),
     ("b200_version", C.c_char_p, []),
@@ -488,6 +489,15 @@ class Planner:
 
     def getPath(self):
         return self._path
+
+    def getVisitedNodes(self):
+        """getVisitedNodes (AlgorithmBase.cpp:185-189) of the last findPath: (n,3) positions in creation order."""
+        n = C.c_int64(0)
+        _ck(lib().b200_planner_get_visited_nodes(self.h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), dtype=np.float64)
+        if n.value:
+            _ck(lib().b200_planner_get_visited_nodes(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def findPaths(self, starts, goals, path_cap=None, results=None, path_buf=None):
         """nq independent reset()+findPath() pairs. Host numpy in/out, or CUDA tensors for all of

@@ -931,6 +931,8 @@ struct b200_planner {
   Tier tier[2];
   DevBuf q_in, q_res, q_path, q_order, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
   int last_launches;
+  const NodeRec* last_nodes;   // node records of the last single query (slot 0 of the tier that ran it), else nullptr
+  int64_t last_used;           // use_node_num_ of that query
 };
 
 static void tier_free(Tier& t) {
@@ -1039,6 +1041,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   REQUIRE(nq < (1LL << 31), "too many queries in one call");
   if (!pl->map) return fail(B200_ERR_NO_MAP, "planner has no map");
   pl->last_launches = 0;
+  pl->last_nodes = nullptr;
   if (nq == 0) return B200_OK;
   b200_map* m = pl->map;
   const bool cost_algo = pl->algo == ALGO_COSTASTAR || pl->algo == ALGO_COSTLAZYTHETASTAR;
@@ -1158,6 +1161,21 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   return B200_OK;
 }
 
+int b200_planner_get_visited_nodes(b200_planner_t* pl, double* xyz, int64_t cap, int64_t* n_out) {
+  REQUIRE(pl && n_out && cap >= 0 && (cap == 0 || xyz), "bad argument");
+  if (!pl->last_nodes) return fail(B200_ERR_INVALID, "b200_planner_get_visited_nodes: the last call was not a single-query b200_planner_find_path");
+  // AlgorithmBase.cpp:185-189: path_node_pool_[0 .. use_node_num_ - 1), i.e. every created node but the last, in creation order
+  const int64_t n = std::max<int64_t>(pl->last_used - 1, 0);
+  *n_out = n;
+  const int64_t take = std::min(n, cap);
+  if (take > 0) {
+    CK(cudaSetDevice(pl->map->prm.device));
+    CK(cudaMemcpy2DAsync(xyz, 24, pl->last_nodes, sizeof(NodeRec), 24, (size_t)take, cudaMemcpyDeviceToHost, pl->map->stream));
+    CK(cudaStreamSynchronize(pl->map->stream));
+  }
+  return B200_OK;
+}
+
 int b200_planner_find_path(b200_planner_t* pl, const double start[3], const double goal[3], b200_path_result_t* result,
                            double* path_xyz, int64_t path_cap) {
   REQUIRE(pl && start && goal && result, "NULL argument");
@@ -1171,6 +1189,10 @@ int b200_planner_find_path(b200_planner_t* pl, const double start[3], const doub
     memcpy(path_xyz, tmp.data(), (size_t)std::min<int64_t>(path_cap, result->n_path) * 24);
   }
   if (result->path_offset > 0) result->path_offset = 0;
+  // slot 0 of the tier that produced the result still holds the node records (positions first, creation order)
+  const Tier& t = (pl->last_launches >= 2 && pl->tier[1].base) ? pl->tier[1] : pl->tier[0];
+  pl->last_nodes = t.nodes;
+  pl->last_used = result->explored_nodes;
   return B200_OK;
 }
 

@@ -93,6 +93,16 @@ class AlgorithmBase {
   }
   virtual PathData findPath(Vec3d source, Vec3d target, Vec3d, Vec3d, Vec3d) { return findPath(source, target); }
   std::vector<Vec3d> getPath() { return path_; }
+  // AlgorithmBase.cpp:185-189: the reference hands out Node0 pointers; positions are what its callers could read from them
+  std::vector<Vec3d> getVisitedNodes() {
+    int64_t n = 0;
+    b200_check(b200_planner_get_visited_nodes(h_, nullptr, 0, &n), "getVisitedNodes");
+    std::vector<double> flat((size_t)n * 3);
+    if (n) b200_check(b200_planner_get_visited_nodes(h_, flat.data(), n, &n), "getVisitedNodes");
+    std::vector<Vec3d> out((size_t)n);
+    for (int64_t i = 0; i < n; ++i) out[(size_t)i] = Vec3d(flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]);
+    return out;
+  }
 
   // batched form (new): nq independent reset()+findPath() pairs, one thread block each
   void findPaths(const std::vector<Vec3d>& sources, const std::vector<Vec3d>& targets, std::vector<b200_path_result_t>& results,

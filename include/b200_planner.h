@@ -262,6 +262,11 @@ int b200_planner_find_path(b200_planner_t* planner, const double start[3], const
  * gets path_offset = -1.  Pointers are host pointers unless on_device != 0. */
 int b200_planner_find_paths(b200_planner_t* planner, const double* starts_xyz, const double* goals_xyz, int64_t nq,
                             b200_path_result_t* results, double* path_xyz, int64_t path_cap, int32_t on_device);
+/* AlgorithmBase::getVisitedNodes (AlgorithmBase.cpp:185-189) for the last b200_planner_find_path: the positions of the
+ * nodes created by that query, in creation order, all but the last one (the reference returns
+ * path_node_pool_[0 .. use_node_num_ - 1)).  *n_out = their number (may exceed cap; only cap are written).
+ * B200_ERR_INVALID after a batched call. */
+int b200_planner_get_visited_nodes(b200_planner_t* planner, double* xyz, int64_t cap, int64_t* n_out);
 /* Kernel launches issued by the last find_paths call (for bench accounting). */
 int b200_planner_last_launches(b200_planner_t* planner, int32_t* n_launches);
 

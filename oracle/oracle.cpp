@@ -1301,6 +1301,15 @@ int orc_planner_find_path(void* ph, const double s[3], const double g[3], Result
   for (int64_t i = 0; i < n; ++i) { path[3 * i] = out[i].x; path[3 * i + 1] = out[i].y; path[3 * i + 2] = out[i].z; }
   return 0;
 }
+// AlgorithmBase.cpp:185-189 getVisitedNodes of the last find_path: pool[0 .. use_node_num - 1)
+int64_t orc_planner_visited(void* ph, double* out, int64_t cap) {
+  Planner* p = (Planner*)ph;
+  const int64_t n = std::max(p->use_node_num - 1, 0);
+  for (int64_t i = 0; i < std::min(n, cap); ++i) {
+    out[3 * i] = p->pool[i].position.x; out[3 * i + 1] = p->pool[i].position.y; out[3 * i + 2] = p->pool[i].position.z;
+  }
+  return n;
+}
 // batched: queries are independent; one private planner per thread (reference is single-threaded;
 // this is the "ref-NT" baseline of BASELINE.md §3).  Paths go to path[qi*path_stride ...].
 int orc_planner_find_paths(int algo, int mode, double resolution, double lambda_heuristic, int allocate_num,

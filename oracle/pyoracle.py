@@ -96,6 +96,8 @@ def lib():
         L.orc_planner_find_paths.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp,
                                              vp, vp, vp, i64, vp, vp, i64, C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_planner_visited.argtypes = [vp, vp, i64]
+        L.orc_planner_visited.restype = i64
         L.orc_map_set_depth_params.argtypes = [vp, vp]
         L.orc_map_update_depth.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp]
         L.orc_map_update_depth.restype = C.c_int
@@ -297,6 +299,13 @@ class OraclePlanner:
         lib().orc_planner_find_path(self.h, _d3(start), _d3(goal), C.byref(r), _ptr(path), path_cap)
         res = np.frombuffer(bytes(r), dtype=RESULT_DTYPE)[0]
         return res, path[: min(r.n_path, path_cap)].copy()
+
+    def visited(self):
+        """getVisitedNodes of the last find_path: (n,3) positions in creation order."""
+        n = lib().orc_planner_visited(self.h, None, 0)
+        out = np.empty((n, 3), dtype=np.float64)
+        lib().orc_planner_visited(self.h, _ptr(out), n)
+        return out
 
     def find_paths(self, starts, goals, path_stride=0, nthreads=1):
         s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)

@@ -62,6 +62,8 @@ def lib():
         L.ref_planner_pool_disorder.argtypes = [vp]
         L.ref_planner_pool_disorder.restype = C.c_int
         L.ref_planner_find_path.argtypes = [vp, dp, dp, C.POINTER(Result), vp, i64]
+        L.ref_planner_visited.argtypes = [vp, vp, i64]
+        L.ref_planner_visited.restype = i64
         _LIB = L
     return _LIB
 
@@ -215,6 +217,13 @@ class RefPlanner:
         lib().ref_planner_find_path(self.h, _d3(start), _d3(goal), C.byref(r), _ptr(path), path_cap)
         res = np.frombuffer(bytes(r), dtype=RESULT_DTYPE)[0]
         return res, path[: min(r.n_path, path_cap)].copy()
+
+    def visited(self):
+        """AlgorithmBase::getVisitedNodes() after the last find_path: (n,3) positions."""
+        n = lib().ref_planner_visited(self.h, None, 0)
+        out = np.empty((n, 3), dtype=np.float64)
+        lib().ref_planner_visited(self.h, _ptr(out), n)
+        return out
 
     def find_paths(self, starts, goals, path_cap=65536):
         res = np.zeros(len(starts), dtype=RESULT_DTYPE)

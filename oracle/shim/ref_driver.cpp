@@ -309,4 +309,15 @@ int ref_planner_find_path(void* h, const double s[3], const double g[3], Result*
   return 0;
 }
 
+// AlgorithmBase::getVisitedNodes (AlgorithmBase.cpp:185-189) after the last findPath
+int64_t ref_planner_visited(void* h, double* out, int64_t cap) {
+  RefPlanner* p = (RefPlanner*)h;
+  const auto v = p->algo->getVisitedNodes();
+  const int64_t n = (int64_t)v.size();
+  for (int64_t i = 0; i < std::min(n, cap); ++i) {
+    out[3 * i] = v[i]->position(0); out[3 * i + 1] = v[i]->position(1); out[3 * i + 2] = v[i]->position(2);
+  }
+  return n;
+}
+
 }  // extern "C"

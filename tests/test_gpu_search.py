@@ -184,3 +184,22 @@ def test_air_ground_planners_match_oracle(b200, po, world, algo, semantics):
     assert ro["solved"].sum() > 40
     assert_results_equal(rg, ro)
     _assert_paths_equal(b200, rg, pg, ro, pth)
+
+
+@pytest.mark.parametrize("algo,mode", [("astar", "faithful"), ("thetastar", "faithful"), ("lazythetastar", "canonical")])
+def test_visited_nodes_match_oracle(b200, po, synth, algo, mode):
+    """getVisitedNodes (AlgorithmBase.cpp:185-189) after a single findPath: same nodes in the same creation order."""
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    s, g = synth.random_queries(9, om.get_inflate_occupancy, c["origin"], c["size"], 3, min_dist=6.0)
+    pl = b200.Planner(algo, resolution=c["resolution"], lambda_heuristic=5.0, allocate_num=200000, semantics=mode)
+    pl.setGridMap(gm)
+    op = po.OraclePlanner(algo, om, c["resolution"], 5.0, 200000, mode=po.FAITHFUL if mode == "faithful" else po.CANONICAL)
+    for i in range(len(s)):
+        r = pl.findPath(s[i], g[i])
+        o, _ = op.find_path(s[i], g[i])
+        vg, vo = pl.getVisitedNodes(), op.visited()
+        assert r["explored_nodes"] == int(o["explored_nodes"]) and len(vg) == r["explored_nodes"] - 1
+        assert np.array_equal(vg, vo)
+    pl.findPaths(s, g)
+    with pytest.raises(b200.B200Error):
+        pl.getVisitedNodes()  # only defined after a single-query call

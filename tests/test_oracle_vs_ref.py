@@ -31,6 +31,12 @@ def test_map_los_and_planners_match_reference(po, synth, seed, size, res, infl):
             assert np.array_equal(rr[f], ro[f]), (algo, f)
         for i in range(len(s)):
             assert np.array_equal(pth[i * 8192: i * 8192 + ro["n_path"][i]], rpaths[i]), (algo, i)
+        # getVisitedNodes (AlgorithmBase.cpp:185-189): every created node but the last, in pool order
+        rp, op = pr.RefPlanner(algo, rm, res, 5.0, 100000), po.OraclePlanner(algo, om, res, 5.0, 100000, mode=po.FAITHFUL)
+        r1, _ = rp.find_path(s[0], g[0])
+        o1, _ = op.find_path(s[0], g[0])
+        vr, vo = rp.visited(), op.visited()
+        assert len(vr) == int(r1["explored_nodes"]) - 1 and np.array_equal(vr, vo)
 
 
 def test_clear_box_matches_reference(po, synth):
