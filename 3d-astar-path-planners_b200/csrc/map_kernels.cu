@@ -106,6 +106,8 @@ scatter_kernel(MapDev m, const uint8_t* __restrict__ pts, long long n, int step,
     }
   }
   const int side = 2 * s + 1;
+  // the three z cells straddle a word boundary for 2 points in 32: the second word's pass runs only for warps that need it
+  const int nslots = __any_sync(0xffffffffu, zw[1] >= 0) ? 2 : 1;
 #pragma unroll
   for (int a = 0; a < SIDE; ++a) {
     if (a >= side) break;  // warp-uniform
@@ -121,6 +123,7 @@ scatter_kernel(MapDev m, const uint8_t* __restrict__ pts, long long n, int step,
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
+        if (q >= nslots) break;  // warp-uniform
         bool need = false;
         uint32_t* addr = m.occ;
         if (in && zw[q] >= 0) {
