@@ -134,28 +134,29 @@ scatter_kernel(MapDev m, const uint8_t* __restrict__ pts, long long n, int step,
       }
     }
   }
-  // running min/max of the generated positions; monotone rounding => extremes are at k = -s / +s (z: -1 / +1)
-  double mn[3], mx[3];
-  if (accept) {
-    mn[0] = dadd((double)fx, dmul((double)(-s), m.res)); mx[0] = dadd((double)fx, dmul((double)s, m.res));
-    mn[1] = dadd((double)fy, dmul((double)(-s), m.res)); mx[1] = dadd((double)fy, dmul((double)s, m.res));
-    mn[2] = dadd((double)fz, dmul(-1.0, m.res));         mx[2] = dadd((double)fz, dmul(1.0, m.res));
-  }
+  // running min/max of the generated positions; monotone rounding => extremes are at k = -s / +s (z: -1 / +1) of the
+  // extreme coordinates, so the warp reduces the float coordinates themselves (one redux.sync per key on
+  // order-preserving uint32 images) and only lane 0 forms the FP64 positions
   const unsigned am = __ballot_sync(0xffffffffu, accept);
-  if (am) {
+  const float f3[3] = {fx, fy, fz};
+  float fmin3[3], fmax3[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t b = __float_as_uint(f3[a]);
+    const uint32_t k = (b >> 31) ? ~b : (b | 0x80000000u);
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, accept ? k : 0xffffffffu);
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, accept ? k : 0u);
+    fmin3[a] = __uint_as_float((kmin >> 31) ? (kmin & 0x7fffffffu) : ~kmin);
+    fmax3[a] = __uint_as_float((kmax >> 31) ? (kmax & 0x7fffffffu) : ~kmax);
+  }
+  if (am && (threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      long long lo = accept ? dkey(mn[a]) : 0x7fffffffffffffffLL;
-      long long hi = accept ? dkey(mx[a]) : (long long)0x8000000000000000ULL;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-      }
-      if ((threadIdx.x & 31) == 0) {
-        if (lo < bounds[a]) atomicMin(bounds + a, lo);
-        if (hi > bounds[3 + a]) atomicMax(bounds + 3 + a, hi);
-      }
+      const double k = a == 2 ? 1.0 : (double)s;
+      const long long lo = dkey(dadd((double)fmin3[a], dmul(-k, m.res)));
+      const long long hi = dkey(dadd((double)fmax3[a], dmul(k, m.res)));
+      if (lo < bounds[a]) atomicMin(bounds + a, lo);
+      if (hi > bounds[3 + a]) atomicMax(bounds + 3 + a, hi);
     }
   }
 }
