@@ -53,14 +53,16 @@ __device__ __forceinline__ long long dkey(double v) {
 // slower than it saves on the C2 frame: scatter 82 us with it, 60 us with plain atomics (its cost grows with the
 // number of distinct addresses in the warp, which is the common case).
 __device__ __forceinline__ void or_aggregated(uint32_t* addr, uint32_t mask, bool need) {
+  // every collective runs with the full mask in warp-uniform control flow: sub-warp masks inside divergent code cost a
+  // WARPSYNC / collective bracket per call (96 of them in the first version of this kernel)
   const unsigned todo = __ballot_sync(0xffffffffu, need);
-  if (!need) return;
+  if (todo == 0u) return;
   const int leader = __ffs(todo) - 1;
-  const unsigned long long a0 = __shfl_sync(todo, (unsigned long long)addr, leader);
-  if (__all_sync(todo, (unsigned long long)addr == a0)) {
-    const uint32_t merged = __reduce_or_sync(todo, mask);
+  const unsigned long long a0 = __shfl_sync(0xffffffffu, (unsigned long long)addr, leader);
+  if (__all_sync(0xffffffffu, !need || (unsigned long long)addr == a0)) {
+    const uint32_t merged = __reduce_or_sync(0xffffffffu, need ? mask : 0u);
     if ((int)(threadIdx.x & 31) == leader) atomicOr(addr, merged);
-  } else {
+  } else if (need) {
     atomicOr(addr, mask);
   }
 }
