@@ -506,7 +506,7 @@ def main():
                        "grid": list(gm.dims), "points": int(n_pts), "d_safe_m": D_SAFE, "l2": "flushed (256 MiB write) before every timed frame",
                        "multi_gpu": "map replicated: every rank rebuilds its replica (value = ms/frame / n_gpus); query batches sharded, no collective"},
             "e2e": {"value": e2e_ms / world, "unit": "ms/frame", "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": 48,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "p50_ms_per_step": float(np.median(e2e_t))},
             "gpu_launches": int(args.steps * 9), "kernels_per_step": ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_cross_kernel", "edt_fill_y_kernel", "edt_scan_x_kernel", "edt_cross_kernel", "edt_fill_x_kernel", "(+1 cudaMemsetAsync clear)"],
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
