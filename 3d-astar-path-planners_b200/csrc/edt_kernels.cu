@@ -160,10 +160,12 @@ __device__ __forceinline__ int floor_div_small(int num, int den) {
 template <int PF, class In>
 __device__ __forceinline__ int envelope_scan(In& in, uint2* __restrict__ st, size_t stride, int n, int u_begin, int u_end) {
   int q = 0;
-  int sq = u_begin, tq = 0, sb = 0, tb = 0;  // top entry, entry below it
-  int32_t gq = in.first(), gb = 0;
-  uint2* sp = st;                            // slot of the top entry
-  *sp = make_uint2(pack_st(u_begin, 0), (uint32_t)gq);
+  int sq = u_begin, tq = 0;  // top entry (site, start)
+  int32_t gq0 = in.first();
+  int cq = sq * sq + gq0;    // ... and c = s^2 + g: with it the pop test and the separator share one numerator,
+                             //   f(t; s) > f(t; u)  <=>  c_u - c_s < 2 t (u - s),   sep(s, u) = floor((c_u - c_s) / (2 (u - s)))
+  uint2* sp = st;            // slot of the top entry
+  *sp = make_uint2(pack_st(u_begin, 0), (uint32_t)gq0);
   for (int u0 = u_begin + 1; u0 < u_end; u0 += PF) {
     int32_t gbuf[PF];
 #pragma unroll
@@ -173,32 +175,32 @@ __device__ __forceinline__ int envelope_scan(In& in, uint2* __restrict__ st, siz
       const int u = u0 + j;
       if (u < u_end) {
         const int32_t gu = gbuf[j];
-        while (q >= 0) {
-          const int a = tq - sq, b = tq - u;
-          if (a * a + gq > b * b + gu) {
-            --q;  // pop: the cached entry below becomes the top; refill the cache with one early load
-            sp -= stride;
-            sq = sb; tq = tb; gq = gb;
-            if (q >= 1) {
-              const uint2 e = *(sp - stride);
-              sb = (int)(e.x & 0xffffu);
-              tb = (int)(e.x >> 16);
-              gb = (int32_t)e.y;
-            }
-          } else break;
+        const int cu = u * u + gu;
+        int num = cu - cq, den = 2 * (u - sq);
+        while (q >= 0 && num < tq * den) {
+          // pop: reload the new top (an L1 hit).  Keeping the entry below the top in registers paid while the scan was
+          // latency-bound; now that it is issue-bound the register shuffling costs more than the load (112 -> 107 us)
+          --q;
+          sp -= stride;
+          if (q >= 0) {
+            const uint2 e = *sp;
+            sq = (int)(e.x & 0xffffu);
+            tq = (int)(e.x >> 16);
+            cq = sq * sq + (int32_t)e.y;
+            num = cu - cq; den = 2 * (u - sq);
+          }
         }
         if (q < 0) {
-          q = 0; sq = u; tq = 0; gq = gu;
+          q = 0; sq = u; tq = 0; cq = cu;
           sp = st;
           *sp = make_uint2(pack_st(u, 0), (uint32_t)gu);
         } else {
           // after the loop parabola sq is still no worse than u at tq >= 0, so the numerator is >= 0
-          const int w = 1 + floor_div_small(u * u - sq * sq + gu - gq, 2 * (u - sq));
+          const int w = 1 + floor_div_small(num, den);
           if (w < n) {
             ++q;
             sp += stride;
-            sb = sq; tb = tq; gb = gq;
-            sq = u; tq = w; gq = gu;
+            sq = u; tq = w; cq = cu;
             *sp = make_uint2(pack_st(u, w), (uint32_t)gu);
           }
         }
