@@ -30,7 +30,8 @@ namespace b200 {
 // halo (optional, z-slab sharding): below_gap[c] / above_gap[c] = distance in voxels from the slab's first / last
 // z-plane to the nearest occupied voxel in the slabs below / above (>= 1), or < 0 when there is none.
 template <class T>
-__global__ void __launch_bounds__(256) edt_z_kernel(MapDev m, T* __restrict__ dz, const int32_t* __restrict__ below_gap,
+__global__ void __launch_bounds__(256, 4) edt_z_kernel(  // 64 registers: 28.7 -> 26.9 us; 48 or fewer spill the 32 distances (51+ us)
+MapDev m, T* __restrict__ dz, const int32_t* __restrict__ below_gap,
                                                     const int32_t* __restrict__ above_gap) {
   constexpr int kNone = sizeof(T) == 1 ? 255 : 65535;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (column, word)
