@@ -113,26 +113,34 @@ scatter_kernel(MapDev m, const uint8_t* __restrict__ pts, long long n, int step,
 #pragma unroll
   for (int a = 0; a < SIDE; ++a) {
     if (a >= side) break;  // warp-uniform
+    // a row's words are all requested first (independent loads in flight together), then voted on: with a vote right
+    // after each load a warp waits for SIDE * nslots L2 round trips one after the other
+    uint32_t* addr[SIDE][2];
+    uint32_t cur[SIDE][2];
 #pragma unroll
     for (int b = 0; b < SIDE; ++b) {
-      if (b >= side) break;
       bool in = false;
       size_t col = 0;
-      if (accept) {
+      if (accept && b < side) {
         const int ix = ixs[a], iy = iys[b];
         in = ix >= 0 && ix <= m.Nx - 1 && iy >= 0 && iy <= m.Ny - 1;
         col = ((size_t)ix * m.Ny + iy) * m.wz;
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
+        const bool live = in && q < nslots && zw[q] >= 0;
+        addr[b][q] = live ? m.occ + col + zw[q] : m.occ;
+        cur[b][q] = live ? *addr[b][q] : 0xffffffffu;  // "everything already set" for cells that do not exist
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < SIDE; ++b) {
+      if (b >= side) break;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
         if (q >= nslots) break;  // warp-uniform
-        bool need = false;
-        uint32_t* addr = m.occ;
-        if (in && zw[q] >= 0) {
-          addr = m.occ + col + zw[q];
-          need = (*addr & zmask[q]) != zmask[q];  // already set by an earlier point: nothing to do
-        }
-        or_aggregated(addr, zmask[q], need);
+        // a word that already holds the bits (set by an earlier point) needs nothing
+        or_aggregated(addr[b][q], zmask[q], (cur[b][q] & zmask[q]) != zmask[q]);
       }
     }
   }
