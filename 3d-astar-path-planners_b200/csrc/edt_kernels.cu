@@ -253,35 +253,6 @@ __device__ __forceinline__ int covering_entry(const uint2* __restrict__ st, size
   }
   return lo;
 }
-// same, but starting from one end of the stack and galloping: near a band boundary the covering entry of the left
-// band is at (or just below) its top and that of the right band at (or just above) its bottom
-__device__ __forceinline__ int covering_entry_finger(const uint2* __restrict__ st, size_t stride, int q, int u, bool from_top) {
-  auto T = [&](int k) { return (int)(__ldg(&st[(size_t)k * stride].x) >> 16); };
-  int lo, hi;  // invariant: t_lo <= u, and (hi > q or t_hi > u); answer in [lo, hi)
-  if (from_top) {
-    if (T(q) <= u) return q;
-    hi = q; lo = q - 1;
-    int step = 1;
-    while (lo > 0 && T(lo) > u) { hi = lo; lo -= step; step <<= 1; }
-    if (lo < 0) lo = 0;
-  } else {
-    if (q == 0 || T(1) > u) return 0;
-    lo = 1; hi = 2;
-    int step = 1;
-    while (hi <= q && T(hi) <= u) { lo = hi; hi += step; step <<= 1; }
-    if (hi > q + 1) hi = q + 1;
-  }
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (T(mid) <= u) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-__device__ __forceinline__ long long envelope_at(const uint2* __restrict__ st, size_t stride, int q, int u, bool from_top) {
-  const uint2 e = __ldg(st + (size_t)covering_entry_finger(st, stride, q, u, from_top) * stride);
-  const long long d = u - (int)(e.x & 0xffffu);
-  return d * d + (long long)(int32_t)e.y;
-}
 struct LineBands {  // one line's band stacks + crossovers (nb <= 4)
   const uint2* st;  // slot of site 0 of the line
   size_t stride;
@@ -294,6 +265,60 @@ struct LineBands {  // one line's band stacks + crossovers (nb <= 4)
     return u < cmid ? (u < c01 ? 0 : 1) : (u < c23 ? 2 : 3);
   }
   __device__ __forceinline__ const uint2* band_stack(int b) const { return st + (size_t)b * bl * stride; }
+};
+// A band envelope evaluated at a moving site: the covering entry is remembered, so the next evaluation searches
+// outward from it (no load at all while the site stays inside the entry's interval, a gallop of log(distance) probes
+// otherwise) instead of restarting from an end of the stack.  The crossover search probes sites that move away from
+// the band boundary and then close in on the answer, so the fingers only ever move a little.
+struct Finger {
+  const uint2* st;
+  size_t stride;
+  int q;       // last entry; < 0: the band does not exist
+  int k;       // covering entry of the last evaluation
+  int t, tn;   // its start and the start of the next entry (INT_MAX at the top)
+  int s, g;
+  __device__ __forceinline__ int T(int i) const { return (int)(__ldg(&st[(size_t)i * stride].x) >> 16); }
+  __device__ __forceinline__ void load(int i) {
+    const uint2 e = __ldg(st + (size_t)i * stride);
+    k = i; s = (int)(e.x & 0xffffu); t = (int)(e.x >> 16); g = (int)e.y;
+    tn = i < q ? T(i + 1) : 0x7fffffff;
+  }
+  __device__ __forceinline__ void init(const uint2* stack, size_t str, int last, bool from_top) {
+    st = stack; stride = str; q = last;
+    if (q >= 0) load(from_top ? q : 0);
+  }
+  __device__ __forceinline__ long long at(int u) {
+    if (q < 0) return 1LL << 60;  // a band that does not exist never wins
+    if (u >= tn) {         // covering entry is above k: tn = t_{k+1} <= u
+      int lo = k + 1, hi;  // invariant: t_lo <= u, and (hi > q or t_hi > u)
+      for (int step = 1;; step <<= 1) {
+        hi = lo + step;
+        if (hi > q) { hi = q + 1; break; }
+        if (T(hi) > u) break;
+        lo = hi;
+      }
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (T(mid) <= u) lo = mid; else hi = mid;
+      }
+      load(lo);
+    } else if (u < t) {    // below k: t_k > u
+      int hi = k, lo;
+      for (int step = 1;; step <<= 1) {
+        lo = hi - step;
+        if (lo <= 0) { lo = 0; break; }
+        if (T(lo) <= u) break;
+        hi = lo;
+      }
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (T(mid) <= u) lo = mid; else hi = mid;
+      }
+      load(lo);
+    }
+    const long long d = u - s;
+    return d * d + (long long)g;
+  }
 };
 // first u in [0, n] with F_right(u) < F_left(u) (monotone predicate: false ... false true ... true).
 // The crossover of two neighbouring band envelopes is almost always at (or a few sites from) their common
@@ -330,15 +355,19 @@ __global__ void __launch_bounds__(128) edt_cross_kernel(const uint2* __restrict_
   const size_t base = line_div ? (size_t)(l / line_div) * line_mul + (size_t)(l % line_div) : (size_t)l;
   const int bl = band_len(n, nb);
   const int* q = counts + l * nb;
-  const long long kNever = 1LL << 60;
-  auto E = [&](int b, int u, bool from_top) -> long long {
-    return q[b] < 0 ? kNever : envelope_at(st + base + (size_t)b * bl * stride, stride, q[b], u, from_top);
-  };
-  int c = n;
-  if (nb == 2 || which == 0) c = first_right_wins(n, bl, [&](int u) { return E(0, u, true); }, [&](int u) { return E(1, u, false); });
-  else if (which == 2) c = first_right_wins(n, 3 * bl, [&](int u) { return E(2, u, true); }, [&](int u) { return E(3, u, false); });
-  else c = first_right_wins(n, 2 * bl, [&](int u) { return min(E(0, u, true), E(1, u, true)); },
-                            [&](int u) { return min(E(2, u, false), E(3, u, false)); });
+  // left set = bands [l_lo, l_hi] probed from their tops, right set = [r_lo, r_hi] probed from their bottoms
+  const int l_hi = nb == 2 || which == 0 ? 0 : (which == 2 ? 2 : 1);
+  const int l_lo = (nb == 4 && which == 1) ? 0 : l_hi;
+  const int r_lo = l_hi + 1;
+  const int r_hi = (nb == 4 && which == 1) ? 3 : r_lo;
+  Finger fl0, fl1, fr0, fr1;  // (fl1 / fr1 only exist for the middle crossover)
+  fl0.init(st + base + (size_t)l_hi * bl * stride, stride, __ldg(q + l_hi), true);
+  fr0.init(st + base + (size_t)r_lo * bl * stride, stride, __ldg(q + r_lo), false);
+  const bool two = l_lo != l_hi;
+  fl1.init(st + base + (size_t)l_lo * bl * stride, stride, two ? __ldg(q + l_lo) : -1, true);
+  fr1.init(st + base + (size_t)r_hi * bl * stride, stride, two ? __ldg(q + r_hi) : -1, false);
+  const int b0 = r_lo * bl;
+  const int c = first_right_wins(n, b0, [&](int u) { return min(fl0.at(u), fl1.at(u)); }, [&](int u) { return min(fr0.at(u), fr1.at(u)); });
   cross[l * 4 + which] = c;
 }
 
