@@ -284,7 +284,8 @@ __device__ __forceinline__ AgrCand agrpp_candidate(const SearchParams& P, double
 }
 
 // resident blocks per SM the register allocation is capped for.  Measured (1xB200, C2 world, queries/s): the
-// 32-thread kernels at 28 blocks (<= 72 registers, a few spills) — Lazy Theta* 593k -> 723k, A* 992k -> 983k;
+// 32-thread kernels at 28 blocks (<= 72 registers, a few spills) — Lazy Theta* 593k -> 723k, A* 992k -> 983k; at 32
+// blocks (64 registers) Lazy Theta* gains another 6 % (700k -> 746k) while A* loses 4 %, so only the lazy variants use 32;
 // the 128-thread LoS kernels at 6 blocks (<= 80 registers) — Theta* 79.7k -> 87.5k, 8 blocks no better.
 #ifndef SEARCH_MINB1
 #define SEARCH_MINB1 28
@@ -293,7 +294,9 @@ __device__ __forceinline__ AgrCand agrpp_candidate(const SearchParams& P, double
 #define SEARCH_MINB4 6
 #endif
 template <int ALGO, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 1 ? SEARCH_MINB1 : SEARCH_MINB4) search_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(NW * 32, NW != 1 ? SEARCH_MINB4
+                                           : (ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR) ? 32 : SEARCH_MINB1)
+search_kernel(const SearchParams P) {
   constexpr bool IS_AGR = ALGO == ALGO_THETASTARAGR, IS_AGRPP = ALGO == ALGO_THETASTARAGRPP;
   constexpr bool IS_THETA = ALGO == ALGO_THETASTAR || IS_AGR || IS_AGRPP;  // one fastLOS per generated neighbour
   constexpr bool IS_LAZY = ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR;
