@@ -6,7 +6,8 @@
 //
 // Differences from the reference node are confined to three places, marked  // B200:
 //   1. parameters are copied from the NodeHandle into a ParamMap once (configureAlgorithm)
-//   2. the cloud / odom subscribers live here instead of inside GridMap::initMap
+//   2. the cloud / odom / depth+pose subscribers live here instead of inside GridMap::initMap, and a depth frame is
+//      fused when it arrives instead of from the reference's 20 Hz timer (grid_map.cpp:119, :635-666)
 //   3. GetPath.time_spent is the real device time (the reference's is always 0)
 // Wire format (srv/GetPath.srv, srv/SetAlgorithm.srv), topic names and the request flow are unchanged.
 #if defined(B200_WITH_ROS) && defined(B200_WITH_EIGEN)
@@ -14,6 +15,13 @@
 #include <sensor_msgs/PointCloud2.h>
 #include <nav_msgs/Odometry.h>
 #include <nav_msgs/Path.h>
+#include <sensor_msgs/Image.h>
+#include <sensor_msgs/image_encodings.h>
+#include <geometry_msgs/PoseStamped.h>
+#include <cv_bridge/cv_bridge.h>
+#include <message_filters/subscriber.h>
+#include <message_filters/synchronizer.h>
+#include <message_filters/sync_policies/approximate_time.h>
 #include <heuristic_planners/GetPath.h>
 #include <heuristic_planners/SetAlgorithm.h>
 
@@ -34,11 +42,20 @@ class HeuristicPlannerROS {
     // B200 (2): GridMap::initMap's own subscriptions (grid_map.cpp:116-117)
     cloud_sub_ = lnh_.subscribe<sensor_msgs::PointCloud2>("/grid_map/cloud", 10, &HeuristicPlannerROS::cloudCallback, this);
     odom_sub_ = lnh_.subscribe<nav_msgs::Odometry>("/grid_map/odom", 10, &HeuristicPlannerROS::odomCallback, this);
+    // depth image + camera pose, synchronised like grid_map.cpp:96-105 (pose_type POSE_STAMPED)
+    depth_sub_.reset(new message_filters::Subscriber<sensor_msgs::Image>(lnh_, "/grid_map/depth", 50));
+    pose_sub_.reset(new message_filters::Subscriber<geometry_msgs::PoseStamped>(lnh_, "/grid_map/pose", 25));
+    sync_image_pose_.reset(new message_filters::Synchronizer<SyncPolicyImagePose>(SyncPolicyImagePose(100), *depth_sub_, *pose_sub_));
+    sync_image_pose_->registerCallback(boost::bind(&HeuristicPlannerROS::depthPoseCallback, this, _1, _2));
   }
 
  private:
   void cloudCallback(const sensor_msgs::PointCloud2ConstPtr& msg) { grid_map_->cloudCallback(msg); }
   void odomCallback(const nav_msgs::OdometryConstPtr& msg) { grid_map_->odomCallback(msg); }
+  // depthPoseCallback + updateOccupancyCallback of the reference in one step (b200host::GridMap::depthPoseCallback)
+  void depthPoseCallback(const sensor_msgs::ImageConstPtr& img, const geometry_msgs::PoseStampedConstPtr& pose) {
+    grid_map_->depthPoseCallback(img, pose);
+  }
 
   bool setAlgorithm(heuristic_planners::SetAlgorithmRequest& req, heuristic_planners::SetAlgorithmResponse& rep) {
     configureAlgorithm(req.algorithm.data, req.heuristic.data);
@@ -128,6 +145,10 @@ class HeuristicPlannerROS {
   ros::NodeHandle lnh_{"~"};
   ros::ServiceServer request_path_server_, change_planner_server_;
   ros::Subscriber cloud_sub_, odom_sub_;
+  typedef message_filters::sync_policies::ApproximateTime<sensor_msgs::Image, geometry_msgs::PoseStamped> SyncPolicyImagePose;  // grid_map.h:228
+  std::shared_ptr<message_filters::Subscriber<sensor_msgs::Image>> depth_sub_;
+  std::shared_ptr<message_filters::Subscriber<geometry_msgs::PoseStamped>> pose_sub_;
+  std::shared_ptr<message_filters::Synchronizer<SyncPolicyImagePose>> sync_image_pose_;
   ros::Publisher global_path_pub_;
   std::unique_ptr<Planners::AlgorithmBase> algorithm_;
   GridMap::Ptr grid_map_;
