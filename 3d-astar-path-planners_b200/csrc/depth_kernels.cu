@@ -200,7 +200,19 @@ __global__ void __launch_bounds__(128) depth_path_count_kernel(DepthDev D, MapDe
   ray_setup(D, m, id, w);
   int ix, iy, iz;
   unsigned steps = 0;
-  while (steps < (unsigned)D.max_steps && w.step(ix, iy, iz)) ++steps;
+  // Lattice cells map to voxels monotonically along every axis, so a ray can only meet one of its OWN voxels again as
+  // an immediate repeat (two consecutive cells in one voxel — possible when origin / resolution has fractional part
+  // 1/2).  The reference then stops the ray at its own flag (:410): the cached path ends with that repeated voxel.
+  long long prev = -1;
+  while (steps < (unsigned)D.max_steps && w.step(ix, iy, iz)) {
+    ++steps;
+    const long long a = pos_address(m, dmul(dadd((double)ix, 0.5), m.res), dmul(dadd((double)iy, 0.5), m.res),
+                                    dmul(dadd((double)iz, 0.5), m.res));
+    if (a >= 0) {
+      if (a == prev) break;
+      prev = a;
+    }
+  }
   const unsigned slot = atomicAdd(&D.ctl->n_cast_rays, 1u);
   D.cast_id[slot] = (uint32_t)id;
   D.path_len[slot] = steps;

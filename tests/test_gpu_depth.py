@@ -115,3 +115,27 @@ def test_depth_errors(b200, golden):
     gm.depthPoseCallback(odd, sc["pos"][0], sc["rot"][0])  # arms the filter
     with pytest.raises(b200.B200Error):
         gm.depthPoseCallback(odd, sc["pos"][0], sc["rot"][0])  # the reference would read past the image end here
+
+
+def test_half_voxel_origin_matches_the_oracle(b200, po, synth):
+    """A map whose origin / resolution has fractional part 1/2 (size 12.9 m at 0.1 m): consecutive lattice cells of a ray
+    can then fall into the same voxel, and the reference stops such a ray at its own flag."""
+    size, res, gh = (12.9, 12.9, 3.05), 0.1, -0.05
+    origin = (-6.45, -6.45, gh)
+    rng_ = (5.5, 5.5, 4.5)
+    gm = b200.GridMap(size, res, origin=origin, local_update_range=rng_, ground_height=gh)
+    om = po.OracleMap(origin, size, res, local_update_range=rng_, ground_height=gh)
+    intr = dict(fx=96.8, fy=96.8, cx=80.3, cy=60.9, use_depth_filter=0)
+    gm.set_depth_params(**intr)
+    om.set_depth_params(**intr)
+    boxes = synth.pillar_boxes(8, origin, size, 30)
+    r = np.random.default_rng(4)
+    for f in range(6):
+        pos = (-2.0 + 0.1 * f + r.uniform(-0.02, 0.02), 1.0, 1.0 + 0.05 * f)
+        R, _ = synth.look_at(0.3 + 0.05 * f, 0.2)
+        img = synth.render_depth(boxes, gh, pos, R, 120, 160, intr["fx"], intr["fy"], intr["cx"], intr["cy"], max_depth=8.0, dropout=0.03, seed=f)
+        assert gm.depthPoseCallback(img, pos, R) == om.update_depth(img, pos, R)
+        so, sg = om.depth_stats(), gm.depth_stats()
+        assert (sg["projected"], sg["rays_cast"], sg["ray_steps"], sg["updates"]) == tuple(int(x) for x in so[:4]), f"frame {f}"
+        assert np.array_equal(gm.occupancy(), om.occupancy()), f"frame {f}"
+        assert np.array_equal(gm.inflate(), om.inflate()), f"frame {f}"

@@ -87,3 +87,78 @@ def test_oracle_depth_vs_live_reference(po, synth):
             assert np.array_equal(rm.publish_occupancy(1), om.export_occupancy_cloud(1, 0))
         if f == 4:
             assert len(om.export_occupancy_cloud(0, 1)) > 20 and len(om.export_occupancy_cloud(1, 0)) > 1000
+
+
+def _sequential_reach(paths):
+    """The reference's loop (grid_map.cpp:397-419): ray i walks its path, counts every voxel it reaches, and stops at
+    (and including) the first voxel an earlier ray has flagged; voxels it passes get flagged."""
+    flagged, reach = set(), []
+    for p in paths:
+        n = 0
+        for v in p:
+            n += 1
+            if v in flagged:
+                break
+            flagged.add(v)
+        reach.append(n)
+    return reach
+
+
+def _fixpoint_reach(paths):
+    """The order-free formulation the CUDA path uses (csrc/depth_kernels.cu): F(v) = smallest ray id reaching v, iterated
+    from +inf until it stops changing; ray i stops at the first voxel with F(v) < i.  Returns (reach, rounds)."""
+    inf = len(paths)
+    F, rounds = {}, 0
+    while True:
+        rounds += 1
+        Fn = {}
+        for i, p in enumerate(paths):
+            for v in p:
+                if F.get(v, inf) < i:
+                    break
+                if Fn.get(v, inf) > i:
+                    Fn[v] = i
+        if Fn == F:
+            break
+        F = Fn
+        assert rounds <= len(paths) + 2
+    reach = []
+    for i, p in enumerate(paths):
+        n = 0
+        for v in p:
+            n += 1
+            if F.get(v, inf) < i:
+                break
+        reach.append(n)
+    return reach, rounds
+
+
+def test_ray_order_fixed_point_equals_the_sequential_loop(po):
+    """The claim behind the parallel depth fusion, checked on the host: for ANY set of ordered paths the fixed point of
+    'smallest ray id reaching each voxel' reproduces the sequential first-come flags exactly — on rays to a common
+    camera (voxel sequences from the RayCaster restatement) and on arbitrary random paths."""
+    r = np.random.default_rng(5)
+    cam = np.array([20.3, 17.8, 9.1])
+    ends = cam + r.normal(0, 12, (600, 3))
+    paths = [[tuple(c) for c in po.ray_cells(e, cam, cap=256)] for e in ends]
+    want = _sequential_reach(paths)
+    got, rounds = _fixpoint_reach(paths)
+    assert got == want and 2 <= rounds <= 60
+    assert sum(want) < sum(len(p) for p in paths)  # rays really do stop early
+    for trial in range(20):  # no geometry at all: random repeat-free paths over a small voxel set, many collisions
+        paths = [list(r.permutation(40)[: r.integers(1, 12)]) for _ in range(60)]
+        got, _ = _fixpoint_reach(paths)
+        assert got == _sequential_reach(paths), trial
+    # a path that meets one of its OWN earlier voxels stops there in the sequential loop (its own flag); the parallel
+    # form gets the same by cutting every path after its first repeated voxel (depth_path_count_kernel does that)
+    paths = [[1, 2, 2, 3, 4], [5, 2, 6], [7, 8, 7, 9]]
+    cut = []
+    for p in paths:
+        seen, q = set(), []
+        for v in p:
+            q.append(v)
+            if v in seen:
+                break
+            seen.add(v)
+        cut.append(q)
+    assert _fixpoint_reach(cut)[0] == _sequential_reach(paths) == [3, 2, 3]
