@@ -98,6 +98,12 @@ ABI = [
     ("b200_map_depth_stats", C.c_int, [_vp, C.POINTER(_i64)]),
     ("b200_map_set_depth_frame_count", C.c_int, [_vp, _i32]),
     ("b200_map_build_edt", C.c_int, [_vp, _dbl]),
+    ("b200_map_set_edt_pipeline", C.c_int, [_vp, _i32]),
+    ("b200_map_has_distance_field", C.c_int, [_vp, _dbl]),
+    ("b200_map_set_occupied", C.c_int, [_vp, _vp, _i64, _i32]),
+    ("b200_map_set_occupancy", C.c_int, [_vp, _vp, _vp, _i64, _i32]),
+    ("b200_map_path_distance_metrics", C.c_int, [_vp, _vp, _i64, C.POINTER(_dbl), _vp]),
+    ("b200_map_edt_pipeline_used", C.c_int, [_vp]),
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
     ("b200_map_download_dist2", C.c_int, [_vp, _vp]),
@@ -258,6 +264,27 @@ class GridMap:
         _ck(lib().b200_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out), 0))
         return out
 
+    def setOccupied(self, pos):
+        """setOccupied(Vector3d) (grid_map.h:310-321) for an (n,3) batch: inflated grid <- 1 where isInMap."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        _ck(lib().b200_map_set_occupied(self.h, _ptr(pos), len(pos), 0))
+
+    def setOccupancy(self, pos, occ):
+        """setOccupancy(Vector3d, double) (grid_map.h:323-337) for an (n,3) batch: log-odds grid <- occ (0 or 1 only)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        occ = np.ascontiguousarray(np.broadcast_to(np.asarray(occ, dtype=np.float64), (len(pos),)))
+        _ck(lib().b200_map_set_occupancy(self.h, _ptr(pos), _ptr(occ), len(pos), 0))
+
+    def path_distance_metrics(self, path, return_distances=False):
+        """GetPath.srv:20-23 -> dict(mean, std, min, max) of the distance to the nearest obstacle (m) over the path points
+        (metrics.cpp:62-97 arithmetic over sqrt(dist2) * resolution)."""
+        path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, 3)
+        out = (C.c_double * 4)()
+        d = np.empty(len(path), dtype=np.float64)
+        _ck(lib().b200_map_path_distance_metrics(self.h, _ptr(path), len(path), out, _ptr(d)))
+        r = dict(mean=out[0], std=out[1], min=out[2], max=out[3])
+        return (r, d) if return_distances else r
+
     def log_odds(self, pos):
         """occupancy_buffer_ at the (clamped) voxel of each position."""
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
@@ -358,6 +385,16 @@ class GridMap:
     # --- new functionality ------------------------------------------------------------------------
     def build_edt(self, d_safe=0.0):
         _ck(lib().b200_map_build_edt(self.h, float(d_safe)))
+
+    def has_distance_field(self, d_safe=0.0):
+        return bool(lib().b200_map_has_distance_field(self.h, float(d_safe)))
+
+    def set_edt_pipeline(self, mode):
+        """0: automatic (fused shared-memory kernels when they fit), 1: always the seven-kernel HBM-stack pipeline."""
+        _ck(lib().b200_map_set_edt_pipeline(self.h, int(mode)))
+
+    def edt_pipeline_used(self):
+        return "fused" if lib().b200_map_edt_pipeline_used(self.h) else "hbm-stack"
 
     def column_extents(self, lowest=None, highest=None):
         """Lowest / highest occupied z per (x,y) column (-1 = empty): what a z-slab publishes to the others."""

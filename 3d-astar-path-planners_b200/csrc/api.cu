@@ -62,6 +62,9 @@ struct b200_map {
   int dz_bytes;
   int* d_counts;
   int4* d_cross;
+  uint8_t* d_plane_empty;  // fused EDT: planes of pass 1 without any obstacle (edt_fused.cu)
+  bool edt_fused;          // which pipeline the last build_edt ran
+  int edt_mode;            // 0 automatic, 1 always the seven-kernel pipeline
   uint16_t* d_lut;
   int lut_cap;
   double* d_dk;
@@ -184,6 +187,9 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->dz_bytes = 0;
   m->d_counts = nullptr;
   m->d_cross = nullptr;
+  m->d_plane_empty = nullptr;
+  m->edt_fused = false;
+  m->edt_mode = 0;
   m->d_lut = nullptr;
   m->lut_cap = 0;
   m->has_edt = false;
@@ -214,6 +220,7 @@ int b200_map_destroy(b200_map_t* m) {
   if (m->d_dz) cudaFree(m->d_dz);
   if (m->d_counts) cudaFree(m->d_counts);
   if (m->d_cross) cudaFree(m->d_cross);
+  if (m->d_plane_empty) cudaFree(m->d_plane_empty);
   if (m->d_lut) cudaFree(m->d_lut);
   cudaFree(m->d_dk);
   cudaFree(m->d_bounds);
@@ -257,6 +264,7 @@ int b200_map_clear_box(b200_map_t* m, const double mn[3], const double mx[3]) {
     b[i] = host_floor_idx(mx[i], o[i], m->d.inv_res, m->N[i]);
   }
   launch_clear_box(m->d, a, b, m->sm_count, m->stream);
+  m->has_edt = false;  // the distance / cost field describes the previous grid
   m->launches++;
   CK(cudaGetLastError());
   return B200_OK;
@@ -304,6 +312,7 @@ int b200_map_update_cloud(b200_map_t* m, const void* pts, int64_t n, int32_t ste
   if (launch_scatter(m->d, dpts, n, step, ox, oy, oz, cam, m->prm.local_update_range, s, m->d_bounds, m->stream))
     return fail(B200_ERR_UNSUPPORTED, "scatter: inflation step");
   m->launches++;
+  m->has_edt = false;
   if (m->profiling) cudaEventRecord(m->ev[2], m->stream);
   CK(cudaGetLastError());
   m->bounds_pending = true;
@@ -373,6 +382,7 @@ int b200_map_upload_inflate(b200_map_t* m, const uint8_t* src) {
   if (m->stage_in.ensure(nv)) return fail(B200_ERR_NOMEM, "upload staging");
   CK(cudaMemcpyAsync(m->stage_in.p, src, nv, cudaMemcpyHostToDevice, m->stream));
   launch_pack(m->d, (const uint8_t*)m->stage_in.p, m->sm_count, m->stream);
+  m->has_edt = false;
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->stream));
@@ -396,14 +406,9 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
     return true;
   };
   const bool halo = below_gap || above_gap;
-  const int dz_bytes = edt_dz_is_wide(m->d, halo) ? 2 : 1;
-  if (m->d_dz && m->dz_bytes < dz_bytes) { cudaFree(m->d_dz); m->d_dz = nullptr; }
-  const size_t max_lines = (size_t)std::max(m->N[0], m->N[1]) * m->N[2];
-  if (!need((void**)&m->d_tmp, nv * 4) || !need((void**)&m->d_st, nv * 8) || !need((void**)&m->d.dist2, nv * 4) ||
-      !need((void**)&m->d_dz, nv * dz_bytes) || !need((void**)&m->d_counts, max_lines * 4 * 4) ||
-      !need((void**)&m->d_cross, max_lines * sizeof(int4)))
+  if (!need((void**)&m->d_tmp, nv * 4) || !need((void**)&m->d.dist2, nv * 4) ||
+      !need((void**)&m->d_plane_empty, edt_fused_plane_flags_bytes(m->d)))
     return fail(B200_ERR_NOMEM, "distance-field buffers");
-  m->dz_bytes = std::max(m->dz_bytes, dz_bytes);
   const int32_t* d_below = below_gap;
   const int32_t* d_above = above_gap;
   if (halo && !on_device) {  // stage the two per-column halo arrays
@@ -422,10 +427,27 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
       if (!need((void**)&m->d_lut, (size_t)lut_n * 2)) return fail(B200_ERR_NOMEM, "cost table");
       m->lut_cap = lut_n;
     }
+    launch_cost_lut(m->d_lut, lut_n, m->prm.resolution, d_safe, m->stream);
+    m->launches++;
   }
-  launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d_cross, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, d_below, d_above,
-             m->stream, m->profiling ? &m->ev[3] : nullptr);
-  m->launches += 7 + (lut_n > 0 ? 1 : 0);
+  // two shared-memory-staged kernels when a line's hull stack fits in shared memory (edt_fused.cu) ...
+  static const bool force_legacy = getenv("B200_EDT_LEGACY") != nullptr;
+  m->edt_fused = !force_legacy && m->edt_mode == 0 && launch_edt_fused(m->d, m->d_tmp, m->d_plane_empty, m->d.dist2, d_safe > 0 ? m->d.costq : nullptr, m->d_lut,
+                                                   lut_n, d_below, d_above, m->stream, m->profiling ? &m->ev[3] : nullptr);
+  if (m->edt_fused) m->launches += 2;
+  else {
+    // ... else the seven-kernel pipeline with its stacks in HBM (edt_kernels.cu)
+    const int dz_bytes = edt_dz_is_wide(m->d, halo) ? 2 : 1;
+    if (m->d_dz && m->dz_bytes < dz_bytes) { cudaFree(m->d_dz); m->d_dz = nullptr; }
+    const size_t max_lines = (size_t)std::max(m->N[0], m->N[1]) * m->N[2];
+    if (!need((void**)&m->d_st, nv * 8) || !need((void**)&m->d_dz, nv * dz_bytes) || !need((void**)&m->d_counts, max_lines * 4 * 4) ||
+        !need((void**)&m->d_cross, max_lines * sizeof(int4)))
+      return fail(B200_ERR_NOMEM, "distance-field buffers");
+    m->dz_bytes = std::max(m->dz_bytes, dz_bytes);
+    launch_edt(m->d, m->d_dz, m->d_tmp, m->d_st, m->d_counts, m->d_cross, m->d.dist2, m->d.costq, m->d_lut, lut_n, d_safe, d_below, d_above,
+               m->stream, m->profiling ? &m->ev[3] : nullptr);
+    m->launches += 7;
+  }
   CK(cudaGetLastError());
   if (halo && !on_device) CK(cudaStreamSynchronize(m->stream));  // staging buffer is reused by other calls
   m->has_edt = true;
@@ -658,6 +680,46 @@ int b200_map_get_occupancy(b200_map_t* m, const double* pos, int64_t n, int8_t* 
     launch_depth_get_occupancy(m->d, m->dd.occ, m->dd.min_occ_log, p, n, o, m->stream);
   });
 }
+// GridMap::setOccupied (grid_map.h:310-321)
+int b200_map_set_occupied(b200_map_t* m, const double* pos, int64_t n, int32_t on_device) {
+  REQUIRE(m && (n == 0 || pos) && n >= 0, "b200_map_set_occupied: bad argument");
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  const double* dpos = pos;
+  if (!on_device) {
+    if (m->stage_in.ensure((size_t)n * 24)) return fail(B200_ERR_NOMEM, "position staging");
+    CK(cudaMemcpyAsync(m->stage_in.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+    dpos = (const double*)m->stage_in.p;
+  }
+  launch_set_occupied(m->d, dpos, n, m->stream);
+  m->launches++;
+  m->has_edt = false;
+  CK(cudaGetLastError());
+  if (!on_device) CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+// GridMap::setOccupancy (grid_map.h:323-337)
+int b200_map_set_occupancy(b200_map_t* m, const double* pos, const double* occ, int64_t n, int32_t on_device) {
+  REQUIRE(m && (n == 0 || (pos && occ)) && n >= 0 && n < 0xfffffffeLL, "b200_map_set_occupancy: bad argument");
+  if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_set_occupancy: call b200_map_set_depth_params first");
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  int rc = depth_ensure_state(m);
+  if (rc) return rc;
+  const double *dpos = pos, *docc = occ;
+  if (!on_device) {
+    if (m->stage_in.ensure((size_t)n * 32)) return fail(B200_ERR_NOMEM, "position staging");
+    CK(cudaMemcpyAsync(m->stage_in.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync((char*)m->stage_in.p + (size_t)n * 24, occ, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
+    dpos = (const double*)m->stage_in.p;
+    docc = (const double*)((char*)m->stage_in.p + (size_t)n * 24);
+  }
+  launch_set_occupancy(m->d, m->dd.occ, dpos, docc, n, m->dd.E, m->stream);  // E: per-frame scratch, 0xffffffff between frames
+  m->launches += 2;
+  CK(cudaGetLastError());
+  if (!on_device) CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
 int b200_map_get_log_odds(b200_map_t* m, const double* pos, int64_t n, double* out, int32_t on_device) {
   REQUIRE(m, "NULL map");
   if (!m->depth_set) return fail(B200_ERR_INVALID, "b200_map_get_log_odds: call b200_map_set_depth_params first");
@@ -681,6 +743,13 @@ int b200_map_download_occupancy(b200_map_t* m, double* dst) {
 }
 
 int b200_map_build_edt(b200_map_t* m, double d_safe) { return build_edt_impl(m, d_safe, nullptr, nullptr, 0); }
+int b200_map_has_distance_field(const b200_map_t* m, double d_safe) { return m && m->has_edt && m->d_safe == d_safe ? 1 : 0; }
+int b200_map_set_edt_pipeline(b200_map_t* m, int32_t mode) {
+  REQUIRE(m && (mode == 0 || mode == 1), "b200_map_set_edt_pipeline: mode must be 0 or 1");
+  m->edt_mode = mode;
+  return B200_OK;
+}
+int b200_map_edt_pipeline_used(const b200_map_t* m) { return m && m->edt_fused ? 1 : 0; }
 int b200_map_build_edt_slab(b200_map_t* m, double d_safe, const int32_t* below_gap, const int32_t* above_gap, int32_t on_device) {
   return build_edt_impl(m, d_safe, below_gap, above_gap, on_device);
 }
@@ -714,6 +783,33 @@ static int download_field(b200_map_t* m, const void* src, void* dst, size_t byte
 int b200_map_download_dist2(b200_map_t* m, int32_t* dst) {
   REQUIRE(m && dst && m->has_edt, "no distance field (call b200_map_build_edt)");
   return download_field(m, m->d.dist2, dst, (size_t)m->N[0] * m->N[1] * m->N[2] * 4);
+}
+// distance-to-obstacle statistics of a path: distances = sqrt(dist2[voxel(p_i)]) * resolution gathered on the device,
+// then mean / population standard deviation / min / max accumulated on the host in the element order and arithmetic
+// of the reference's calculateDistancesMetrics / getAverage / getStdDev (src/utils/metrics.cpp:62-97)
+int b200_map_path_distance_metrics(b200_map_t* m, const double* path_xyz, int64_t n, double out[4], double* distances) {
+  REQUIRE(m && out && (n == 0 || path_xyz) && n >= 0, "b200_map_path_distance_metrics: bad argument");
+  REQUIRE(m->has_edt, "no distance field (call b200_map_build_edt)");
+  out[0] = out[1] = out[2] = out[3] = 0.0;  // metrics.cpp:77
+  if (n == 0) return B200_OK;
+  CK(cudaSetDevice(m->prm.device));
+  if (m->stage_in.ensure((size_t)n * 24) || m->stage_out.ensure((size_t)n * 8)) return fail(B200_ERR_NOMEM, "path staging");
+  CK(cudaMemcpyAsync(m->stage_in.p, path_xyz, (size_t)n * 24, cudaMemcpyHostToDevice, m->stream));
+  launch_distance_at(m->d, (const double*)m->stage_in.p, n, (double*)m->stage_out.p, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  std::vector<double> d((size_t)n);
+  CK(cudaMemcpyAsync(d.data(), m->stage_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  double sum = 0.0, mn = d[0], mx = d[0];
+  for (int64_t i = 0; i < n; ++i) { sum += d[i]; if (d[i] < mn) mn = d[i]; if (mx < d[i]) mx = d[i]; }
+  const double mean = sum / (double)n;
+  double sd = 0.0;
+  for (int64_t i = 0; i < n; ++i) sd += std::pow(d[i] - mean, 2);
+  sd = std::sqrt(sd / (double)n);
+  out[0] = mean; out[1] = sd; out[2] = mn; out[3] = mx;
+  if (distances) memcpy(distances, d.data(), (size_t)n * 8);
+  return B200_OK;
 }
 int b200_map_download_costq(b200_map_t* m, uint16_t* dst) {
   REQUIRE(m && dst && m->has_edt && m->d_safe > 0 && m->d.costq, "no cost field (build_edt with d_safe > 0)");
@@ -866,8 +962,13 @@ int b200_map_get_stage_ms(b200_map_t* m, double out[16]) {
   float t;
   if (cudaEventElapsedTime(&t, m->ev[0], m->ev[1]) == cudaSuccess) out[0] = t;
   if (cudaEventElapsedTime(&t, m->ev[1], m->ev[2]) == cudaSuccess) out[1] = t;
-  for (int i = 0; i < 7; ++i)
-    if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[2 + i] = t;
+  if (m->edt_fused) {
+    for (int i = 0; i < 2; ++i)
+      if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[9 + i] = t;
+  } else {
+    for (int i = 0; i < 7; ++i)
+      if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[2 + i] = t;
+  }
   cudaGetLastError();
   return B200_OK;
 }

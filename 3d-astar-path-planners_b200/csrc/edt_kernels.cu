@@ -463,6 +463,10 @@ __global__ void cost_lut_kernel(uint16_t* __restrict__ lut, int n, float res, fl
   lut[i] = (uint16_t)__fadd_rn(__fmul_rn(c, 65535.0f), 0.5f);
 }
 
+void launch_cost_lut(uint16_t* lut, int lut_n, double res, double d_safe, cudaStream_t stream) {
+  if (d_safe > 0 && lut_n > 0) cost_lut_kernel<<<(lut_n + 255) / 256, 256, 0, stream>>>(lut, lut_n, (float)res, (float)d_safe);
+}
+
 int edt_lut_size(double res, double d_safe) {
   if (!(d_safe > 0)) return 0;
   const double r = d_safe / res + 2.0;  // every d2 with sqrt(d2)*res < d_safe is below r*r
@@ -487,7 +491,6 @@ void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* coun
   const long long words = (long long)m.Nx * m.Ny * m.wz;
   const unsigned gz = (unsigned)((words + 255) / 256);
   const bool wide = edt_dz_is_wide(m, below_gap || above_gap);
-  if (d_safe > 0 && lut_n > 0) cost_lut_kernel<<<(lut_n + 255) / 256, 256, 0, stream>>>(lut, lut_n, (float)m.res, (float)d_safe);
   if (ev) cudaEventRecord(ev[0], stream);
   if (wide) edt_z_kernel<uint16_t><<<gz, 256, 0, stream>>>(m, (uint16_t*)dzbuf, below_gap, above_gap);
   else edt_z_kernel<uint8_t><<<gz, 256, 0, stream>>>(m, (uint8_t*)dzbuf, below_gap, above_gap);

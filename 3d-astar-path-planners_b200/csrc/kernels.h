@@ -14,6 +14,10 @@ void launch_pack(const MapDev& m, const uint8_t* src, int sm_count, cudaStream_t
 void launch_occupancy(const MapDev& m, const double* pos, long long n, int8_t* out, cudaStream_t st);
 void launch_in_map(const MapDev& m, const double* pos, long long n, uint8_t* out, cudaStream_t st);
 void launch_pos_to_index(const MapDev& m, const double* pos, long long n, int32_t* out, cudaStream_t st);
+void launch_set_occupied(const MapDev& m, const double* pos, long long n, cudaStream_t st);
+void launch_set_occupancy(const MapDev& m, double* logodds, const double* pos, const double* occ, long long n, uint32_t* winner,
+                          cudaStream_t st);
+void launch_distance_at(const MapDev& m, const double* pos, long long n, double* out, cudaStream_t st);
 void launch_los_batch(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* nsamples, int sm_count,
                       cudaStream_t st);
 
@@ -28,6 +32,11 @@ bool edt_dz_is_wide(const MapDev& m, bool halo);
 void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* counts, int4* cross, int32_t* dist2, uint16_t* costq,
                 uint16_t* lut, int lut_n, double d_safe, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream,
                 cudaEvent_t* ev);
+void launch_cost_lut(uint16_t* lut, int lut_n, double res, double d_safe, cudaStream_t stream);
+// ---- edt_fused.cu: two shared-memory-staged kernels; false when no configuration fits the grid
+size_t edt_fused_plane_flags_bytes(const MapDev& m);
+bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
+                      const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev);
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
 
 // ---- search_kernels.cu

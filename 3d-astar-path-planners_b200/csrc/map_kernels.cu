@@ -216,6 +216,47 @@ __global__ void __launch_bounds__(256) pos_to_index_kernel(MapDev m, const doubl
   }
 }
 
+// GridMap::setOccupied (grid_map.h:310-321): inflated buffer <- 1 at the voxel of every in-map position
+__global__ void __launch_bounds__(256) set_occupied_kernel(MapDev m, const double* __restrict__ pos, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+  if (!is_in_map(m, x, y, z)) return;
+  const int ix = pos_to_idx1(x, m.ox, m.inv_res), iy = pos_to_idx1(y, m.oy, m.inv_res), iz = pos_to_idx1(z, m.oz, m.inv_res);
+  if (ix < 0 || iy < 0 || iz < 0 || ix >= m.Nx || iy >= m.Ny || iz >= m.Nz) return;  // the reference would write outside its buffer
+  atomicOr(m.occ + ((size_t)ix * m.Ny + iy) * m.wz + (iz >> 5), 1u << (iz & 31));
+}
+// GridMap::setOccupancy (grid_map.h:323-337): occupancy_buffer_ (log-odds grid) <- occ for occ in {0, 1}.  Where several
+// positions of one call hit the same voxel the LAST one wins, like the sequential calls: pass 1 leaves the largest
+// index per voxel in `winner` (a per-voxel uint32 scratch holding 0xffffffff; keys are n-1-i under atomicMin), pass 2
+// lets that position write and restores the scratch.
+template <bool APPLY>
+__global__ void __launch_bounds__(256) set_occupancy_kernel(MapDev m, double* __restrict__ logodds, const double* __restrict__ pos,
+                                                            const double* __restrict__ occ, long long n, uint32_t* __restrict__ winner) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double o = occ[i];
+  if (o != 1.0 && o != 0.0) return;  // "occ value error!"
+  const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+  if (!is_in_map(m, x, y, z)) return;
+  const int ix = pos_to_idx1(x, m.ox, m.inv_res), iy = pos_to_idx1(y, m.oy, m.inv_res), iz = pos_to_idx1(z, m.oz, m.inv_res);
+  if (ix < 0 || iy < 0 || iz < 0 || ix >= m.Nx || iy >= m.Ny || iz >= m.Nz) return;
+  const size_t a = vox_addr(m, ix, iy, iz);
+  const uint32_t key = (uint32_t)(n - 1 - i);
+  if (!APPLY) atomicMin(winner + a, key);
+  else if (winner[a] == key) { logodds[a] = o; winner[a] = 0xffffffffu; }
+}
+// distance to the nearest obstacle (metres) at the voxel of every position: sqrt(dist2) * resolution, index clamped
+// into the map like GridMap::boundIndex (grid_map.h:267-274)
+__global__ void __launch_bounds__(256) distance_at_kernel(MapDev m, const double* __restrict__ pos, long long n, double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ix = min(max(pos_to_idx1(pos[3 * i], m.ox, m.inv_res), 0), m.Nx - 1);
+  const int iy = min(max(pos_to_idx1(pos[3 * i + 1], m.oy, m.inv_res), 0), m.Ny - 1);
+  const int iz = min(max(pos_to_idx1(pos[3 * i + 2], m.oz, m.inv_res), 0), m.Nz - 1);
+  out[i] = dmul(__dsqrt_rn((double)m.dist2[vox_addr(m, ix, iy, iz)]), m.res);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // batched fastLOS: one warp per segment, grid-stride over segments
 // ---------------------------------------------------------------------------------------------------
@@ -350,6 +391,20 @@ void launch_in_map(const MapDev& m, const double* pos, long long n, uint8_t* out
 }
 void launch_pos_to_index(const MapDev& m, const double* pos, long long n, int32_t* out, cudaStream_t st) {
   if (n > 0) pos_to_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n, out);
+}
+void launch_set_occupied(const MapDev& m, const double* pos, long long n, cudaStream_t st) {
+  if (n > 0) set_occupied_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n);
+}
+// winner: per-voxel uint32 scratch holding 0xffffffff (restored on return); n < 2^32 - 1
+void launch_set_occupancy(const MapDev& m, double* logodds, const double* pos, const double* occ, long long n, uint32_t* winner,
+                          cudaStream_t st) {
+  if (n <= 0) return;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  set_occupancy_kernel<false><<<g, 256, 0, st>>>(m, logodds, pos, occ, n, winner);
+  set_occupancy_kernel<true><<<g, 256, 0, st>>>(m, logodds, pos, occ, n, winner);
+}
+void launch_distance_at(const MapDev& m, const double* pos, long long n, double* out, cudaStream_t st) {
+  if (n > 0) distance_at_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, pos, n, out);
 }
 void launch_los_batch(const MapDev& m, const double* s, const double* e, long long n, uint8_t* vis, int32_t* nsamples, int sm_count,
                       cudaStream_t st) {

@@ -204,7 +204,11 @@ __device__ __forceinline__ uint32_t hash_insert(const Slot& s, double x, double 
 
 struct Shared {
   long long q;
-  int state;       // 0 continue, 1 query finished
+  int state;       // 0 continue, 1 query finished (written by the control warp before the first barrier of an expansion)
+  int stop2;       // 1: query finished in UpdateVertex.  A separate flag: the other warps may still be reading `state`
+                   // when the control warp gets here (no barrier in between when the LoS phase is skipped)
+  int used;        // nodes the finished query created (hash-clearing pass); not `state`: a warp that is late reading
+                   // state == 1 at the loop exit must not see this value instead
   int los_phase;   // this expansion needs the block-wide LoS phase
   unsigned valid;  // neighbour lanes that reach UpdateVertex
   double ppx, ppy, ppz;
@@ -348,6 +352,7 @@ search_kernel(const SearchParams P) {
       __syncwarp();
       heap_push(s, fkey(s.nodes[0].f), 0u, lane);
       sh.state = 0;
+      sh.stop2 = 0;
     }
 
     // ---------------- search loop (AStar.cpp:103-173) ----------------
@@ -586,11 +591,11 @@ search_kernel(const SearchParams P) {
         // any valid heap holding the same entries will do.
         heap_update_batch(s, improved, nb_hpos, fkey(new_f), (uint32_t)nb_idx, lane);
         if (status == ST_POOL_EXHAUSTED) {
-          if (lane == 0) sh.state = 1;
+          if (lane == 0) sh.stop2 = 1;
         }
       }
       if (NW > 1) __syncthreads(); else __syncwarp();
-      if (sh.state == 1) break;
+      if (sh.stop2 == 1) break;
     }
 
     // ---------------- result (AlgorithmBase.cpp:123-175, :202-212; geometry_utils.cpp:10-20) -------------
@@ -656,11 +661,11 @@ search_kernel(const SearchParams P) {
         P.results[q] = r;
         if (status == ST_TIER_OVERFLOW && P.overflow_list) P.overflow_list[atomicAdd(P.overflow_count, 1)] = (int)q;
       }
-      sh.state = s.use;  // broadcast the number of used nodes for the clearing pass
+      sh.used = s.use;  // broadcast the number of used nodes for the clearing pass
     }
     __syncthreads();
     // reset(): clear only the hash slots this query touched (AlgorithmBase.cpp:17-32 analogue)
-    const int used = min(sh.state, P.cap);
+    const int used = min(sh.used, P.cap);
     for (int i = tid; i < used; i += NW * 32) s.hash[s.nodes[i].slot] = 0u;
     __syncthreads();
   }
@@ -743,6 +748,7 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
       }
       __syncwarp();
       sh.state = 0;
+      sh.stop2 = 0;
     }
 
     int cur = 0;
@@ -913,10 +919,10 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         }
         const int ovf = __shfl_sync(0xffffffffu, set.overflow ? 1 : 0, 0);
         if (ovf) { status = P.cap < P.allocate_num ? ST_TIER_OVERFLOW : ST_OPEN_LIST_FULL; last = cur; }
-        if (lane == 0 && (ovf || status == ST_POOL_EXHAUSTED)) sh.state = 1;
+        if (lane == 0 && (ovf || status == ST_POOL_EXHAUSTED)) sh.stop2 = 1;
       }
       if (NW > 1) __syncthreads(); else __syncwarp();
-      if (sh.state == 1) break;
+      if (sh.stop2 == 1) break;
     }
 
     // ---------------- result (same as the canonical kernel) ----------------
@@ -981,10 +987,10 @@ __global__ void __launch_bounds__(NW * 32) search_faithful_kernel(const SearchPa
         P.results[q] = r;
         if (status == ST_TIER_OVERFLOW && P.overflow_list) P.overflow_list[atomicAdd(P.overflow_count, 1)] = (int)q;
       }
-      sh.state = s.use;
+      sh.used = s.use;
     }
     __syncthreads();
-    const int used = min(sh.state, P.cap);
+    const int used = min(sh.used, P.cap);
     for (int i = tid; i < used; i += NW * 32) s.hash[s.nodes[i].slot] = 0u;
     __syncthreads();
   }

@@ -6,12 +6,13 @@
 //
 // What is mirrored: initMap (geometry + parameters of the cloud path), cloudCallback, odomCallback
 // (camera position), resetBuffer (x2), posToIndex, indexToPos, toAddress, isInMap (x2), boundIndex,
-// getInflateOccupancy, setOccupied, getRegion, getResolution, getOrigin, odomValid, plus the new
-// buildDistanceField / getDistance2, and the depth-image path (depthPoseCallback = the reference's callback plus its
+// getInflateOccupancy, setOccupied, setOccupancy, getRegion, getResolution, getOrigin, odomValid, plus the new
+// buildDistanceField / ensureDistanceField / pathDistanceMetrics, and the depth-image path (depthPoseCallback = the reference's callback plus its
 // occupancy timer body; getOccupancy, isKnownOccupied, hasDepthObservation).
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <iostream>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -190,6 +191,25 @@ class GridMap {
                       Vec3d(pose->pose.position.x, pose->pose.position.y, pose->pose.position.z), o.w, o.x, o.y, o.z);
   }
 #endif
+#ifdef B200_WITH_ROS
+  void depthOdomCallback(const sensor_msgs::ImageConstPtr& img, const nav_msgs::OdometryConstPtr& odom) {  // grid_map.cpp:965-994
+    cv_bridge::CvImagePtr cv_ptr = cv_bridge::toCvCopy(img, img->encoding);
+    if (img->encoding == sensor_msgs::image_encodings::TYPE_32FC1) (cv_ptr->image).convertTo(cv_ptr->image, CV_16UC1, dprm_.k_depth_scaling_factor);
+    const auto& o = odom->pose.pose.orientation;
+    const auto& p = odom->pose.pose.position;
+    depthOdomCallback(cv_ptr->image.ptr<uint16_t>(0), cv_ptr->image.rows, cv_ptr->image.cols, Vec3d(p.x, p.y, p.z), o.w, o.x, o.y, o.z);
+  }
+#endif
+  // grid_map.h:310-337 — setOccupied writes the inflated grid, setOccupancy the log-odds grid (values 0 / 1 only)
+  inline void setOccupied(Vec3d pos) {
+    const double p[3] = {pos(0), pos(1), pos(2)};
+    b200_check(b200_map_set_occupied(h_, p, 1, 0), "setOccupied");
+  }
+  inline void setOccupancy(Vec3d pos, double occ = 1) {
+    if (occ != 1 && occ != 0) { std::cout << "occ value error!" << std::endl; return; }  // grid_map.h:325-329
+    const double p[3] = {pos(0), pos(1), pos(2)};
+    b200_check(b200_map_set_occupancy(h_, p, &occ, 1, 0), "setOccupancy");
+  }
   // grid_map.h:339-348 / :276-311 — single reads of occupancy_buffer_ (log-odds) and the inflated grid
   inline int getOccupancy(Vec3d pos) const {
     int8_t v = 0;
@@ -313,6 +333,20 @@ class GridMap {
   }
   // new: exact squared EDT + safety cost field (replaces the commented-out evaluateCoarseEDT hook)
   void buildDistanceField(double d_safe) { b200_check(b200_map_build_edt(h_, d_safe), "build_edt"); }
+  // (re)build only when a map update has invalidated the field or d_safe changed
+  void ensureDistanceField(double d_safe) {
+    if (!b200_map_has_distance_field(h_, d_safe)) buildDistanceField(d_safe);
+  }
+  // GetPath.srv:20-23 — {mean, std_dev, min, max} of the distance to the nearest obstacle (m) over the path points,
+  // DistancesData order of calculateDistancesMetrics (metrics.cpp:62-78)
+  struct DistancesData { double mean, std_dev, min, max; };
+  DistancesData pathDistanceMetrics(const std::vector<Vec3d>& path) const {
+    std::vector<double> flat(path.size() * 3);
+    for (size_t i = 0; i < path.size(); ++i) for (int k = 0; k < 3; ++k) flat[3 * i + k] = path[i](k);
+    double o[4];
+    b200_check(b200_map_path_distance_metrics(h_, flat.data(), (int64_t)path.size(), o, nullptr), "pathDistanceMetrics");
+    return DistancesData{o[0], o[1], o[2], o[3]};
+  }
 
   b200_map_t* handle() const { return h_; }
   const int* voxelNum() const { return n_; }

@@ -83,11 +83,20 @@ int main(int argc, char** argv) {
     const bool solved = std::get<bool>(path_data["solved"]);
     const auto path = algorithm->getPath();
     const Vec3d gc = std::get<Vec3d>(path_data["goal_coords"]);
+    // GetPath.srv:20-23 from the distance field; then setOccupied must invalidate that field
+    grid_map->ensureDistanceField(1.0);
+    const GridMap::DistancesData dd = grid_map->pathDistanceMetrics(path);
+    const int before = grid_map->getInflateOccupancy(Vec3d(3.0, 3.0, 1.0));
+    grid_map->setOccupied(Vec3d(3.0, 3.0, 1.0));
+    grid_map->setOccupied(outside);
+    const int after = grid_map->getInflateOccupancy(Vec3d(3.0, 3.0, 1.0));
+    const int stale = b200_map_has_distance_field(grid_map->handle(), 1.0) ? 0 : 1;
     std::printf("{\"algorithm\": \"%s\", \"solved\": %d, \"n_path\": %zu, \"g_final_node\": %.17g, \"path_length\": %.17g, "
+                "\"dist_mean\": %.17g, \"dist_std\": %.17g, \"dist_min\": %.17g, \"dist_max\": %.17g, \"set_occupied\": [%d, %d], \"edt_stale\": %d, "
                 "\"explored_nodes\": %zu, \"line_of_sight_checks\": %u, \"goal_coords\": [%.17g, %.17g, %.17g], "
                 "\"collide_wall\": %d, \"collide_outside\": %d, \"total_cost1\": %u, \"time_spent_us\": %.3f}\n",
                 std::get<std::string>(path_data["algorithm"]).c_str(), solved ? 1 : 0, path.size(), std::get<double>(path_data["g_final_node"]),
-                std::get<double>(path_data["path_length"]), std::get<size_t>(path_data["explored_nodes"]),
+                std::get<double>(path_data["path_length"]), dd.mean, dd.std_dev, dd.min, dd.max, before, after, stale, std::get<size_t>(path_data["explored_nodes"]),
                 std::get<unsigned int>(path_data["line_of_sight_checks"]), gc(0), gc(1), gc(2), c1 ? 1 : 0, c2 ? 1 : 0,
                 std::get<unsigned int>(path_data["total_cost1"]), std::get<double>(path_data["time_spent"]));
     algorithm->reset();

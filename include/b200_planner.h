@@ -133,6 +133,14 @@ int b200_map_update_depth(b200_map_t* map, const uint16_t* depth, int32_t rows, 
                           const double cam_rot[9], int32_t on_device, int32_t* fused);
 /* GridMap::getOccupancy(Vector3d) (grid_map.h:339-348): -1 outside, else occupancy_buffer_ > logit(p_occ). */
 int b200_map_get_occupancy(b200_map_t* map, const double* pos_xyz, int64_t n, int8_t* out, int32_t on_device);
+/* GridMap::setOccupied(Vector3d) (grid_map.h:310-321), batched: the inflated grid is set to 1 at the voxel of every
+ * position that isInMap; positions outside are ignored.  Invalidates the distance field. */
+int b200_map_set_occupied(b200_map_t* map, const double* pos_xyz, int64_t n, int32_t on_device);
+/* GridMap::setOccupancy(Vector3d, double) (grid_map.h:323-337), batched: occupancy_buffer_ (the log-odds grid the depth
+ * path fuses into) is set to occ[i] at the voxel of pos i.  Like the reference, values other than 0 and 1 and
+ * positions outside the map are ignored; positions apply in index order (the last one on a voxel wins).  Needs
+ * b200_map_set_depth_params (it owns that grid). */
+int b200_map_set_occupancy(b200_map_t* map, const double* pos_xyz, const double* occ, int64_t n, int32_t on_device);
 /* The raw log-odds of the voxel holding each position, index clamped into the map (posToIndex + boundIndex): the read
  * behind GridMap::isUnknown (value < logit(p_min) - 1e-3) and isKnownFree (value >= logit(p_min) and the inflated voxel
  * is free), grid_map.h:276-300. */
@@ -159,6 +167,15 @@ int b200_map_set_depth_frame_count(b200_map_t* map, int32_t raycast_num);
  * the nearest inflated-occupied voxel, plus — when d_safe > 0 — the safety-cost field
  * c = max(0, 1 - sqrt(d2)*res/d_safe) (float32) and its uint16 quantisation the cost-aware planners read. */
 int b200_map_build_edt(b200_map_t* map, double d_safe);
+/* The distance / cost field describes the inflated grid at the time of the build: every call that rewrites the grid
+ * (update_cloud, update_depth, clear_box, reset, upload_inflate, set_occupancy) invalidates it, and the field readers and
+ * cost-aware planners then fail with B200_ERR_INVALID until build_edt runs again.
+ * Pipeline selection (diagnostic; outputs are bit-identical): 0 = automatic (two shared-memory-staged kernels when a
+ * line's hull stack fits in shared memory, else the seven-kernel pipeline with stacks in HBM), 1 = always the latter.
+ * b200_map_edt_pipeline_used reports what the last build ran (1 = fused, 0 = seven-kernel). */
+int b200_map_has_distance_field(const b200_map_t* map, double d_safe); /* 1: built for the current grid with this d_safe */
+int b200_map_set_edt_pipeline(b200_map_t* map, int32_t mode);
+int b200_map_edt_pipeline_used(const b200_map_t* map);
 /* z-slab sharding of the distance transform for grids too large for one GPU (north star).  The map is
  * one z-slab (full x,y extent).  Because the z pass runs first and on bits, the only information an EXACT,
  * untruncated transform needs from the other slabs is, per (x,y) column (index x*Ny + y), the distance in voxels
@@ -169,6 +186,13 @@ int b200_map_column_extents(b200_map_t* map, int32_t* lowest_z, int32_t* highest
 int b200_map_build_edt_slab(b200_map_t* map, double d_safe, const int32_t* below_gap, const int32_t* above_gap,
                             int32_t on_device);
 int b200_map_download_dist2(b200_map_t* map, int32_t* dst);
+/* The distance-to-obstacle statistics GetPath.srv:20-23 carries (min/max/mean/std_dev; the reference leaves them 0
+ * because its EDT hook is commented out): d_i = sqrt(dist2[voxel(p_i)]) * resolution at every path point (index clamped
+ * into the map, grid_map.h:267-274), then out = {mean, std_dev, min, max} with the element order and arithmetic of
+ * calculateDistancesMetrics / getAverage / getStdDev (src/utils/metrics.cpp:62-97; population std-dev).  n = 0 gives
+ * zeros (:77).  distances (optional, n doubles) receives the d_i.  path_xyz is a host pointer. */
+int b200_map_path_distance_metrics(b200_map_t* map, const double* path_xyz, int64_t n, double out_mean_std_min_max[4],
+                                   double* distances);
 int b200_map_download_costq(b200_map_t* map, uint16_t* dst);
 int b200_map_download_cost(b200_map_t* map, float* dst);
 
@@ -188,8 +212,9 @@ int b200_los_batch_dda(b200_map_t* map, const double* seg_start_xyz, const doubl
                        uint8_t* visible, int32_t* n_cells, int32_t on_device);
 
 /* Per-stage device times (ms, CUDA events on the map's stream) of the last update_cloud / build_edt when
- * profiling is enabled: [0] clear, [1] scatter, [2] edt z, [3] scan y, [4] band crossovers y,
- * [5] fill y, [6] scan x, [7] band crossovers x, [8] fill x (+cost), [9..15] reserved. */
+ * profiling is enabled: [0] clear, [1] scatter; seven-kernel EDT: [2] edt z, [3] scan y, [4] band crossovers y,
+ * [5] fill y, [6] scan x, [7] band crossovers x, [8] fill x (+cost); fused EDT: [9] pass z+y, [10] pass x (+cost);
+ * [11..15] reserved. */
 int b200_map_set_profiling(b200_map_t* map, int32_t enable);
 int b200_map_get_stage_ms(b200_map_t* map, double out_ms[16]);
 

@@ -1,0 +1,168 @@
+// Host-side check of the building blocks in csrc/edt_fused.cuh: the phases of the fused EDT kernels are executed
+// thread after thread (a __syncthreads between phases == finishing the loop) and the result is compared with a
+// brute-force squared EDT.  usage: edt_fused_host_test Nx Ny Nz NB W density seed [wide]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+#include "../../3d-astar-path-planners_b200/csrc/edt_fused.cuh"
+using namespace b200::edtf;
+static const int kInf = 1 << 29;
+
+static int bits_of(unsigned v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+template <int NB, int W, class TrY, class TrX, class DZ, bool PACKED>
+static int run(int Nx, int Ny, int Nz, double density, unsigned seed, int pillars) {
+  const int wz = (Nz + 31) / 32;
+  std::mt19937 rng(seed);
+  std::vector<uint32_t> occ((size_t)Nx * Ny * wz, 0);
+  std::uniform_real_distribution<double> U(0, 1);
+  if (pillars) {
+    for (int p = 0; p < pillars; ++p) {
+      int cx = rng() % Nx, cy = rng() % Ny, w = 1 + rng() % 6, h = 1 + rng() % Nz;
+      for (int x = cx; x < cx + w && x < Nx; ++x) for (int y = cy; y < cy + w && y < Ny; ++y) for (int z = 0; z < h; ++z)
+        occ[((size_t)x * Ny + y) * wz + (z >> 5)] |= 1u << (z & 31);
+    }
+  } else {
+    for (int x = 0; x < Nx; ++x) for (int y = 0; y < Ny; ++y) for (int z = 0; z < Nz; ++z)
+      if (U(rng) < density) occ[((size_t)x * Ny + y) * wz + (z >> 5)] |= 1u << (z & 31);
+  }
+  const size_t nv = (size_t)Nx * Ny * Nz;
+  // ---- reference: separable brute force
+  std::vector<int> ref(nv);
+  {
+    std::vector<int> a(nv), b(nv);
+    for (int x = 0; x < Nx; ++x) for (int y = 0; y < Ny; ++y) for (int z = 0; z < Nz; ++z) {
+      int best = kInf;
+      for (int s = 0; s < Nz; ++s) if (occ[((size_t)x * Ny + y) * wz + (s >> 5)] >> (s & 31) & 1u) { int d = (z - s) * (z - s); if (d < best) best = d; }
+      a[((size_t)x * Ny + y) * Nz + z] = best;
+    }
+    for (int x = 0; x < Nx; ++x) for (int z = 0; z < Nz; ++z) for (int y = 0; y < Ny; ++y) {
+      long long best = kInf;
+      for (int s = 0; s < Ny; ++s) { long long v = (long long)(y - s) * (y - s) + a[((size_t)x * Ny + s) * Nz + z]; if (v < best) best = v; }
+      b[((size_t)x * Ny + y) * Nz + z] = (int)best;
+    }
+    for (int y = 0; y < Ny; ++y) for (int z = 0; z < Nz; ++z) for (int x = 0; x < Nx; ++x) {
+      long long best = kInf;
+      for (int s = 0; s < Nx; ++s) { long long v = (long long)(x - s) * (x - s) + b[((size_t)s * Ny + y) * Nz + z]; if (v < best) best = v; }
+      ref[((size_t)x * Ny + y) * Nz + z] = (int)best;
+    }
+  }
+  // ---- emulated kernels
+  using EY = typename TrY::E;
+  using EX = typename TrX::E;
+  constexpr int kNone = sizeof(DZ) == 1 ? 255 : 65535;
+  const int ztiles = (Nz + W - 1) / W;
+  const int SBy = bits_of(Ny - 1), SBx = bits_of(Nx - 1), DYB = SBy;
+  std::vector<uint16_t> tmp16(PACKED ? nv : 0);
+  std::vector<int> tmp32(PACKED ? 0 : nv);
+  std::vector<uint8_t> plane_empty(Nx, 0);
+  std::vector<int> out(nv, -1);
+  {  // pass y
+    const int BL = (Ny + NB - 1) / NB;
+    std::vector<EY> st((size_t)NB * BL * W);
+    std::vector<DZ> dzt((size_t)Ny * W);
+    std::vector<uint32_t> rg(NB * W);
+    std::vector<uint16_t> off(NB * W);
+    std::vector<int> total(W);
+    for (int x = 0; x < Nx; ++x) for (int zt = 0; zt < ztiles; ++zt) {
+      const int z0 = zt * W;
+      for (int y = 0; y < Ny; ++y) column_dz<W, DZ>(&occ[((size_t)x * Ny + y) * wz], wz, Nz, z0, 0, 0, &dzt[(size_t)y * W], 1);
+      for (int band = 0; band < NB; ++band) for (int lane = 0; lane < W; ++lane) {
+        HullBuilder<TrY> hb;
+        hb.init(&st[(size_t)band * BL * W + lane], W, SBy);
+        if (z0 + lane < Nz)
+          for (int u = band * BL; u < Ny && u < (band + 1) * BL; ++u) { int d = dzt[(size_t)u * W + lane]; if (d != kNone) hb.push(u, d); }
+        rg[band * W + lane] = hb.range();
+      }
+      for (int gs = 2; gs <= NB; gs <<= 1)
+        for (int band = 0; band < NB; band += gs) for (int lane = 0; lane < W; ++lane) {
+          LineHull<TrY> L{&st[lane], &rg[lane], W, SBy, BL};
+          zipper<TrY>(L, band, band + gs / 2, band + gs);
+        }
+      for (int lane = 0; lane < W; ++lane) total[lane] = hull_offsets(&rg[lane], &off[lane], W, NB);
+      for (int band = 0; band < NB; ++band) for (int lane = 0; lane < W; ++lane) {
+        const int z = z0 + lane;
+        if (z >= Nz) continue;
+        const int T = total[lane];
+        const int u0 = band * BL, u1 = std::min(Ny, (band + 1) * BL);
+        if (T == 0) {
+          if (PACKED) plane_empty[x] = 1;
+          else for (int u = u0; u < u1; ++u) tmp32[((size_t)x * Ny + u) * Nz + z] = kInf;
+          continue;
+        }
+        LineHull<TrY> L{&st[lane], &rg[lane], W, SBy, BL};
+        hull_fill<TrY>(L, &off[lane], NB, T, u0, u1, [&](int u, int s, uint32_t p, typename TrY::X v) {
+          const size_t a = ((size_t)x * Ny + u) * Nz + z;
+          if (PACKED) tmp16[a] = (uint16_t)((u > s ? u - s : s - u) | (p << DYB));
+          else tmp32[a] = (int)v;
+        });
+      }
+    }
+  }
+  {  // pass x
+    const int BL = (Nx + NB - 1) / NB;
+    std::vector<EX> st((size_t)NB * BL * W);
+    std::vector<uint32_t> rg(NB * W);
+    std::vector<uint16_t> off(NB * W);
+    std::vector<int> total(W);
+    for (int y = 0; y < Ny; ++y) for (int zt = 0; zt < ztiles; ++zt) {
+      const int z0 = zt * W;
+      for (int band = 0; band < NB; ++band) for (int lane = 0; lane < W; ++lane) {
+        HullBuilder<TrX> hb;
+        hb.init(&st[(size_t)band * BL * W + lane], W, SBx);
+        const int z = z0 + lane;
+        if (z < Nz)
+          for (int u = band * BL; u < Nx && u < (band + 1) * BL; ++u) {
+            const size_t a = ((size_t)u * Ny + y) * Nz + z;
+            if (PACKED) {
+              if (plane_empty[u]) continue;
+              const int c = tmp16[a], dy = c & ((1 << DYB) - 1), dz = c >> DYB;
+              hb.push(u, (uint32_t)(dy * dy + dz * dz));
+            } else if (tmp32[a] < kInf) hb.push(u, (uint32_t)tmp32[a]);
+          }
+        rg[band * W + lane] = hb.range();
+      }
+      for (int gs = 2; gs <= NB; gs <<= 1)
+        for (int band = 0; band < NB; band += gs) for (int lane = 0; lane < W; ++lane) {
+          LineHull<TrX> L{&st[lane], &rg[lane], W, SBx, BL};
+          zipper<TrX>(L, band, band + gs / 2, band + gs);
+        }
+      for (int lane = 0; lane < W; ++lane) total[lane] = hull_offsets(&rg[lane], &off[lane], W, NB);
+      for (int band = 0; band < NB; ++band) for (int lane = 0; lane < W; ++lane) {
+        const int z = z0 + lane;
+        if (z >= Nz) continue;
+        const int T = total[lane];
+        const int u0 = band * BL, u1 = std::min(Nx, (band + 1) * BL);
+        if (T == 0) { for (int u = u0; u < u1; ++u) out[((size_t)u * Ny + y) * Nz + z] = kInf; continue; }
+        LineHull<TrX> L{&st[lane], &rg[lane], W, SBx, BL};
+        hull_fill<TrX>(L, &off[lane], NB, T, u0, u1, [&](int u, int, uint32_t, typename TrX::X v) { out[((size_t)u * Ny + y) * Nz + z] = (int)v; });
+      }
+    }
+  }
+  size_t bad = 0;
+  for (size_t i = 0; i < nv; ++i) if (out[i] != ref[i]) { if (bad < 5) printf("  mismatch at %zu: got %d want %d\n", i, out[i], ref[i]); ++bad; }
+  printf("%dx%dx%d NB=%d W=%d packed=%d seed=%u: %zu mismatches\n", Nx, Ny, Nz, NB, W, (int)PACKED, seed, bad);
+  return bad != 0;
+}
+
+int main(int argc, char** argv) {
+  int rc = 0;
+  using SY = PassY<uint16_t, int32_t>; using SX = PassX<uint32_t, int32_t>;
+  using GY = PassY<uint32_t, long long>; using GX = PassX<uint64_t, long long>;
+  unsigned seed = argc > 1 ? atoi(argv[1]) : 1;
+  for (unsigned s = seed; s < seed + 3; ++s) {
+    rc |= run<8, 32, SY, SX, uint8_t, true>(40, 70, 50, 0.002, s, 0);
+    rc |= run<8, 32, SY, SX, uint8_t, true>(33, 64, 64, 0.05, s, 0);
+    rc |= run<8, 32, SY, SX, uint8_t, true>(48, 96, 40, 0.0, s, 9);
+    rc |= run<8, 32, SY, SX, uint8_t, true>(20, 20, 33, 0.0, s, 0);   // empty map
+    rc |= run<8, 32, SY, SX, uint8_t, true>(64, 5, 7, 0.01, s, 0);    // fewer sites than bands
+    rc |= run<8, 32, GY, GX, uint16_t, false>(40, 70, 50, 0.002, s, 0);
+    rc |= run<16, 16, GY, GX, uint16_t, false>(50, 90, 40, 0.001, s, 0);
+    rc |= run<32, 8, GY, GX, uint16_t, false>(70, 130, 20, 0.0005, s, 0);
+    rc |= run<32, 8, GY, GX, uint16_t, false>(30, 60, 24, 0.0, s, 5);
+  }
+  printf(rc ? "FAILED\n" : "ALL OK\n");
+  return rc;
+}

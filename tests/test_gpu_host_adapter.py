@@ -1,6 +1,7 @@
 """-m gpu: the C++ adapter classes (3d-astar-path-planners_b200/host) driven like the reference's ROS node, compared
 with the same world through the ctypes binding."""
 import json
+import math
 import os
 import subprocess
 
@@ -44,6 +45,23 @@ def test_cpp_adapter_matches_ctypes_path(b200, algo):
     assert np.array_equal(np.array(d["goal_coords"]), r["goal_coords"])
     assert d["collide_wall"] == 1 and d["collide_outside"] == 1 and d["total_cost1"] == 0
     assert d["time_spent_us"] > 0
+    # GetPath.srv:20-23 through the adapter == the ctypes path == metrics.cpp arithmetic over the field the GPU built
+    gm.build_edt(1.0)
+    m, dist = gm.path_distance_metrics(pl.getPath(), return_distances=True)
+    assert (d["dist_mean"], d["dist_std"], d["dist_min"], d["dist_max"]) == (m["mean"], m["std"], m["min"], m["max"])
+    idx = gm.posToIndex(pl.getPath())
+    want = np.sqrt(gm.dist2()[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float64)) * 0.1
+    assert np.array_equal(dist, want)
+    acc = 0.0
+    for v in want:
+        acc += float(v)
+    mean = acc / len(want)
+    sd = 0.0
+    for v in want:
+        sd += (float(v) - mean) ** 2
+    assert m["mean"] == mean and m["std"] == math.sqrt(sd / len(want)) and m["min"] == want.min() and m["max"] == want.max()
+    assert m["min"] > 0
+    assert d["set_occupied"] == [0, 1] and d["edt_stale"] == 1
 
 
 def test_cpp_adapter_depth_path(b200, po):
