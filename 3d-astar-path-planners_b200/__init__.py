@@ -106,6 +106,7 @@ ABI = [
     ("b200_map_edt_pipeline_used", C.c_int, [_vp]),
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
+    ("b200_map_set_slab_extent", C.c_int, [_vp, _i32]),
     ("b200_map_download_dist2", C.c_int, [_vp, _vp]),
     ("b200_map_download_costq", C.c_int, [_vp, _vp]),
     ("b200_map_download_cost", C.c_int, [_vp, _vp]),
@@ -405,6 +406,10 @@ class GridMap:
         hi = np.empty(self.dims[:2], dtype=np.int32)
         _ck(lib().b200_map_column_extents(self.h, _ptr(lo), _ptr(hi), 0))
         return lo, hi
+
+    def set_slab_extent(self, total_nz):
+        """z-slab sharding: height (voxels) of the whole stacked grid — bounds the halo distances (narrower hull entries)."""
+        _ck(lib().b200_map_set_slab_extent(self.h, int(total_nz)))
 
     def build_edt_slab(self, d_safe=0.0, below_gap=None, above_gap=None):
         """EDT of one z-slab given the per-column gaps to the nearest occupied voxel in the slabs below / above."""

@@ -65,6 +65,7 @@ struct b200_map {
   uint8_t* d_plane_empty;  // fused EDT: planes of pass 1 without any obstacle (edt_fused.cu)
   bool edt_fused;          // which pipeline the last build_edt ran
   int edt_mode;            // 0 automatic, 1 always the seven-kernel pipeline
+  int slab_total_nz;       // z-slab sharding: height of the whole stacked grid (bounds the halo distances), 0 = unknown
   uint16_t* d_lut;
   int lut_cap;
   double* d_dk;
@@ -190,6 +191,7 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->d_plane_empty = nullptr;
   m->edt_fused = false;
   m->edt_mode = 0;
+  m->slab_total_nz = 0;
   m->d_lut = nullptr;
   m->lut_cap = 0;
   m->has_edt = false;
@@ -433,7 +435,7 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   // two shared-memory-staged kernels when a line's hull stack fits in shared memory (edt_fused.cu) ...
   static const bool force_legacy = getenv("B200_EDT_LEGACY") != nullptr;
   m->edt_fused = !force_legacy && m->edt_mode == 0 && launch_edt_fused(m->d, m->d_tmp, m->d_plane_empty, m->d.dist2, d_safe > 0 ? m->d.costq : nullptr, m->d_lut,
-                                                   lut_n, d_below, d_above, m->stream, m->profiling ? &m->ev[3] : nullptr);
+                                                   lut_n, d_below, d_above, m->slab_total_nz, m->stream, m->profiling ? &m->ev[3] : nullptr);
   if (m->edt_fused) m->launches += 2;
   else {
     // ... else the seven-kernel pipeline with its stacks in HBM (edt_kernels.cu)
@@ -752,6 +754,11 @@ int b200_map_set_edt_pipeline(b200_map_t* m, int32_t mode) {
 int b200_map_edt_pipeline_used(const b200_map_t* m) { return m && m->edt_fused ? 1 : 0; }
 int b200_map_build_edt_slab(b200_map_t* m, double d_safe, const int32_t* below_gap, const int32_t* above_gap, int32_t on_device) {
   return build_edt_impl(m, d_safe, below_gap, above_gap, on_device);
+}
+int b200_map_set_slab_extent(b200_map_t* m, int32_t total_nz) {
+  REQUIRE(m && total_nz >= 0, "b200_map_set_slab_extent: bad argument");
+  m->slab_total_nz = total_nz;
+  return B200_OK;
 }
 int b200_map_column_extents(b200_map_t* m, int32_t* lowest, int32_t* highest, int32_t on_device) {
   REQUIRE(m && lowest && highest, "NULL argument");

@@ -5,8 +5,9 @@
 //
 // Block = tile of one (x) [pass 1] or one (y) [pass 2], W consecutive z, the WHOLE line in the third axis:
 //   pass 1 (y):  the plane's bit words arrive in shared memory by one bulk async copy (cp.async.bulk + mbarrier);
-//                thread per column turns them into W z distances (clz/ffs sweep) in a shared tile; thread (band, lane)
-//                builds the band's lower hull in the shared stack; log2(NB) zipper levels; prefix of the surviving
+//                thread per column finds the nearest occupied z outside the tile's own word; thread (band, lane) derives
+//                each site's z distance from the bit word on the fly (two masks, clz / ffs) and builds the band's lower
+//                hull in the shared stack; log2(NB) zipper levels; prefix of the surviving
 //                intervals; thread (band, lane) walks the hull over its 1/NB of the line and stores, per voxel, the
 //                PAIR (|y - y*|, dz(y*)) packed in 16 bits instead of the 19-bit squared distance: the intermediate
 //                volume is 2 B/voxel (67 MB at C2: it stays in the 126 MB L2 for pass 2).
@@ -14,6 +15,8 @@
 //                g = dy^2 + dz^2, hull in shared memory, zipper, walk; writes dist2 (int32) and costq (uint16, table).
 // HBM traffic per voxel: 1/8 B in, 2 B + 2 B through L2, 4 B + 2 B out; no stack, z-distance or crossover arrays.
 // Per-thread logic: edt_fused.cuh (also compiled for the host by tests/cpu/edt_fused_host_test.cpp).
+#include <algorithm>
+
 #include "kernels.h"
 #include "edt_fused.cuh"
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ int merge_bands(const typename Tr::E* st, uint32_t* r
     __syncthreads();
     if ((band & (gs - 1)) == 0) zipper<Tr>(L, band, band + gs / 2, band + gs);
   }
-  __syncthreads();
+  // band 0's thread made the last merge itself: it can go straight on to the prefix of the surviving intervals
   if (band == 0) total[lane] = hull_offsets(rng + lane, off + lane, W, NB);
   __syncthreads();
   return total[lane];
@@ -69,21 +72,22 @@ __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(siz
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
-// pass 1: bits -> z distances -> hull along y -> packed (dy, dz) or int32 squared distance
+// pass 1: bits -> z distance (on the fly, per site) -> hull along y -> packed (dy, dz) or int32 squared distance
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int W, class Tr, class DZ, class TmpT, bool BULK>
-__global__ void __launch_bounds__(NB* W) edt_fused_y_kernel(MapDev m, const int32_t* __restrict__ below_gap, const int32_t* __restrict__ above_gap,
-                                                           TmpT* __restrict__ tmp, uint8_t* __restrict__ plane_empty, int SB, int BL) {
+template <int NB, int W, class Tr, class TmpT, bool BULK>
+__global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
+    edt_fused_y_kernel(MapDev m, const int32_t* __restrict__ below_gap, const int32_t* __restrict__ above_gap, TmpT* __restrict__ tmp,
+                       uint8_t* __restrict__ plane_empty, int SB, int BL, int DYB) {
   using E = typename Tr::E;
   using X = typename Tr::X;
   constexpr bool PACKED = sizeof(TmpT) == 2;
-  constexpr int kNone = sizeof(DZ) == 1 ? 255 : 65535;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Ny = m.Ny, Nz = m.Nz, wz = m.wz;
   E* st = reinterpret_cast<E*>(smem_raw);
-  DZ* dzt = reinterpret_cast<DZ*>(smem_raw + align16((size_t)NB * BL * W * sizeof(E)));
-  uint32_t* bits = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dzt) + align16((size_t)Ny * W * sizeof(DZ)));
-  uint32_t* rng = bits + (BULK ? (((size_t)Ny * wz + 3) & ~(size_t)3) : 0);
+  // BULK: all the plane's bit words [Ny][wz]; else only the tile's own word of every column [Ny]
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw + align16((size_t)NB * BL * W * sizeof(E)));
+  int2* outside = reinterpret_cast<int2*>(bits + (((size_t)Ny * (BULK ? wz : 1) + 3) & ~(size_t)3));  // per column: nearest z below / above the own word
+  uint32_t* rng = reinterpret_cast<uint32_t*>(outside + Ny);
   uint16_t* off = reinterpret_cast<uint16_t*>(rng + NB * W);
   int* total = reinterpret_cast<int*>(off + NB * W);
   __shared__ __align__(8) uint64_t bar;
@@ -91,8 +95,10 @@ __global__ void __launch_bounds__(NB* W) edt_fused_y_kernel(MapDev m, const int3
   const int ztiles = (Nz + W - 1) / W;
   const int x = blockIdx.x / ztiles, z0 = (blockIdx.x % ztiles) * W;
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
+  const int wi = z0 >> 5;
   const uint32_t* plane_bits = m.occ + (size_t)x * Ny * wz;
-  if (BULK) {
+  const int bstride = BULK ? wz : 1, boff = BULK ? wi : 0;
+  if (BULK) {  // one bulk async copy of the plane's words (TMA engine), completion on an mbarrier
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -102,61 +108,58 @@ __global__ void __launch_bounds__(NB* W) edt_fused_y_kernel(MapDev m, const int3
     }
     mbar_wait(&bar, 0);
   }
-  // z distances of the tile: thread per column
   for (int y = tid; y < Ny; y += NB * W) {
     const size_t col = (size_t)x * Ny + y;
     const int bg = below_gap ? __ldg(below_gap + col) : 0, ag = above_gap ? __ldg(above_gap + col) : 0;
-    __align__(16) DZ v[W];
-    uint32_t cw[8];
-    const uint32_t* c = BULK ? bits + (size_t)y * wz : plane_bits + (size_t)y * wz;
-    if (!BULK && wz <= 8) {  // read the column once through the read-only path
-      for (int j = 0; j < wz; ++j) cw[j] = __ldg(c + j);
-      c = cw;
+    int lo, hi;
+    if (BULK) column_outside(bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
+    else {  // planes too large to stage whole: the other words of the column come straight from L2
+      column_outside(plane_bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
+      bits[y] = __ldg(plane_bits + (size_t)y * wz + wi);
     }
-    column_dz<W, DZ>(c, wz, Nz, z0, bg, ag, v, 1);
-    constexpr int kBytes = W * (int)sizeof(DZ);
-    if (kBytes >= 16) {
-#pragma unroll
-      for (int k = 0; k < kBytes / 16; ++k) reinterpret_cast<uint4*>(dzt + (size_t)y * W)[k] = reinterpret_cast<const uint4*>(v)[k];
-    } else {
-      reinterpret_cast<uint2*>(dzt + (size_t)y * W)[0] = reinterpret_cast<const uint2*>(v)[0];
-    }
+    outside[y] = make_int2(lo, hi);
   }
   __syncthreads();
-  const int z = z0 + lane;
+  const int z = z0 + lane, bi = z & 31;
   const bool active = z < Nz;
   const int u0 = band * BL, u1 = min(Ny, u0 + BL);
   {
     HullBuilder<Tr> hb;
-    hb.init(st + (size_t)band * BL * W + lane, W, SB);
-    if (active)
-      for (int u = u0; u < u1; ++u) {
-        const int d = dzt[(size_t)u * W + lane];
-        if (d != kNone) hb.push(u, (uint32_t)d);
+    hb.init(st + (size_t)band * BL * W + lane, W, SB, u0);
+    if (active) {
+      const uint32_t* wp = bits + (size_t)u0 * bstride + boff;
+      for (int u = u0; u < u1; ++u, wp += bstride) {
+        const int2 o = outside[u];
+        const int d = site_dz(*wp, bi, z, o.x, o.y);
+        if (d < kDzNone) hb.push(u, (uint32_t)d);
       }
+    }
     rng[band * W + lane] = hb.range();
   }
   const int T = merge_bands<NB, W, Tr>(st, rng, off, total, SB, BL, band, lane);
   if (!active) return;
   if (PACKED && blockIdx.x % ztiles == 0 && tid == 0) plane_empty[x] = T == 0;
-  TmpT* o = tmp + (size_t)x * Ny * Nz + z;
+  TmpT* o = tmp + ((size_t)x * Ny + u0) * Nz + z;
   if (T == 0) {
     if (!PACKED)
-      for (int u = u0; u < u1; ++u) o[(size_t)u * Nz] = (TmpT)kDistInf;
+      for (int u = u0; u < u1; ++u, o += Nz) *o = (TmpT)kDistInf;
     return;
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
-  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, [&](int u, int s, uint32_t p, X v) {
-    if (PACKED) o[(size_t)u * Nz] = (TmpT)((uint32_t)abs(u - s) | (p << SB));
-    else o[(size_t)u * Nz] = (TmpT)v;
+  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, X v) {
+    if (PACKED) *o = (TmpT)((uint32_t)abs(d) | (p << DYB));
+    else *o = (TmpT)v;
+    o += Nz;
   });
 }
 
 // ---------------------------------------------------------------------------------------------------
 // pass 2: hull along x over pass 1's volume -> dist2 (+ costq)
 // ---------------------------------------------------------------------------------------------------
+constexpr int kSmemLut = 2048;  // cost-table entries kept in shared memory (d_safe / resolution up to 43 voxels)
+
 template <int NB, int W, class Tr, class TmpT>
-__global__ void __launch_bounds__(NB* W) edt_fused_x_kernel(MapDev m, const TmpT* __restrict__ tmp, const uint8_t* __restrict__ plane_empty,
+__global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const TmpT* __restrict__ tmp, const uint8_t* __restrict__ plane_empty,
                                                            int32_t* __restrict__ dist2, uint16_t* __restrict__ costq,
                                                            const uint16_t* __restrict__ lut, int lut_n, int SB, int BL, int DYB) {
   using E = typename Tr::E;
@@ -169,62 +172,79 @@ __global__ void __launch_bounds__(NB* W) edt_fused_x_kernel(MapDev m, const TmpT
   uint32_t* rng = reinterpret_cast<uint32_t*>(smem_raw + align16((size_t)NB * BL * W * sizeof(E)));
   uint16_t* off = reinterpret_cast<uint16_t*>(rng + NB * W);
   int* total = reinterpret_cast<int*>(off + NB * W);
-  uint8_t* pe = reinterpret_cast<uint8_t*>(total + W);
+  uint16_t* slut = reinterpret_cast<uint16_t*>(total + W);  // [min(lut_n, kSmemLut) + 1], last entry 0
+  uint8_t* pe = reinterpret_cast<uint8_t*>(slut + kSmemLut + 2);
 
   const int ztiles = (Nz + W - 1) / W;
   const int y = blockIdx.x / ztiles, z0 = (blockIdx.x % ztiles) * W;
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
-  if (PACKED) {
-    for (int i = tid; i < Nx; i += NB * W) pe[i] = __ldg(plane_empty + i);
-    __syncthreads();
-  }
+  const bool smem_lut = costq != nullptr && lut_n <= kSmemLut;
+  int any_empty = 0;
+  if (PACKED)
+    for (int i = tid; i < Nx; i += NB * W) { const uint8_t v = __ldg(plane_empty + i); pe[i] = v; any_empty |= v; }
+  if (smem_lut)
+    for (int i = tid; i <= lut_n; i += NB * W) slut[i] = i < lut_n ? __ldg(lut + i) : (uint16_t)0;
+  any_empty = __syncthreads_or(any_empty);
   const int z = z0 + lane;
   const bool active = z < Nz;
   const int u0 = band * BL, u1 = min(Nx, u0 + BL);
   const size_t plane = (size_t)Ny * Nz, base = (size_t)y * Nz + z;
   {
     HullBuilder<Tr> hb;
-    hb.init(st + (size_t)band * BL * W + lane, W, SB);
+    hb.init(st + (size_t)band * BL * W + lane, W, SB, u0);
     if (active) {
-      const TmpT* in = tmp + base;
+      const TmpT* in = tmp + base + (size_t)u0 * plane;
       const uint32_t dmask = (1u << DYB) - 1u;
-      for (int ub = u0; ub < u1; ub += PF) {
-        TmpT buf[PF];
+      auto site = [&](int u, TmpT raw) {
+        if (PACKED) {
+          const uint32_t c = (uint32_t)raw, dy = c & dmask, dz = c >> DYB;
+          hb.push(u, dy * dy + dz * dz);
+        } else if ((int32_t)raw < kDistInf) hb.push(u, (uint32_t)raw);
+      };
+      int ub = u0;
+      if (!(PACKED && any_empty)) {
+        for (; ub + PF <= u1; ub += PF) {  // PF sites requested ahead of the serial hull update
+          TmpT buf[PF];
 #pragma unroll
-        for (int j = 0; j < PF; ++j) buf[j] = (ub + j < u1) ? __ldg(in + (size_t)(ub + j) * plane) : (TmpT)0;
+          for (int j = 0; j < PF; ++j, in += plane) buf[j] = __ldg(in);
 #pragma unroll
-        for (int j = 0; j < PF; ++j) {
-          const int u = ub + j;
-          if (u < u1) {
-            if (PACKED) {
-              if (!pe[u]) {
-                const uint32_t c = (uint32_t)buf[j], dy = c & dmask, dz = c >> DYB;
-                hb.push(u, dy * dy + dz * dz);
-              }
-            } else if ((int32_t)buf[j] < kDistInf) hb.push(u, (uint32_t)buf[j]);
-          }
+          for (int j = 0; j < PF; ++j) site(ub + j, buf[j]);
         }
       }
+      for (; ub < u1; ++ub, in += plane)
+        if (!(PACKED && pe[ub])) site(ub, __ldg(in));
     }
     rng[band * W + lane] = hb.range();
   }
   const int T = merge_bands<NB, W, Tr>(st, rng, off, total, SB, BL, band, lane);
   if (!active) return;
-  int32_t* o = dist2 + base;
-  uint16_t* cq = costq ? costq + base : nullptr;
+  int32_t* o = dist2 + base + (size_t)u0 * plane;
+  uint16_t* cq = costq ? costq + base + (size_t)u0 * plane : nullptr;
   if (T == 0) {
-    for (int u = u0; u < u1; ++u) {
-      o[(size_t)u * plane] = kDistInf;
-      if (cq) cq[(size_t)u * plane] = 0;
+    for (int u = u0; u < u1; ++u, o += plane) {
+      *o = kDistInf;
+      if (cq) { *cq = 0; cq += plane; }
     }
     return;
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
-  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, [&](int u, int, uint32_t, X v) {
-    const int32_t d = (int32_t)v;
-    o[(size_t)u * plane] = d;
-    if (cq) cq[(size_t)u * plane] = d < lut_n ? __ldg(lut + d) : (uint16_t)0;
-  });
+  if (!cq) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) { *o = (int32_t)v; o += plane; });
+  } else if (smem_lut) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) {
+      const int32_t d = (int32_t)v;
+      *o = d;
+      *cq = slut[min(d, lut_n)];
+      o += plane; cq += plane;
+    });
+  } else {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) {
+      const int32_t d = (int32_t)v;
+      *o = d;
+      *cq = d < lut_n ? __ldg(lut + d) : (uint16_t)0;
+      o += plane; cq += plane;
+    });
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -232,44 +252,61 @@ __global__ void __launch_bounds__(NB* W) edt_fused_x_kernel(MapDev m, const TmpT
 // ---------------------------------------------------------------------------------------------------
 namespace {
 int bits_of(unsigned long long v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
-constexpr int kMaxSmem = 227 * 1024;
+constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int NB, int W, class E, class DZ>
-size_t smem_y(int Ny, int wz, bool bulk) {
-  const int BL = (Ny + NB - 1) / NB;
-  return align16((size_t)NB * BL * W * sizeof(E)) + align16((size_t)Ny * W * sizeof(DZ)) + (bulk ? (((size_t)Ny * wz + 3) & ~(size_t)3) * 4 : 0) +
-         (size_t)NB * W * 6 + (size_t)W * 4 + 16;
+struct Cfg { size_t smem; int blocks_per_sm; };
+// blocks of `smem` dynamic bytes (+1 KB reserved each) an SM holds
+Cfg cfg_of(size_t smem, int threads) {
+  Cfg c{smem, 0};
+  if (smem <= kMaxSmem) c.blocks_per_sm = (int)std::min<size_t>((228 * 1024) / (smem + 1024), 2048 / threads);
+  return c;
+}
+bool bulk_ok(const MapDev& m) { return ((size_t)m.Ny * m.wz) % 4 == 0 && (size_t)m.Ny * m.wz * 4 <= 16 * 1024; }
+template <int NB, int W, class E>
+size_t smem_y(const MapDev& m) {
+  const int BL = (m.Ny + NB - 1) / NB;
+  const size_t words = (((size_t)m.Ny * (bulk_ok(m) ? m.wz : 1)) + 3) & ~(size_t)3;
+  return align16((size_t)NB * BL * W * sizeof(E)) + words * 4 + (size_t)m.Ny * 8 + (size_t)NB * W * 6 + (size_t)W * 4 + 16;
 }
 template <int NB, int W, class E>
-size_t smem_x(int Nx) {
-  const int BL = (Nx + NB - 1) / NB;
-  return align16((size_t)NB * BL * W * sizeof(E)) + (size_t)NB * W * 6 + (size_t)W * 4 + (size_t)Nx + 32;
+size_t smem_x(const MapDev& m) {
+  const int BL = (m.Nx + NB - 1) / NB;
+  return align16((size_t)NB * BL * W * sizeof(E)) + (size_t)NB * W * 6 + (size_t)W * 4 + (size_t)(kSmemLut + 2) * 2 + (size_t)m.Nx + 32;
 }
 
-template <int NB, int W, class TrY, class TrX, class DZ, class TmpT>
-bool launch_family(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-                   const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev) {
-  const bool bulk = ((size_t)m.Ny * m.wz) % 4 == 0 && (((size_t)m.Ny * m.wz * 4) < (1u << 20));
-  const size_t sy = smem_y<NB, W, typename TrY::E, DZ>(m.Ny, m.wz, bulk), sx = smem_x<NB, W, typename TrX::E>(m.Nx);
-  if (sy > (size_t)kMaxSmem || sx > (size_t)kMaxSmem) return false;
-  const int ztiles = (m.Nz + W - 1) / W;
-  const int SBy = bits_of((unsigned)(m.Ny - 1)), SBx = bits_of((unsigned)(m.Nx - 1));
-  const int BLy = (m.Ny + NB - 1) / NB, BLx = (m.Nx + NB - 1) / NB;
-  auto ky_bulk = edt_fused_y_kernel<NB, W, TrY, DZ, TmpT, true>;
-  auto ky_plain = edt_fused_y_kernel<NB, W, TrY, DZ, TmpT, false>;
-  auto kx = edt_fused_x_kernel<NB, W, TrX, TmpT>;
-  auto ky = bulk ? ky_bulk : ky_plain;
-  if (cudaFuncSetAttribute(ky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sy) != cudaSuccess ||
-      cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  if (ev) cudaEventRecord(ev[0], stream);
-  ky<<<(unsigned)(m.Nx * ztiles), NB * W, sy, stream>>>(m, below_gap, above_gap, (TmpT*)tmp, plane_empty, SBy, BLy);
-  if (ev) cudaEventRecord(ev[1], stream);
-  kx<<<(unsigned)(m.Ny * ztiles), NB * W, sx, stream>>>(m, (const TmpT*)tmp, plane_empty, dist2, costq, lut, lut_n, SBx, BLx, SBy);
-  if (ev) cudaEventRecord(ev[2], stream);
+template <int NB, int W, class Tr, class TmpT>
+bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream) {
+  const size_t sy = smem_y<NB, W, typename Tr::E>(m);
+  const bool bulk = bulk_ok(m);
+  auto k = bulk ? edt_fused_y_kernel<NB, W, Tr, TmpT, true> : edt_fused_y_kernel<NB, W, Tr, TmpT, false>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sy) != cudaSuccess) { cudaGetLastError(); return false; }
+  const int ztiles = (m.Nz + W - 1) / W, BL = (m.Ny + NB - 1) / NB;
+  k<<<(unsigned)(m.Nx * ztiles), NB * W, sy, stream>>>(m, below_gap, above_gap, (TmpT*)tmp, plane_empty, bits_of((unsigned)(BL - 1)), BL,
+                                                        bits_of((unsigned)(m.Ny - 1)));
   return true;
+}
+template <int NB, int W, class Tr, class TmpT>
+bool launch_x(const MapDev& m, const void* tmp, const uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
+              cudaStream_t stream) {
+  const size_t sx = smem_x<NB, W, typename Tr::E>(m);
+  auto k = edt_fused_x_kernel<NB, W, Tr, TmpT>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx) != cudaSuccess) { cudaGetLastError(); return false; }
+  const int ztiles = (m.Nz + W - 1) / W, BL = (m.Nx + NB - 1) / NB;
+  k<<<(unsigned)(m.Ny * ztiles), NB * W, sx, stream>>>(m, (const TmpT*)tmp, plane_empty, dist2, costq, lut, lut_n, bits_of((unsigned)(BL - 1)), BL,
+                                                        bits_of((unsigned)(m.Ny - 1)));
+  return true;
+}
+// The three tile shapes (bands x lanes, 256 threads): the widest whose hull stack leaves at least two blocks per SM,
+// else the widest that fits at all.  0 = none fits.
+template <class E, bool Y>
+int pick_shape(const MapDev& m) {
+  const size_t s[3] = {Y ? smem_y<8, 32, E>(m) : smem_x<8, 32, E>(m), Y ? smem_y<16, 16, E>(m) : smem_x<16, 16, E>(m),
+                       Y ? smem_y<32, 8, E>(m) : smem_x<32, 8, E>(m)};
+  for (int i = 0; i < 3; ++i)
+    if (cfg_of(s[i], 256).blocks_per_sm >= 2) return i + 1;
+  for (int i = 0; i < 3; ++i)
+    if (cfg_of(s[i], 256).blocks_per_sm >= 1) return i + 1;
+  return 0;
 }
 }  // namespace
 
@@ -277,28 +314,59 @@ size_t edt_fused_plane_flags_bytes(const MapDev& m) { return (size_t)m.Nx + 16; 
 
 // Returns false when no fused configuration fits this grid (the caller then runs the seven-kernel pipeline).
 // tmp: 4 B/voxel scratch (2 B/voxel used in the packed case); ev (optional): 3 events before y, between, after x.
+// dz_bound: with a halo, an upper bound on any z distance (the stacked grid's total height), 0 when unknown.
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-                      const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev) {
+                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev) {
   if (m.Nx < 2 || m.Ny < 2 || m.Nx > 32768 || m.Ny > 32768) return false;
   const bool halo = below_gap || above_gap;
   const unsigned long long ny1 = m.Ny - 1, nx1 = m.Nx - 1, nz1 = m.Nz - 1;
-  const unsigned long long g1 = nz1 * nz1 + ny1 * ny1;  // largest finite value after pass 1
-  // "small" family: 16-bit (s, dz) hull entries and 16-bit (dy, dz) intermediate, 32-bit cross products
-  const bool small = !halo && m.Nz <= 254 && bits_of(ny1) + bits_of(nz1) <= 16 && bits_of(nx1) + bits_of(g1) <= 32 &&
-                     (ny1 * ny1 + nz1 * nz1) * ny1 < (1ull << 31) && (nx1 * nx1 + g1) * nx1 < (1ull << 31);
+  const unsigned long long g1 = nz1 * nz1 + ny1 * ny1;  // largest finite value after pass 1 (no halo)
+  // "small" family (C1-C3 shapes): 16-bit (s, dz) / 32-bit (s, g) hull entries, 16-bit (dy, dz) intermediate volume,
+  // 32-bit cross products; 8 bands x 32 lanes.  Band-relative sites need at most bits(ceil(N/8) - 1) bits.
+  const int sby8 = bits_of((unsigned)((m.Ny + 7) / 8 - 1)), sbx8 = bits_of((unsigned)((m.Nx + 7) / 8 - 1));
+  const bool small = !halo && bits_of(ny1) + bits_of(nz1) <= 16 && sby8 + bits_of(nz1) <= 16 && sbx8 + bits_of(g1) <= 32 &&
+                     (ny1 * ny1 + nz1 * nz1) * ny1 < (1ull << 31) && (nx1 * nx1 + g1) * nx1 < (1ull << 31) &&
+                     cfg_of(smem_y<8, 32, uint16_t>(m), 256).blocks_per_sm >= 2 && cfg_of(smem_x<8, 32, uint32_t>(m), 256).blocks_per_sm >= 2;
+  if (ev) cudaEventRecord(ev[0], stream);
+  bool ok;
   if (small) {
     using TY = PassY<uint16_t, int32_t>;
     using TX = PassX<uint32_t, int32_t>;
-    if (launch_family<8, 32, TY, TX, uint8_t, uint16_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, nullptr, nullptr, stream, ev)) return true;
+    ok = launch_y<8, 32, TY, uint16_t>(m, tmp, plane_empty, nullptr, nullptr, stream);
+    if (ev) cudaEventRecord(ev[1], stream);
+    ok = ok && launch_x<8, 32, TX, uint16_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream);
+  } else {
+    // "large" family: int32 intermediate, 64-bit cross products, 32-bit (s, dz) entries (z distances < 65535, as in the
+    // seven-kernel pipeline's wide mode), (s, g) entries of 32 bits when 6..8 bits of band-relative site + g fit, else 64;
+    // tile shape chosen per pass
+    using GY = PassY<uint32_t, long long>;
+    using GX4 = PassX<uint32_t, long long>;
+    using GX8 = PassX<uint64_t, long long>;
+    const int shy = pick_shape<uint32_t, true>(m);
+    // g after pass 1 is < 2^29 by construction (kDistInf); 32-bit entries need the real bound
+    // (with a halo the z distances reach into the neighbouring slabs: dz_bound = the caller's bound on them, 0 = unknown)
+    const unsigned long long dzb = (unsigned long long)std::max(dz_bound, m.Nz);
+    const unsigned long long gmax = !halo ? g1 : (dz_bound > 0 ? std::min<unsigned long long>(dzb * dzb + ny1 * ny1, (1ull << 29) - 1) : (1ull << 29) - 1);
+    auto sbx = [&](int nb) { return bits_of((unsigned)((m.Nx + nb - 1) / nb - 1)); };
+    int shx = pick_shape<uint32_t, false>(m);
+    bool x32 = shx != 0 && sbx(shx == 1 ? 8 : shx == 2 ? 16 : 32) + bits_of(gmax) <= 32;
+    if (!x32) shx = pick_shape<uint64_t, false>(m);
+    if (!shy || !shx) return false;
+    ok = shy == 1   ? launch_y<8, 32, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+         : shy == 2 ? launch_y<16, 16, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+                    : launch_y<32, 8, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
+    if (ev) cudaEventRecord(ev[1], stream);
+    if (x32)
+      ok = ok && (shx == 1   ? launch_x<8, 32, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
+                  : shx == 2 ? launch_x<16, 16, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
+                             : launch_x<32, 8, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream));
+    else
+      ok = ok && (shx == 1   ? launch_x<8, 32, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
+                  : shx == 2 ? launch_x<16, 16, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
+                             : launch_x<32, 8, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream));
   }
-  // generic family: 32-bit (s, dz) / 64-bit (s, g) entries, int32 intermediate, 64-bit cross products; z distances < 65535
-  if (bits_of(ny1) > 16 || bits_of(nx1) > 16) return false;
-  using GY = PassY<uint32_t, long long>;
-  using GX = PassX<uint64_t, long long>;
-  if (launch_family<8, 32, GY, GX, uint16_t, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, below_gap, above_gap, stream, ev)) return true;
-  if (launch_family<16, 16, GY, GX, uint16_t, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, below_gap, above_gap, stream, ev)) return true;
-  if (launch_family<32, 8, GY, GX, uint16_t, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, below_gap, above_gap, stream, ev)) return true;
-  return false;
+  if (ev) cudaEventRecord(ev[2], stream);
+  return ok;
 }
 
 }  // namespace b200

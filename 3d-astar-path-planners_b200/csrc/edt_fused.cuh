@@ -49,10 +49,12 @@ struct Vtx {
   uint32_t p;
   typename Tr::X c;
 };
+// entries hold the site RELATIVE to their band's first site (SB = bits of band length - 1): 6 bits for 64-site bands,
+// which is what lets a 16-bit (pass 1) / 32-bit (pass 2) entry carry the payload of grids as large as 2048^2 x 512
 template <class Tr>
-EDT_HD Vtx<Tr> unpack(typename Tr::E e, int SB) {
+EDT_HD Vtx<Tr> unpack(typename Tr::E e, int SB, int sbase) {
   Vtx<Tr> v;
-  v.s = (int)((uint32_t)e & ((1u << SB) - 1u));
+  v.s = (int)((uint32_t)e & ((1u << SB) - 1u)) + sbase;
   v.p = (uint32_t)(e >> SB);
   v.c = (typename Tr::X)v.s * v.s + Tr::g_of(v.p);
   return v;
@@ -76,23 +78,26 @@ template <class Tr>
 struct HullBuilder {
   using E = typename Tr::E;
   using X = typename Tr::X;
-  E* st;
-  int W, SB, q;
-  int sA, sB;
-  X cA, cB;
-  EDT_HD void init(E* st_, int W_, int SB_) { st = st_; W = W_; SB = SB_; q = 0; sA = sB = 0; cA = cB = 0; }
+  E* top;      // slot of the top entry B (one stride below the band's first slot while the stack is empty)
+  int W, SB, sbase, q;
+  int sB, dS;  // top entry's site, and its distance to the entry A below it (valid while q >= 2)
+  X cB, dC;    // likewise for c: A is recovered as (sB - dS, cB - dC), so a pop needs no copy of A
+  EDT_HD void init(E* st_, int W_, int SB_, int sbase_) { top = st_ - W_; W = W_; SB = SB_; sbase = sbase_; q = 0; sB = dS = 0; cB = dC = 0; }
   EDT_HD void push(int u, uint32_t p) {
     const X cu = (X)u * u + Tr::g_of(p);
-    while (q >= 2 && drops<X>(sA, cA, sB, cB, u, cu)) {
+    // B is on or above the segment A--C  <=>  (cB - cA) (u - sB) >= (cu - cB) (sB - sA)
+    while (q >= 2 && dC * (X)(u - sB) >= (cu - cB) * (X)dS) {
       --q;
-      sB = sA; cB = cA;
+      top -= W;
+      sB -= dS; cB -= dC;
       if (q >= 2) {
-        const Vtx<Tr> a = unpack<Tr>(st[(q - 2) * W], SB);
-        sA = a.s; cA = a.c;
+        const Vtx<Tr> a = unpack<Tr>(top[-W], SB, sbase);
+        dS = sB - a.s; dC = cB - a.c;
       }
     }
-    st[q * W] = (E)((E)(uint32_t)u | ((E)p << SB));
-    sA = sB; cA = cB;
+    top += W;
+    *top = (E)((E)(uint32_t)(u - sbase) | ((E)p << SB));
+    dS = u - sB; dC = cu - cB;
     sB = u; cB = cu;
     ++q;
   }
@@ -110,7 +115,7 @@ struct LineHull {
   const E* st;
   uint32_t* rng;
   int W, SB, BL;
-  EDT_HD Vtx<Tr> at(int b, int i) const { return unpack<Tr>(st[(b * BL + i) * W], SB); }
+  EDT_HD Vtx<Tr> at(int b, int i) const { return unpack<Tr>(st[(b * BL + i) * W], SB, b * BL); }
   EDT_HD uint32_t r(int b) const { return rng[b * W]; }
 };
 
@@ -193,11 +198,14 @@ EDT_HD int hull_offsets(const uint32_t* rng, uint16_t* off, int W, int NB) {
 template <class Tr>
 struct HullCursor {
   using X = typename Tr::X;
+  using E = typename Tr::E;
   const LineHull<Tr>* L;
   const uint16_t* off;
   int NB, T;
-  int v;        // virtual index of the current vertex
-  int b, i, hi; // its band, entry, and the band's last surviving entry
+  int v;            // virtual index of the current vertex
+  const E* ep;      // its stack slot
+  int before, after;  // surviving entries of its band below / above it
+  int sbase;          // first site of its band
   // band of virtual index x: largest b with off[b] <= x (lands on a non-empty band for x < T)
   EDT_HD void seek(int x) {
     int lo_b = 0, hi_b = NB - 1;
@@ -206,116 +214,157 @@ struct HullCursor {
       if ((int)off[mid * L->W] <= x) lo_b = mid; else hi_b = mid - 1;
     }
     const uint32_t r = L->r(lo_b);
-    v = x; b = lo_b; i = rng_lo(r) + (x - (int)off[lo_b * L->W]); hi = rng_hi(r);
+    before = x - (int)off[lo_b * L->W];
+    const int i = rng_lo(r) + before;
+    after = rng_hi(r) - i;
+    sbase = lo_b * L->BL;
+    ep = L->st + (sbase + i) * L->W;
+    v = x;
   }
-  EDT_HD Vtx<Tr> cur() const { return L->at(b, i); }
+  EDT_HD Vtx<Tr> cur() const { return unpack<Tr>(*ep, L->SB, sbase); }
   EDT_HD void next() {  // v + 1 < T
-    if (i < hi) { ++i; ++v; }
+    if (after > 0) { ep += L->W; --after; ++before; ++v; }
     else seek(v + 1);
+  }
+  EDT_HD void prev() {  // v > 0
+    if (before > 0) { ep -= L->W; --before; ++after; --v; }
+    else seek(v - 1);
   }
 };
 
+// emit(d, payload, value) is called once per site in increasing order, d = u - s for a minimising site s and
+// value = d^2 + g_of(payload); the caller keeps its own output cursor.  hint = virtual index to start the search for the
+// tangent vertex of u0 from (the junction of the caller's own band: the nearest obstacle is usually close).
 template <class Tr, class Emit>
-EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T, int u0, int u1, const Emit& emit) {
+EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T, int u0, int u1, int hint, Emit&& emit) {
   using X = typename Tr::X;
   HullCursor<Tr> cu;
   cu.L = &L; cu.off = off; cu.NB = NB; cu.T = T;
-  // tangent vertex of u0: first k whose successor is not strictly better
+  const X two_u0 = (X)(2 * u0);
+  // tangent vertex of u0 = first k whose successor is not strictly better:  val(k+1) < val(k)  <=>  dc < 2 u0 ds.
+  // A few steps from the hint, else bisection over the side that is left.
   int lo = 0, hi = T - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    cu.seek(mid);
-    const Vtx<Tr> a = cu.cur();
-    cu.next();
-    const Vtx<Tr> b = cu.cur();
-    if (b.c - a.c < (X)(2 * u0) * (X)(b.s - a.s)) lo = mid + 1; else hi = mid;
-  }
-  cu.seek(lo);
-  Vtx<Tr> k = cu.cur(), n = k;
-  bool has_n = cu.v + 1 < T;
-  if (has_n) { cu.next(); n = cu.cur(); }
-  for (int u = u0; u < u1; ++u) {
-    while (has_n && n.c - k.c <= (X)(2 * u) * (X)(n.s - k.s)) {
-      k = n;
-      has_n = cu.v + 1 < T;
-      if (has_n) { cu.next(); n = cu.cur(); }
+  cu.seek(hint < T ? hint : T - 1);
+  Vtx<Tr> k = cu.cur();
+  {
+    int steps = 0;
+    bool moved = false, resolved = false;
+    while (cu.v + 1 < T) {  // right while the successor is strictly better
+      HullCursor<Tr> nx = cu;
+      nx.next();
+      const Vtx<Tr> b = nx.cur();
+      if (!(b.c - k.c < two_u0 * (X)(b.s - k.s))) { resolved = true; break; }
+      cu = nx; k = b; moved = true;
+      if (++steps == 6) break;
     }
-    const int d = u - k.s;
-    emit(u, k.s, k.p, (X)d * d + Tr::g_of(k.p));
+    if (cu.v + 1 >= T) resolved = true;
+    if (!resolved) lo = cu.v;                 // successor still better: the answer is at or right of here
+    else if (moved) lo = hi = cu.v;
+    else {                                    // left while the predecessor is at least as good
+      resolved = false;
+      steps = 0;
+      while (cu.v > 0) {
+        HullCursor<Tr> pv = cu;
+        pv.prev();
+        const Vtx<Tr> a = pv.cur();
+        if (k.c - a.c < two_u0 * (X)(k.s - a.s)) { resolved = true; break; }
+        cu = pv; k = a;
+        if (++steps == 6) break;
+      }
+      if (cu.v == 0) resolved = true;
+      if (resolved) lo = hi = cu.v; else hi = cu.v;
+    }
+  }
+  if (lo < hi) {
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      cu.seek(mid);
+      const Vtx<Tr> a = cu.cur();
+      cu.next();
+      const Vtx<Tr> b = cu.cur();
+      if (b.c - a.c < two_u0 * (X)(b.s - a.s)) lo = mid + 1; else hi = mid;
+    }
+    cu.seek(lo);
+    k = cu.cur();
+  }
+  Vtx<Tr> n = k;
+  int left = T - 1 - cu.v;  // vertices after the current one
+  // the successor n takes over at the first u with  n.c - k.c <= 2 u (n.s - k.s):  acc(u) = 2 u ds - dc >= 0,
+  // acc(u + 1) = acc(u) + 2 ds; with no successor acc stays negative
+  X acc = -1, step = 0;
+  if (left > 0) {
+    cu.next(); n = cu.cur();
+    step = (X)(2 * (n.s - k.s));
+    acc = step * (X)u0 - (n.c - k.c);
+  }
+  int d = u0 - k.s;
+  uint32_t kp = k.p;
+  X g = Tr::g_of(kp);
+  for (int u = u0; u < u1; ++u) {
+    while (acc >= 0) {
+      const int ks = n.s;
+      const X kc = n.c;
+      kp = n.p;
+      --left;
+      d = u - ks;
+      g = Tr::g_of(kp);
+      if (left > 0) {
+        cu.next(); n = cu.cur();
+        step = (X)(2 * (n.s - ks));
+        acc = step * (X)u - (n.c - kc);
+      } else {
+        acc = -1; step = 0;
+      }
+    }
+    emit(d, kp, (X)d * d + g);
+    ++d;
+    acc += step;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// z distances of W consecutive voxels [z0, z0 + W) of one column from its bit words (W divides 32).
-// below_gap / above_gap: z-slab halo (distance from the slab's first / last plane to the nearest occupied voxel in
-// the slabs below / above, <= 0 when none).  out[j] = kNone when the column (and the halo) holds no obstacle.
+// z distance from the bit words of a column (z contiguous: bit z & 31 of word z >> 5).
+//   column_outside(): nearest occupied z strictly below / above word wi, looking at the other words of the column and
+//     at the z-slab halo (below_gap / above_gap: distance from the slab's first / last plane to the nearest occupied
+//     voxel in the slabs below / above, <= 0 when none); packed as two int32 "far" sentinels when there is none.
+//   site_dz(): distance of bit `bi` of the own word to the nearest occupied voxel of the column; >= kDzNone = none.
 // ---------------------------------------------------------------------------------------------------
-template <int W, class DZ>
-EDT_HD void column_dz(const uint32_t* col, int wz, int Nz, int z0, int below_gap, int above_gap, DZ* out, int out_stride) {
-  constexpr int kNone = sizeof(DZ) == 1 ? 255 : 65535;
-  const int wi = z0 >> 5, o = z0 & 31;
-  const uint32_t own = col[wi];
-  int below = -(1 << 20), above = 1 << 20;
-  if (below_gap > 0) below = -below_gap;
-  if (above_gap > 0) above = Nz - 1 + above_gap;
-  {
-    const uint32_t lowbits = o ? (own & ((1u << o) - 1u)) : 0u;
-    if (lowbits) {
+constexpr int kDzNone = 65535;
+constexpr int kFar = 1 << 20;
+EDT_HD int edt_clz(uint32_t v) {
 #ifdef __CUDA_ARCH__
-      below = (wi << 5) + 31 - __clz(lowbits);
+  return __clz((int)v);
 #else
-      below = (wi << 5) + 31 - __builtin_clz(lowbits);
+  return __builtin_clz(v);
 #endif
-    } else {
-      for (int j = wi - 1; j >= 0; --j) {
-        const uint32_t v = col[j];
-        if (v) {
+}
+EDT_HD int edt_ffs(uint32_t v) {
 #ifdef __CUDA_ARCH__
-          below = (j << 5) + 31 - __clz(v);
+  return __ffs((int)v);
 #else
-          below = (j << 5) + 31 - __builtin_clz(v);
+  return __builtin_ffs((int)v);
 #endif
-          break;
-        }
-      }
-    }
-    const uint32_t highbits = (o + W < 32) ? (own >> (o + W)) : 0u;
-    if (highbits) {
-#ifdef __CUDA_ARCH__
-      above = z0 + W + __ffs(highbits) - 1;
-#else
-      above = z0 + W + __builtin_ffs(highbits) - 1;
-#endif
-    } else {
-      for (int j = wi + 1; j < wz; ++j) {
-        const uint32_t v = col[j];
-        if (v) {
-#ifdef __CUDA_ARCH__
-          above = (j << 5) + __ffs(v) - 1;
-#else
-          above = (j << 5) + __builtin_ffs(v) - 1;
-#endif
-          break;
-        }
-      }
-    }
+}
+EDT_HD void column_outside(const uint32_t* col, int wz, int Nz, int wi, int below_gap, int above_gap, int* below, int* above) {
+  int lo = -kFar, hi = kFar;
+  if (below_gap > 0) lo = -below_gap;
+  if (above_gap > 0) hi = Nz - 1 + above_gap;
+  for (int j = wi - 1; j >= 0; --j) {
+    const uint32_t v = col[j];
+    if (v) { lo = (j << 5) + 31 - edt_clz(v); break; }
   }
-  const uint32_t bits = own >> o;
-  int up[W];
-  int last = below;
-#pragma unroll
-  for (int j = 0; j < W; ++j) {
-    if ((bits >> j) & 1u) last = z0 + j;
-    up[j] = z0 + j - last;
+  for (int j = wi + 1; j < wz; ++j) {
+    const uint32_t v = col[j];
+    if (v) { hi = (j << 5) + edt_ffs(v) - 1; break; }
   }
-  int nxt = above;
-#pragma unroll
-  for (int j = W - 1; j >= 0; --j) {
-    if ((bits >> j) & 1u) nxt = z0 + j;
-    int d = up[j] < nxt - (z0 + j) ? up[j] : nxt - (z0 + j);
-    if (d > kNone) d = kNone;
-    out[j * out_stride] = (DZ)d;
-  }
+  *below = lo; *above = hi;
+}
+EDT_HD int site_dz(uint32_t own, int bi, int z, int below, int above) {
+  const uint32_t lowm = own & (0xffffffffu >> (31 - bi));  // bits <= bi
+  const uint32_t highm = own & (0xffffffffu << bi);        // bits >= bi
+  const int dn = lowm ? bi - (31 - edt_clz(lowm)) : z - below;
+  const int up = highm ? edt_ffs(highm) - 1 - bi : above - z;
+  return dn < up ? dn : up;
 }
 
 }  // namespace edtf

@@ -36,7 +36,7 @@ void launch_cost_lut(uint16_t* lut, int lut_n, double res, double d_safe, cudaSt
 // ---- edt_fused.cu: two shared-memory-staged kernels; false when no configuration fits the grid
 size_t edt_fused_plane_flags_bytes(const MapDev& m);
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-                      const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream, cudaEvent_t* ev);
+                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev);
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
 
 // ---- search_kernels.cu

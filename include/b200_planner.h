@@ -183,6 +183,10 @@ int b200_map_edt_pipeline_used(const b200_map_t* map);
  * b200_map_column_extents publishes a slab's lowest / highest occupied z per column (-1 = empty column); the host
  * all-gathers those (NCCL/NVLink) and derives the gaps (shard.py: slab_gaps). NULL gap arrays = no neighbour. */
 int b200_map_column_extents(b200_map_t* map, int32_t* lowest_z, int32_t* highest_z, int32_t on_device);
+/* Optional hint for the slab build: the height (voxels) of the whole stacked grid, i.e. a bound on every gap + slab
+ * height.  It only selects narrower hull entries (32 instead of 64 bits) in the shared-memory kernels; results do not
+ * depend on it as long as the bound holds.  0 = unknown (default). */
+int b200_map_set_slab_extent(b200_map_t* map, int32_t total_nz);
 int b200_map_build_edt_slab(b200_map_t* map, double d_safe, const int32_t* below_gap, const int32_t* above_gap,
                             int32_t on_device);
 int b200_map_download_dist2(b200_map_t* map, int32_t* dst);

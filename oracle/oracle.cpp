@@ -1233,6 +1233,30 @@ void orc_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t
   OMap* m = (OMap*)h;
   for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)get_inflate_occupancy(*m, V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
 }
+// grid_map.h:310-321 setOccupied(Vector3d): inflated buffer <- 1 where isInMap
+void orc_map_set_occupied(void* h, const double* pos, int64_t n) {
+  OMap& m = *(OMap*)h;
+  for (int64_t i = 0; i < n; ++i) {
+    const V3 p{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    if (!is_in_map(m, p)) continue;
+    int id[3];
+    pos_to_index(m, p, id);
+    m.inflate[(size_t)id[0] * m.N[1] * m.N[2] + (size_t)id[1] * m.N[2] + id[2]] = 1;
+  }
+}
+// grid_map.h:323-337 setOccupancy(Vector3d, double): occupancy_buffer_ <- occ, values other than 0 / 1 rejected
+void orc_map_set_occupancy(void* h, const double* pos, const double* occ, int64_t n) {
+  OMap& m = *(OMap*)h;
+  depth_alloc(m);
+  for (int64_t i = 0; i < n; ++i) {
+    if (occ[i] != 1 && occ[i] != 0) continue;
+    const V3 p{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    if (!is_in_map(m, p)) continue;
+    int id[3];
+    pos_to_index(m, p, id);
+    m.occ[to_address(m, id[0], id[1], id[2])] = occ[i];
+  }
+}
 void orc_map_is_in_map(void* h, const double* pos, int64_t n, uint8_t* out) {
   OMap* m = (OMap*)h;
   for (int64_t i = 0; i < n; ++i) out[i] = is_in_map(*m, V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});

@@ -107,6 +107,8 @@ def lib():
         L.orc_map_raycast_num.restype = C.c_int
         L.orc_map_depth_stats.argtypes = [vp, vp]
         L.orc_map_get_occupancy.argtypes = [vp, vp, i64, vp]
+        L.orc_map_set_occupied.argtypes = [vp, vp, i64]
+        L.orc_map_set_occupancy.argtypes = [vp, vp, vp, i64]
         L.orc_map_export_occupancy_cloud.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, i64]
         L.orc_map_export_occupancy_cloud.restype = i64
         L.orc_los_batch_dda.argtypes = [vp, vp, vp, i64, vp, vp]
@@ -214,6 +216,15 @@ class OracleMap:
         out = np.empty(len(pos), dtype=np.int8)
         lib().orc_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
         return out
+
+    def set_occupied(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        lib().orc_map_set_occupied(self.h, _ptr(pos), len(pos))
+
+    def set_occupancy(self, pos, occ):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        occ = np.ascontiguousarray(np.broadcast_to(np.asarray(occ, dtype=np.float64), (len(pos),)))
+        lib().orc_map_set_occupancy(self.h, _ptr(pos), _ptr(occ), len(pos))
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

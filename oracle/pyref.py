@@ -52,6 +52,8 @@ def lib():
         L.ref_map_proj_points.restype = C.c_int
         L.ref_map_set_raycast_num.argtypes = [vp, C.c_int]
         L.ref_map_get_occupancy.argtypes = [vp, vp, i64, vp]
+        L.ref_map_set_occupied.argtypes = [vp, vp, i64]
+        L.ref_map_set_occupancy.argtypes = [vp, vp, vp, i64]
         L.ref_map_publish_occupancy.argtypes = [vp, C.c_int, vp, i64]
         L.ref_map_publish_occupancy.restype = i64
         L.ref_ray_cells.argtypes = [dp, dp, vp, i64]
@@ -163,6 +165,17 @@ class RefMap:
         out = np.empty(len(pos), dtype=np.int8)
         lib().ref_map_get_occupancy(self.h, _ptr(pos), len(pos), _ptr(out))
         return out
+
+    def set_occupied(self, pos):
+        """GridMap::setOccupied (grid_map.h:310-321), one call per position in order."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        lib().ref_map_set_occupied(self.h, _ptr(pos), len(pos))
+
+    def set_occupancy(self, pos, occ):
+        """GridMap::setOccupancy (grid_map.h:323-337), one call per position in order."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        occ = np.ascontiguousarray(np.broadcast_to(np.asarray(occ, dtype=np.float64), (len(pos),)))
+        lib().ref_map_set_occupancy(self.h, _ptr(pos), _ptr(occ), len(pos))
 
     def get_inflate_occupancy(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)

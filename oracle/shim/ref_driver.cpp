@@ -200,6 +200,15 @@ void ref_map_get_inflate_occupancy(void* h, const double* pos, int64_t n, int8_t
   GridMap& g = *((RefMap*)h)->gm;
   for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)g.getInflateOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
 }
+// GridMap::setOccupied / setOccupancy (grid_map.h:310-337), one call per position, in order
+void ref_map_set_occupied(void* h, const double* pos, int64_t n) {
+  GridMap& g = *((RefMap*)h)->gm;
+  for (int64_t i = 0; i < n; ++i) g.setOccupied(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+}
+void ref_map_set_occupancy(void* h, const double* pos, const double* occ, int64_t n) {
+  GridMap& g = *((RefMap*)h)->gm;
+  for (int64_t i = 0; i < n; ++i) g.setOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), occ[i]);
+}
 void ref_map_is_in_map(void* h, const double* pos, int64_t n, uint8_t* out) {
   GridMap& g = *((RefMap*)h)->gm;
   for (int64_t i = 0; i < n; ++i) out[i] = g.isInMap(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));

@@ -35,3 +35,4 @@ if not ncu:
     if not np.array_equal(res[0][0], res[1][0]):
         bad = np.argwhere(res[0][0] != res[1][0])
         print("mismatches:", len(bad), bad[:5], res[0][0][tuple(bad[0])], res[1][0][tuple(bad[0])])
+gm.close()

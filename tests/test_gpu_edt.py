@@ -111,3 +111,102 @@ def test_z_slab_edt_equals_full_transform(b200, po, splits):
     assert np.array_equal(np.concatenate(got_d2, axis=2), want_d2)
     assert np.array_equal(np.concatenate(got_cq, axis=2), want_cq)
     assert (want_d2[:, :, 50] > 100).any()      # the band really is far from everything
+
+
+def _sparse_grid(rng, dims, n_occ, empty_planes=()):
+    grid = np.zeros(dims, dtype=np.uint8)
+    idx = tuple(rng.integers(0, d, n_occ) for d in dims)
+    grid[idx] = 1
+    for ax, i in empty_planes:
+        sl = [slice(None)] * 3
+        sl[ax] = i
+        grid[tuple(sl)] = 0
+    return grid
+
+
+# every tile shape / entry width the fused kernels instantiate: (dims, what it exercises)
+FUSED_SHAPES = [
+    ((96, 130, 50), "small family: 8 bands x 32 lanes, 16-bit entries, packed 16-bit intermediate, odd band lengths"),
+    ((40, 64, 128), "small family, 4 full z words, bulk-copied plane"),
+    ((1024, 60, 40), "large family: pass 2 lines of 1024 (16 x 16 tile), 32-bit (s, g) entries"),
+    ((24, 1500, 40), "large family: pass 1 lines of 1500 (16 x 16 tile), own-word staging"),
+    ((20, 3000, 33), "large family: pass 1 lines of 3000 (32 x 8 tile)"),
+    ((3000, 20, 33), "large family: pass 2 lines of 3000 (32 x 8 tile)"),
+    ((3, 2, 5), "degenerate: fewer sites than bands"),
+]
+
+
+@pytest.mark.parametrize("dims,what", FUSED_SHAPES, ids=[str(d) for d, _ in FUSED_SHAPES])
+def test_fused_edt_equals_hbm_stack_pipeline_and_oracle(b200, po, dims, what):
+    """The two-kernel shared-memory EDT and the seven-kernel HBM-stack EDT are independent implementations (convex-hull
+    stack without separators vs Meijster's integer separators); both must equal the CPU lower envelope bit for bit."""
+    rng = np.random.default_rng(sum(dims))
+    res = 0.5
+    size = tuple(d * res for d in dims)
+    for n_occ, empties in [(max(2, int(np.prod(dims)) // 4000), ((0, dims[0] // 2), (1, 0))), (1, ()), (0, ())]:
+        grid = _sparse_grid(rng, dims, n_occ, empties)
+        gm = b200.GridMap(size, res, origin=(0, 0, 0))
+        gm.set_inflate(grid)
+        gm.build_edt(d_safe=4.0)
+        assert gm.edt_pipeline_used() == "fused", what
+        d2, cq = gm.dist2().copy(), gm.costq().copy()
+        gm.set_edt_pipeline(1)
+        gm.build_edt(d_safe=4.0)
+        assert gm.edt_pipeline_used() == "hbm-stack"
+        assert np.array_equal(d2, gm.dist2()) and np.array_equal(cq, gm.costq()), what
+        om = po.OracleMap((0, 0, 0), size, res)
+        om.set_inflate(grid)
+        d2o, cqo = om.build_edt(d_safe=4.0, nthreads=8)
+        assert np.array_equal(d2, d2o) and np.array_equal(cq, cqo), what
+        if n_occ == 0:
+            assert (d2 == 1 << 29).all() and (cq == 0).all()
+
+
+def test_fused_edt_slab_with_extent_hint(b200):
+    """z-slab build with the total-height hint (32-bit hull entries in pass 2) == without it == the unsharded transform."""
+    from astar_planners_b200 import shard
+    rng = np.random.default_rng(11)
+    dims, splits, res = (600, 36, 96), (32, 64), 0.5
+    grid = _sparse_grid(rng, dims, 300)
+    grid[:, :, 30:60] = 0
+    full = b200.GridMap(tuple(d * res for d in dims), res, origin=(0, 0, 0))
+    full.set_inflate(grid)
+    full.build_edt(d_safe=3.0)
+    want = full.dist2()
+    for hint in (0, dims[2]):
+        slabs, z0 = [], 0
+        for nz in splits:
+            m = b200.GridMap((dims[0] * res, dims[1] * res, nz * res), res, origin=(0, 0, z0 * res))
+            m.set_inflate(np.ascontiguousarray(grid[:, :, z0:z0 + nz]))
+            m.set_slab_extent(hint)
+            slabs.append(m)
+            z0 += nz
+        ext = [m.column_extents() for m in slabs]
+        got = []
+        for r, m in enumerate(slabs):
+            below, above = shard.slab_gaps([e[0] for e in ext], [e[1] for e in ext], list(splits), r)
+            m.build_edt_slab(3.0, below if r > 0 else None, above if r < len(slabs) - 1 else None)
+            assert m.edt_pipeline_used() == "fused"
+            got.append(m.dist2())
+        assert np.array_equal(np.concatenate(got, axis=2), want)
+
+
+def test_distance_field_is_invalidated_by_grid_writes(b200, po, synth):
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    gm.build_edt(d_safe=1.0)
+    assert gm.has_distance_field(1.0) and not gm.has_distance_field(2.0)
+    gm.setOccupied([(0.0, 0.0, 1.0)])
+    assert not gm.has_distance_field(1.0)
+    with pytest.raises(b200.B200Error):
+        gm.dist2()
+    pl = b200.Planner("costastar", resolution=0.1, cost_weight=1.0)
+    pl.setGridMap(gm)
+    with pytest.raises(b200.B200Error):
+        pl.findPaths(np.zeros((1, 3)), np.ones((1, 3)))
+    gm.build_edt(d_safe=1.0)
+    assert gm.getInflateOccupancy([(0.0, 0.0, 1.0)])[0] == 1 and gm.dist2()[tuple(gm.posToIndex([(0.0, 0.0, 1.0)])[0])] == 0
+    for mutate in (lambda: gm.resetBuffer(), lambda: gm.cloudCallback(synth.pack_cloud(synth.config_cloud("C3")), (0.0, 0.0, 1.0)),
+                   lambda: gm.set_inflate(gm.inflate())):
+        gm.build_edt(d_safe=1.0)
+        mutate()
+        assert not gm.has_distance_field(1.0)

@@ -142,3 +142,27 @@ def test_publish_map_inflate_matches_oracle(b200, po, synth):
                 assert len(got) == n
                 assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
         assert len(gm.publishMapInflate(cap=10)) == 10      # truncated buffer: first 10 points, still ordered
+
+
+def test_set_occupied_and_set_occupancy_match_oracle(b200, po):
+    """GridMap::setOccupied / setOccupancy (grid_map.h:310-337), batched; the oracle is pinned to the reference's own
+    methods in test_oracle_vs_ref.py (same position generator)."""
+    from util import set_positions as _set_positions
+    size, res, gh = (6.4, 4.8, 3.2), 0.1, -0.01
+    origin = (-size[0] / 2, -size[1] / 2, gh)
+    gm = b200.GridMap(size, res, origin=origin, ground_height=gh)
+    om = po.OracleMap(origin, size, res, 0.099, (1e3, 1e3, 1e3), gh)
+    gm.set_depth_params()
+    om.set_depth_params()
+    pos, occ = _set_positions(5, origin, size, 4000)
+    gm.setOccupied(pos[:2000])
+    om.set_occupied(pos[:2000])
+    assert np.array_equal(gm.inflate(), om.inflate())
+    gm.setOccupancy(pos, occ)
+    om.set_occupancy(pos, occ)
+    assert np.array_equal(gm.occupancy(), om.occupancy())
+    assert np.array_equal(gm.getOccupancy(pos), om.get_occupancy(pos))
+    # a later depth frame still works on the same state arrays (the per-voxel scratch was left clean)
+    gm.setOccupancy(pos[:10], 1.0)
+    om.set_occupancy(pos[:10], 1.0)
+    assert np.array_equal(gm.occupancy(), om.occupancy())

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import pyref as pr
+from util import set_positions as _set_positions
 
 pytestmark = pytest.mark.skipif(not pr.available(), reason="/root/reference not present (GPU box): golden vectors cover this")
 
@@ -87,3 +88,19 @@ def test_voxel_traversal_matches_the_reference_raycaster(po):
     for i in range(len(a)):
         got, want = po.ray_cells(a[i], b[i]), pr.ray_cells(a[i], b[i])
         assert np.array_equal(got, want), (i, a[i], b[i], len(got), len(want))
+
+
+def test_set_occupied_and_set_occupancy_match_reference(po):
+    size, res, gh = (6.4, 4.8, 3.2), 0.1, -0.01
+    origin = (-size[0] / 2, -size[1] / 2, gh)
+    rm = pr.RefMap(size, res, 0.099, (1e3, 1e3, 1e3), gh)
+    om = po.OracleMap(origin, size, res, 0.099, (1e3, 1e3, 1e3), gh)
+    om.set_depth_params()
+    pos, occ = _set_positions(5, origin, size, 4000)
+    rm.set_occupied(pos[:2000])
+    om.set_occupied(pos[:2000])
+    assert np.array_equal(rm.inflate(), om.inflate()) and rm.inflate().sum() > 1000
+    rm.set_occupancy(pos, occ)
+    om.set_occupancy(pos, occ)
+    a, b = rm.occupancy(), om.occupancy()
+    assert np.array_equal(a, b) and (a == 1.0).sum() > 500 and (a == 0.0).sum() > 200

@@ -26,3 +26,16 @@ def assert_results_equal(res_gpu, res_cpu, fields=("solved", "status", "n_path",
         a, b = res_gpu[f].view(np.uint64), res_cpu[f].view(np.uint64)
         bad = np.nonzero((a != b).reshape(len(res_gpu), -1).any(axis=1))[0]
         assert len(bad) == 0, f"{f}: {len(bad)} bit mismatches, first {bad[:5]} gpu={res_gpu[f][bad[:5]]} cpu={res_cpu[f][bad[:5]]}"
+
+
+def set_positions(seed, origin, size, n):
+    """positions inside, on the +-1e-4 rim, outside, and repeated voxels; occ values incl. invalid ones"""
+    rng = np.random.default_rng(seed)
+    o, s = np.asarray(origin), np.asarray(size)
+    pos = o - 0.3 + rng.random((n, 3)) * (s + 0.6)
+    pos[: n // 8] = pos[n // 8: n // 4]                       # repeats: the last call on a voxel wins
+    pos[-3] = o + 1e-4
+    pos[-2] = np.nextafter(o + 1e-4, 10.0)
+    pos[-1] = o + s - 1e-4
+    occ = rng.choice([0.0, 1.0, 1.0, 0.5, -1.0, 2.0], n)
+    return pos, occ
