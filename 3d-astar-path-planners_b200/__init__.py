@@ -107,6 +107,9 @@ ABI = [
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
     ("b200_map_set_slab_extent", C.c_int, [_vp, _i32]),
+    ("b200_map_device_fields", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    ("b200_map_column_extents16", C.c_int, [_vp, _vp, _i32]),
+    ("b200_map_slab_gaps", C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     ("b200_map_download_dist2", C.c_int, [_vp, _vp]),
     ("b200_map_download_costq", C.c_int, [_vp, _vp]),
     ("b200_map_download_cost", C.c_int, [_vp, _vp]),
@@ -407,6 +410,22 @@ class GridMap:
         _ck(lib().b200_map_column_extents(self.h, _ptr(lo), _ptr(hi), 0))
         return lo, hi
 
+    def column_extents16(self, lo_hi=None):
+        """Packed (lowest, highest) int16 pair per column; lo_hi: optional device tensor [Nx, Ny, 2] int16 to fill."""
+        if lo_hi is not None and _is_dev(lo_hi):
+            _ck(lib().b200_map_column_extents16(self.h, _ptr(lo_hi), 1))
+            return lo_hi
+        out = np.empty(self.dims[:2] + (2,), dtype=np.int16)
+        _ck(lib().b200_map_column_extents16(self.h, _ptr(out), 0))
+        return out
+
+    def slab_gaps(self, gathered, slab_nz, rank, below, above):
+        """Device-side halo derivation: gathered = device tensor [P, Nx, Ny, 2] int16 (all-gathered column_extents16),
+        below / above = device int32 [Nx, Ny] outputs for b200_map_build_edt_slab."""
+        nz = np.ascontiguousarray(slab_nz, dtype=np.int32)
+        _ck(lib().b200_map_slab_gaps(self.h, _ptr(gathered), _ptr(nz), len(nz), int(rank), _ptr(below), _ptr(above)))
+        return below, above
+
     def set_slab_extent(self, total_nz):
         """z-slab sharding: height (voxels) of the whole stacked grid — bounds the halo distances (narrower hull entries)."""
         _ck(lib().b200_map_set_slab_extent(self.h, int(total_nz)))
@@ -419,6 +438,21 @@ class GridMap:
             above_gap = None if above_gap is None else np.ascontiguousarray(above_gap, dtype=np.int32)
         self._keep_gaps = (below_gap, above_gap)
         _ck(lib().b200_map_build_edt_slab(self.h, float(d_safe), _ptr(below_gap), _ptr(above_gap), dev))
+
+    def device_fields(self):
+        """(dist2, costq) as zero-copy torch CUDA tensors [Nx, Ny, Nz] (int32 / int16 view of the uint16 cost); None if absent."""
+        import torch
+        d, c = C.c_void_p(), C.c_void_p()
+        _ck(lib().b200_map_device_fields(self.h, C.byref(d), C.byref(c)))
+
+        class _Arr:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr, False), version=3)
+
+        dev = torch.device("cuda", int(self.params.device))
+        td = torch.as_tensor(_Arr(d.value, tuple(self.dims), "<i4"), device=dev) if d.value else None
+        tc = torch.as_tensor(_Arr(c.value, tuple(self.dims), "<i2"), device=dev) if c.value else None
+        return td, tc
 
     def dist2(self):
         out = np.empty(self.dims, dtype=np.int32)

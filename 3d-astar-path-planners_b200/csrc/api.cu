@@ -781,10 +781,46 @@ int b200_map_column_extents(b200_map_t* m, int32_t* lowest, int32_t* highest, in
   return B200_OK;
 }
 
+int b200_map_column_extents16(b200_map_t* m, int16_t* lo_hi, int32_t on_device) {
+  REQUIRE(m && lo_hi, "NULL argument");
+  REQUIRE(m->N[2] <= 32767, "b200_map_column_extents16: slab higher than 32767 voxels");
+  CK(cudaSetDevice(m->prm.device));
+  const size_t cols = (size_t)m->N[0] * m->N[1];
+  if (on_device) {
+    launch_column_extents16(m->d, (short2*)lo_hi, m->stream);
+    m->launches++;
+    CK(cudaGetLastError());
+    return B200_OK;
+  }
+  if (m->stage_out.ensure(cols * 4)) return fail(B200_ERR_NOMEM, "extent staging");
+  launch_column_extents16(m->d, (short2*)m->stage_out.p, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(lo_hi, m->stage_out.p, cols * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_slab_gaps(b200_map_t* m, const int16_t* gathered_lo_hi, const int32_t* slab_nz, int32_t n_slabs, int32_t rank,
+                       int32_t* below_gap, int32_t* above_gap) {
+  REQUIRE(m && gathered_lo_hi && slab_nz && below_gap && above_gap, "NULL argument");
+  REQUIRE(n_slabs >= 1 && n_slabs <= kMaxSlabs && rank >= 0 && rank < n_slabs, "b200_map_slab_gaps: bad slab count / rank");
+  CK(cudaSetDevice(m->prm.device));
+  launch_slab_gaps((const short2*)gathered_lo_hi, slab_nz, n_slabs, rank, (long long)m->N[0] * m->N[1], below_gap, above_gap, m->stream);
+  m->launches++;
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
 static int download_field(b200_map_t* m, const void* src, void* dst, size_t bytes) {
   CK(cudaSetDevice(m->prm.device));
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
+  return B200_OK;
+}
+int b200_map_device_fields(b200_map_t* m, void** dist2, void** costq) {
+  REQUIRE(m && dist2 && costq, "NULL argument");
+  *dist2 = m->has_edt ? (void*)m->d.dist2 : nullptr;
+  *costq = m->has_edt && m->d_safe > 0 ? (void*)m->d.costq : nullptr;
   return B200_OK;
 }
 int b200_map_download_dist2(b200_map_t* m, int32_t* dst) {

@@ -16,6 +16,7 @@
 // HBM traffic per voxel: 1/8 B in, 2 B + 2 B through L2, 4 B + 2 B out; no stack, z-distance or crossover arrays.
 // Per-thread logic: edt_fused.cuh (also compiled for the host by tests/cpu/edt_fused_host_test.cpp).
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "edt_fused.cuh"
@@ -79,7 +80,6 @@ __global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
     edt_fused_y_kernel(MapDev m, const int32_t* __restrict__ below_gap, const int32_t* __restrict__ above_gap, TmpT* __restrict__ tmp,
                        uint8_t* __restrict__ plane_empty, int SB, int BL, int DYB) {
   using E = typename Tr::E;
-  using X = typename Tr::X;
   constexpr bool PACKED = sizeof(TmpT) == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Ny = m.Ny, Nz = m.Nz, wz = m.wz;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
     return;
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
-  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, X v) {
+  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, int32_t v) {
     if (PACKED) *o = (TmpT)((uint32_t)abs(d) | (p << DYB));
     else *o = (TmpT)v;
     o += Nz;
@@ -163,7 +163,6 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
                                                            int32_t* __restrict__ dist2, uint16_t* __restrict__ costq,
                                                            const uint16_t* __restrict__ lut, int lut_n, int SB, int BL, int DYB) {
   using E = typename Tr::E;
-  using X = typename Tr::X;
   constexpr bool PACKED = sizeof(TmpT) == 2;
   constexpr int PF = 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -229,16 +228,16 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
   if (!cq) {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) { *o = (int32_t)v; o += plane; });
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) { *o = (int32_t)v; o += plane; });
   } else if (smem_lut) {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) {
       const int32_t d = (int32_t)v;
       *o = d;
       *cq = slut[min(d, lut_n)];
       o += plane; cq += plane;
     });
   } else {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, X v) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) {
       const int32_t d = (int32_t)v;
       *o = d;
       *cq = d < lut_n ? __ldg(lut + d) : (uint16_t)0;
@@ -279,7 +278,13 @@ bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* b
   const size_t sy = smem_y<NB, W, typename Tr::E>(m);
   const bool bulk = bulk_ok(m);
   auto k = bulk ? edt_fused_y_kernel<NB, W, Tr, TmpT, true> : edt_fused_y_kernel<NB, W, Tr, TmpT, false>;
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sy) != cudaSuccess) { cudaGetLastError(); return false; }
+  static size_t configured[64][2] = {};  // per instantiation and device: the opt-in is a driver call, pay it once per size
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sy > configured[dev & 63][bulk]) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sy) != cudaSuccess) { cudaGetLastError(); return false; }
+    configured[dev & 63][bulk] = sy;
+  }
   const int ztiles = (m.Nz + W - 1) / W, BL = (m.Ny + NB - 1) / NB;
   k<<<(unsigned)(m.Nx * ztiles), NB * W, sy, stream>>>(m, below_gap, above_gap, (TmpT*)tmp, plane_empty, bits_of((unsigned)(BL - 1)), BL,
                                                         bits_of((unsigned)(m.Ny - 1)));
@@ -290,23 +295,35 @@ bool launch_x(const MapDev& m, const void* tmp, const uint8_t* plane_empty, int3
               cudaStream_t stream) {
   const size_t sx = smem_x<NB, W, typename Tr::E>(m);
   auto k = edt_fused_x_kernel<NB, W, Tr, TmpT>;
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx) != cudaSuccess) { cudaGetLastError(); return false; }
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sx > configured[dev & 63]) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx) != cudaSuccess) { cudaGetLastError(); return false; }
+    configured[dev & 63] = sx;
+  }
   const int ztiles = (m.Nz + W - 1) / W, BL = (m.Nx + NB - 1) / NB;
   k<<<(unsigned)(m.Ny * ztiles), NB * W, sx, stream>>>(m, (const TmpT*)tmp, plane_empty, dist2, costq, lut, lut_n, bits_of((unsigned)(BL - 1)), BL,
                                                         bits_of((unsigned)(m.Ny - 1)));
   return true;
 }
-// The three tile shapes (bands x lanes, 256 threads): the widest whose hull stack leaves at least two blocks per SM,
-// else the widest that fits at all.  0 = none fits.
+// The three tile shapes (bands x lanes, 256 threads): the one that keeps the most blocks resident per SM (the kernels are
+// latency-bound chains: resident warps matter more than tile width), the wider one on ties.  0 = none fits.
+// B200_EDT_SHAPE_Y / _X = 1, 2, 3 force a shape (tuning knob; ignored when that shape does not fit).
 template <class E, bool Y>
 int pick_shape(const MapDev& m) {
   const size_t s[3] = {Y ? smem_y<8, 32, E>(m) : smem_x<8, 32, E>(m), Y ? smem_y<16, 16, E>(m) : smem_x<16, 16, E>(m),
                        Y ? smem_y<32, 8, E>(m) : smem_x<32, 8, E>(m)};
-  for (int i = 0; i < 3; ++i)
-    if (cfg_of(s[i], 256).blocks_per_sm >= 2) return i + 1;
-  for (int i = 0; i < 3; ++i)
-    if (cfg_of(s[i], 256).blocks_per_sm >= 1) return i + 1;
-  return 0;
+  static const int forced_y = getenv("B200_EDT_SHAPE_Y") ? atoi(getenv("B200_EDT_SHAPE_Y")) : 0;
+  static const int forced_x = getenv("B200_EDT_SHAPE_X") ? atoi(getenv("B200_EDT_SHAPE_X")) : 0;
+  const int forced = Y ? forced_y : forced_x;
+  if (forced >= 1 && forced <= 3 && cfg_of(s[forced - 1], 256).blocks_per_sm >= 1) return forced;
+  int best = 0, best_blocks = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int b = cfg_of(s[i], 256).blocks_per_sm;
+    if (b > best_blocks) { best = i + 1; best_blocks = b; }
+  }
+  return best;
 }
 }  // namespace
 
@@ -340,9 +357,15 @@ bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t*
     // seven-kernel pipeline's wide mode), (s, g) entries of 32 bits when 6..8 bits of band-relative site + g fit, else 64;
     // tile shape chosen per pass
     using GY = PassY<uint32_t, long long>;
+    using GY2 = PassY<uint16_t, long long>;
     using GX4 = PassX<uint32_t, long long>;
     using GX8 = PassX<uint64_t, long long>;
-    const int shy = pick_shape<uint32_t, true>(m);
+    // pass 1 entries: 16 bits when band-relative site + z distance fit (with a halo: only under the caller's bound)
+    const unsigned long long dzmax = !halo ? nz1 : (dz_bound > 0 ? (unsigned long long)std::max(dz_bound, m.Nz) : 65535ull);
+    auto sby = [&](int nb) { return bits_of((unsigned)((m.Ny + nb - 1) / nb - 1)); };
+    int shy = pick_shape<uint16_t, true>(m);
+    const bool y16 = shy != 0 && sby(shy == 1 ? 8 : shy == 2 ? 16 : 32) + bits_of(dzmax) <= 16;
+    if (!y16) shy = pick_shape<uint32_t, true>(m);
     // g after pass 1 is < 2^29 by construction (kDistInf); 32-bit entries need the real bound
     // (with a halo the z distances reach into the neighbouring slabs: dz_bound = the caller's bound on them, 0 = unknown)
     const unsigned long long dzb = (unsigned long long)std::max(dz_bound, m.Nz);
@@ -352,9 +375,14 @@ bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t*
     bool x32 = shx != 0 && sbx(shx == 1 ? 8 : shx == 2 ? 16 : 32) + bits_of(gmax) <= 32;
     if (!x32) shx = pick_shape<uint64_t, false>(m);
     if (!shy || !shx) return false;
-    ok = shy == 1   ? launch_y<8, 32, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-         : shy == 2 ? launch_y<16, 16, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-                    : launch_y<32, 8, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
+    if (y16)
+      ok = shy == 1   ? launch_y<8, 32, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+           : shy == 2 ? launch_y<16, 16, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+                      : launch_y<32, 8, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
+    else
+      ok = shy == 1   ? launch_y<8, 32, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+           : shy == 2 ? launch_y<16, 16, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
+                      : launch_y<32, 8, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
     if (ev) cudaEventRecord(ev[1], stream);
     if (x32)
       ok = ok && (shx == 1   ? launch_x<8, 32, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)

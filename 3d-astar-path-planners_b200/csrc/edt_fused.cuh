@@ -28,26 +28,27 @@
 namespace b200 {
 namespace edtf {
 
-// Pass traits: E = stack entry type (s in the low SB bits, payload above), X = type wide enough for the cross
-// products (max c difference times max site difference), g_of = payload -> g.
+// Pass traits: E = stack entry type (s in the low SB bits, payload above), X = type of the cross PRODUCTS (c difference
+// times site difference: int32 when they fit, else int64 — one IMAD.WIDE of two 32-bit operands), g_of = payload -> g.
+// c = s^2 + g itself always fits 32 bits (s < 2^15, g < 2^29).
 template <class E_, class X_>
 struct PassY {  // payload = z distance
   using E = E_;
   using X = X_;
-  static EDT_HD X g_of(uint32_t p) { return (X)p * (X)p; }
+  static EDT_HD int32_t g_of(uint32_t p) { return (int32_t)(p * p); }
 };
 template <class E_, class X_>
 struct PassX {  // payload = g itself
   using E = E_;
   using X = X_;
-  static EDT_HD X g_of(uint32_t p) { return (X)p; }
+  static EDT_HD int32_t g_of(uint32_t p) { return (int32_t)p; }
 };
 
 template <class Tr>
 struct Vtx {
   int s;
   uint32_t p;
-  typename Tr::X c;
+  int32_t c;
 };
 // entries hold the site RELATIVE to their band's first site (SB = bits of band length - 1): 6 bits for 64-site bands,
 // which is what lets a 16-bit (pass 1) / 32-bit (pass 2) entry carry the payload of grids as large as 2048^2 x 512
@@ -56,13 +57,13 @@ EDT_HD Vtx<Tr> unpack(typename Tr::E e, int SB, int sbase) {
   Vtx<Tr> v;
   v.s = (int)((uint32_t)e & ((1u << SB) - 1u)) + sbase;
   v.p = (uint32_t)(e >> SB);
-  v.c = (typename Tr::X)v.s * v.s + Tr::g_of(v.p);
+  v.c = v.s * v.s + Tr::g_of(v.p);
   return v;
 }
 // b is on or above the segment a--c (s_a < s_b < s_c): b can never be the unique minimiser, drop it
 template <class X>
-EDT_HD bool drops(int sa, X ca, int sb, X cb, int sc, X cc) {
-  return (cb - ca) * (X)(sc - sb) >= (cc - cb) * (X)(sb - sa);
+EDT_HD bool drops(int sa, int32_t ca, int sb, int32_t cb, int sc, int32_t cc) {
+  return (X)(cb - ca) * (X)(sc - sb) >= (X)(cc - cb) * (X)(sb - sa);
 }
 
 // interval of a band's stack that is still on the line's hull: lo | hi << 16; empty when lo > hi
@@ -81,12 +82,12 @@ struct HullBuilder {
   E* top;      // slot of the top entry B (one stride below the band's first slot while the stack is empty)
   int W, SB, sbase, q;
   int sB, dS;  // top entry's site, and its distance to the entry A below it (valid while q >= 2)
-  X cB, dC;    // likewise for c: A is recovered as (sB - dS, cB - dC), so a pop needs no copy of A
+  int32_t cB, dC;  // likewise for c: A is recovered as (sB - dS, cB - dC), so a pop needs no copy of A
   EDT_HD void init(E* st_, int W_, int SB_, int sbase_) { top = st_ - W_; W = W_; SB = SB_; sbase = sbase_; q = 0; sB = dS = 0; cB = dC = 0; }
   EDT_HD void push(int u, uint32_t p) {
-    const X cu = (X)u * u + Tr::g_of(p);
+    const int32_t cu = u * u + Tr::g_of(p);
     // B is on or above the segment A--C  <=>  (cB - cA) (u - sB) >= (cu - cB) (sB - sA)
-    while (q >= 2 && dC * (X)(u - sB) >= (cu - cB) * (X)dS) {
+    while (q >= 2 && (X)dC * (X)(u - sB) >= (X)(cu - cB) * (X)dS) {
       --q;
       top -= W;
       sB -= dS; cB -= dC;
@@ -233,7 +234,7 @@ struct HullCursor {
 };
 
 // emit(d, payload, value) is called once per site in increasing order, d = u - s for a minimising site s and
-// value = d^2 + g_of(payload); the caller keeps its own output cursor.  hint = virtual index to start the search for the
+// value = d^2 + g_of(payload) (int32); the caller keeps its own output cursor.  hint = virtual index to start the search for the
 // tangent vertex of u0 from (the junction of the caller's own band: the nearest obstacle is usually close).
 template <class Tr, class Emit>
 EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T, int u0, int u1, int hint, Emit&& emit) {
@@ -253,7 +254,7 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
       HullCursor<Tr> nx = cu;
       nx.next();
       const Vtx<Tr> b = nx.cur();
-      if (!(b.c - k.c < two_u0 * (X)(b.s - k.s))) { resolved = true; break; }
+      if (!((X)(b.c - k.c) < two_u0 * (X)(b.s - k.s))) { resolved = true; break; }
       cu = nx; k = b; moved = true;
       if (++steps == 6) break;
     }
@@ -267,7 +268,7 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
         HullCursor<Tr> pv = cu;
         pv.prev();
         const Vtx<Tr> a = pv.cur();
-        if (k.c - a.c < two_u0 * (X)(k.s - a.s)) { resolved = true; break; }
+        if ((X)(k.c - a.c) < two_u0 * (X)(k.s - a.s)) { resolved = true; break; }
         cu = pv; k = a;
         if (++steps == 6) break;
       }
@@ -282,7 +283,7 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
       const Vtx<Tr> a = cu.cur();
       cu.next();
       const Vtx<Tr> b = cu.cur();
-      if (b.c - a.c < two_u0 * (X)(b.s - a.s)) lo = mid + 1; else hi = mid;
+      if ((X)(b.c - a.c) < two_u0 * (X)(b.s - a.s)) lo = mid + 1; else hi = mid;
     }
     cu.seek(lo);
     k = cu.cur();
@@ -295,15 +296,15 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
   if (left > 0) {
     cu.next(); n = cu.cur();
     step = (X)(2 * (n.s - k.s));
-    acc = step * (X)u0 - (n.c - k.c);
+    acc = step * (X)u0 - (X)(n.c - k.c);
   }
   int d = u0 - k.s;
   uint32_t kp = k.p;
-  X g = Tr::g_of(kp);
+  int32_t g = Tr::g_of(kp);
   for (int u = u0; u < u1; ++u) {
     while (acc >= 0) {
       const int ks = n.s;
-      const X kc = n.c;
+      const int32_t kc = n.c;
       kp = n.p;
       --left;
       d = u - ks;
@@ -311,12 +312,12 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
       if (left > 0) {
         cu.next(); n = cu.cur();
         step = (X)(2 * (n.s - ks));
-        acc = step * (X)u - (n.c - kc);
+        acc = step * (X)u - (X)(n.c - kc);
       } else {
         acc = -1; step = 0;
       }
     }
-    emit(d, kp, (X)d * d + g);
+    emit(d, kp, d * d + g);
     ++d;
     acc += step;
   }
@@ -329,7 +330,7 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
 //     voxel in the slabs below / above, <= 0 when none); packed as two int32 "far" sentinels when there is none.
 //   site_dz(): distance of bit `bi` of the own word to the nearest occupied voxel of the column; >= kDzNone = none.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kDzNone = 65535;
+constexpr int kDzNone = 23171;  // dz^2 >= 2^29 = kDistInf: as far as the transform is concerned there is no obstacle
 constexpr int kFar = 1 << 20;
 EDT_HD int edt_clz(uint32_t v) {
 #ifdef __CUDA_ARCH__

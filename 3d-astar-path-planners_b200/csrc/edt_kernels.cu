@@ -104,6 +104,51 @@ __global__ void __launch_bounds__(256) column_extents_kernel(MapDev m, int32_t* 
   lowest[col] = lo;
   highest[col] = hi;
 }
+// the same extents as one packed (lowest, highest) int16 pair per column: what the slabs exchange (4 B per column)
+__global__ void __launch_bounds__(256) column_extents16_kernel(MapDev m, short2* __restrict__ lo_hi) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)m.Nx * m.Ny) return;
+  const uint32_t* c = m.occ + col * m.wz;
+  int lo = -1, hi = -1;
+  for (int j = 0; j < m.wz; ++j) {
+    const uint32_t v = __ldg(c + j);
+    if (v) { if (lo < 0) lo = (j << 5) + __ffs(v) - 1; hi = (j << 5) + 31 - __clz(v); }
+  }
+  lo_hi[col] = make_short2((short)lo, (short)hi);
+}
+void launch_column_extents16(const MapDev& m, short2* lo_hi, cudaStream_t stream) {
+  const long long cols = (long long)m.Nx * m.Ny;
+  column_extents16_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(m, lo_hi);
+}
+// z-slab halo from the all-gathered extents: per column, the distance from this slab's first / last z-plane to the
+// nearest occupied voxel in the slabs below / above (>= 1), -1 where there is none.  gathered = [P][cols] pairs.
+struct SlabHeights { int nz[kMaxSlabs]; };
+__global__ void __launch_bounds__(256) slab_gaps_kernel(const short2* __restrict__ gathered, SlabHeights h, int P, int rank, long long cols,
+                                                        int32_t* __restrict__ below, int32_t* __restrict__ above) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  int b = -1, gap = 0;
+  for (int r = rank - 1; r >= 0; --r) {
+    const int hi = __ldg(gathered + (size_t)r * cols + col).y;
+    if (hi >= 0) { b = gap + (h.nz[r] - hi); break; }  // local z = hi of slab r sits nz[r] - hi voxels below our z = 0, plus the slabs in between
+    gap += h.nz[r];
+  }
+  int a = -1;
+  gap = 0;
+  for (int r = rank + 1; r < P; ++r) {
+    const int lo = __ldg(gathered + (size_t)r * cols + col).x;
+    if (lo >= 0) { a = gap + lo + 1; break; }
+    gap += h.nz[r];
+  }
+  below[col] = b;
+  above[col] = a;
+}
+void launch_slab_gaps(const short2* gathered, const int* slab_nz, int P, int rank, long long cols, int32_t* below, int32_t* above,
+                      cudaStream_t stream) {
+  SlabHeights h;
+  for (int i = 0; i < kMaxSlabs; ++i) h.nz[i] = i < P ? slab_nz[i] : 0;
+  slab_gaps_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(gathered, h, P, rank, cols, below, above);
+}
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream) {
   const long long cols = (long long)m.Nx * m.Ny;
   column_extents_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(m, lowest, highest);

@@ -38,6 +38,10 @@ size_t edt_fused_plane_flags_bytes(const MapDev& m);
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
                       const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev);
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
+constexpr int kMaxSlabs = 64;
+void launch_column_extents16(const MapDev& m, short2* lo_hi, cudaStream_t stream);
+void launch_slab_gaps(const short2* gathered, const int* slab_nz, int P, int rank, long long cols, int32_t* below, int32_t* above,
+                      cudaStream_t stream);
 
 // ---- search_kernels.cu
 enum Algo { ALGO_ASTAR = 0, ALGO_THETASTAR = 1, ALGO_LAZYTHETASTAR = 2, ALGO_COSTASTAR = 3, ALGO_COSTLAZYTHETASTAR = 4,

@@ -153,11 +153,31 @@ def run_reference(args, rank, world, out):
     print(json.dumps(line), file=out, flush=True)
 
 
-def run_slab_edt(b200, shard, torch, dist, dev, rank, world, local_rank, nxy=2048, nz_total=512, res=0.1):
+PARITY_FIELDS = ("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length")
+
+
+def oracle_mode(po, sem):
+    return po.FAITHFUL if sem == "faithful" else po.CANONICAL
+
+
+def compare_with_oracle(po, b200, om, algo, sem, s, g, res, res_m, nthreads, cost_weight=0.0):
+    """Untimed checker: the first len(s) result records of `res` against the CPU oracle on the same queries."""
+    op = po.OraclePlanner(algo, om, res_m, 5.0, 1000000, mode=oracle_mode(po, sem), cost_weight=cost_weight)
+    ro, _ = op.find_paths(s, g, nthreads=nthreads)
+    bad = [f for f in PARITY_FIELDS if not np.array_equal(res[f][: len(s)], ro[f])]
+    return bad
+
+
+def run_slab_edt(b200, po, torch, dist, dev, rank, world, local_rank, nthreads, nxy=2048, nz_total=512, res=0.1):
+    """BASELINE config 5: 2048 x 2048 x 512 exact EDT, z-slab sharded.  Per step: packed int16 column extents ->
+    ONE all_gather (4 B per column per slab) -> gap derivation kernel -> two fused EDT kernels on the slab.
+    Untimed checks: (1) every voxel of every slab == the unsharded transform built on the same GPU (all seam planes
+    included); (2) the same sharded pipeline on 256 x 256 x 512 crops == the CPU lower-envelope oracle."""
     nz = nz_total // world
     size = (nxy * res, nxy * res, nz * res)
     origin = (-size[0] / 2, -size[1] / 2, -0.01 + rank * nz * res)
     gm = b200.GridMap(size, res, origin=origin, local_update_range=(1e4, 1e4, 1e4), ground_height=-0.01, device=local_rank)
+    gm.set_slab_extent(nz_total)
     # device-generated forest (same seed on every rank): ground plane + pillars, ~2e7 points
     g = torch.Generator(device=dev)
     g.manual_seed(7)
@@ -175,39 +195,244 @@ def run_slab_edt(b200, shard, torch, dist, dev, rank, world, local_rank, nxy=204
     ground = torch.cat([ground, torch.full((ground.shape[0], 1), 0.04, device=dev)], dim=1)
     cloud = torch.zeros(pts.shape[0] + ground.shape[0], 4, device=dev, dtype=torch.float32)
     cloud[:, :3] = torch.cat([pts, ground]).to(torch.float32)
+    del u, pts, ground
     gm.cloudCallback(cloud, (0.0, 0.0, 1.0), point_step=16)
-    lo = torch.empty(nxy, nxy, dtype=torch.int32, device=dev)
-    hi = torch.empty(nxy, nxy, dtype=torch.int32, device=dev)
-    all_lo = torch.empty(world, nxy, nxy, dtype=torch.int32, device=dev)
-    all_hi = torch.empty(world, nxy, nxy, dtype=torch.int32, device=dev)
 
-    def step():
-        gm.column_extents(lo, hi)
-        dist.all_gather_into_tensor(all_lo, lo)
-        dist.all_gather_into_tensor(all_hi, hi)
-        below, above = shard.slab_gaps_torch(all_lo, all_hi, [nz] * world, rank)
-        gm.build_edt_slab(D_SAFE, below if rank > 0 else None, above if rank < world - 1 else None)
-        return below, above
+    def make_step(m, n_xy):
+        ext = torch.empty(n_xy, n_xy, 2, dtype=torch.int16, device=dev)
+        allext = torch.empty(world, n_xy, n_xy, 2, dtype=torch.int16, device=dev)
+        below = torch.empty(n_xy, n_xy, dtype=torch.int32, device=dev)
+        above = torch.empty(n_xy, n_xy, dtype=torch.int32, device=dev)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
-    keep = step()
+        def step():
+            evs[0].record()
+            m.column_extents16(ext)
+            evs[1].record()
+            dist.all_gather_into_tensor(allext.view(torch.int32), ext.view(torch.int32))  # NCCL has no int16: (lo, hi) travels as one int32
+            evs[2].record()
+            m.slab_gaps(allext, [nz] * world, rank, below, above)
+            evs[3].record()
+            m.build_edt_slab(D_SAFE, below if rank > 0 else None, above if rank < world - 1 else None)
+            evs[4].record()
+        return step, evs, (ext, allext, below, above)
+
+    step, evs, keep = make_step(gm, nxy)
+    gm.set_profiling(True)
+    for _ in range(2):
+        step()
     torch.cuda.synchronize()
     dist.barrier()
+    reps = 5
+    stage = np.zeros((reps, 6))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
     a.record()
-    for _ in range(reps):
-        keep = step()
+    for i in range(reps):
+        step()
     b.record()
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    for i in range(3):  # stage split of three more (separately synchronised) steps
+        step()
+        torch.cuda.synchronize()
+        sm = gm.stage_ms()
+        stage[i, :4] = [evs[k].elapsed_time(evs[k + 1]) for k in range(4)]
+        stage[i, 4:6] = sm[9:11] if gm.edt_pipeline_used() == "fused" else [sum(sm[2:6]), sum(sm[6:9])]
+    stage_ms = np.median(stage[:3], axis=0)
     nvox_total = nxy * nxy * nz_total
-    occ_frac = float((hi >= 0).float().mean())
+    out = {"grid": [nxy, nxy, nz_total], "slabs": world, "points": int(cloud.shape[0]), "ms": float(ms),
+           "pipeline": gm.edt_pipeline_used(),
+           "stage_ms_rank0": {"column_extents16": float(stage_ms[0]), "all_gather(nccl)": float(stage_ms[1]), "slab_gaps": float(stage_ms[2]),
+                              "build_edt_slab": float(stage_ms[3]), "edt_pass_zy": float(stage_ms[4]), "edt_pass_x": float(stage_ms[5])},
+           "gbs_survey_def_total": (nvox_total / 8 + 4 * nvox_total) / (float(ms) * 1e-3) / 1e9,
+           "gbs_survey_def_per_gpu": (nvox_total / 8 + 4 * nvox_total) / world / (float(ms) * 1e-3) / 1e9,
+           "exchange_bytes_per_rank": int(world * nxy * nxy * 4)}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        out["hbm_frac_per_gpu"] = out["gbs_survey_def_per_gpu"] / float(json.load(open(peaks_path))["hbm_gbs"])
+
+    # ---- check 1 (untimed): every voxel of this rank's slab == the unsharded 2048 x 2048 x 512 transform on this GPU
+    errors = []
+    full = b200.GridMap((size[0], size[1], nz_total * res), res, origin=(origin[0], origin[1], -0.01),
+                        local_update_range=(1e4, 1e4, 1e4), ground_height=-0.01, device=local_rank)
+    full.cloudCallback(cloud, (0.0, 0.0, 1.0), point_step=16)
+    full.build_edt(D_SAFE)
+    fd, fc = full.device_fields()
+    sd, sc = gm.device_fields()
+    z0 = rank * nz
+    same_d = bool(torch.equal(fd[:, :, z0:z0 + nz], sd))
+    same_c = bool(torch.equal(fc[:, :, z0:z0 + nz], sc))
+    seam_planes = [z for z in (z0, z0 + nz - 1)]
+    seams_ok = all(bool(torch.equal(fd[:, :, z], sd[:, :, z - z0])) for z in seam_planes)
+    finite = int((sd < (1 << 29)).sum().item())
+    far = int(sd.max().item())
+    if not (same_d and same_c and seams_ok):
+        errors.append(f"rank {rank}: slab differs from the unsharded transform (dist2 {same_d}, costq {same_c}, seams {seams_ok})")
+    del fd, fc, sd, sc
+    full.close()
     gm.close()
-    del keep
-    return {"grid": [nxy, nxy, nz_total], "slabs": world, "points": int(cloud.shape[0]), "ms": float(ms),
-            "gbs_survey_def_total": (nvox_total / 8 + 4 * nvox_total) / (float(ms) * 1e-3) / 1e9,
-            "exchange_bytes_per_rank": int(2 * world * nxy * nxy * 4), "columns_with_obstacle_frac": occ_frac}
+    del keep, cloud
+    torch.cuda.empty_cache()
+
+    # ---- check 2 (untimed): the same sharded pipeline on 256 x 256 x 512 crops of the world against the CPU lower envelope
+    crops, n_crop = 4, 256
+    crop_bad = 0
+    rng = np.random.default_rng(5)
+    for c in range(crops):
+        ox, oy = (rng.integers(0, nxy - n_crop, 2) * res - nxy * res / 2).tolist()
+        csize = (n_crop * res, n_crop * res, nz * res)
+        cm = b200.GridMap(csize, res, origin=(ox, oy, -0.01 + rank * nz * res), local_update_range=(1e4, 1e4, 1e4), ground_height=-0.01,
+                          device=local_rank)
+        cm.set_slab_extent(nz_total)
+        # a small forest of its own (seeded per crop, identical on every rank), including columns that are empty in whole slabs
+        gc = torch.Generator(device=dev)
+        gc.manual_seed(100 + c)
+        npc = 60
+        pcx = ox + torch.rand(npc, generator=gc, device=dev) * csize[0]
+        pcy = oy + torch.rand(npc, generator=gc, device=dev) * csize[1]
+        ph = 0.5 + torch.rand(npc, generator=gc, device=dev) * (nz_total * res - 1.0) * (torch.rand(npc, generator=gc, device=dev) < 0.5)
+        uu = torch.rand(npc, 4000, 3, generator=gc, device=dev)
+        pp = torch.stack([pcx[:, None] + (uu[..., 0] - 0.5) * 0.8, pcy[:, None] + (uu[..., 1] - 0.5) * 0.8, uu[..., 2] * ph[:, None]], dim=-1).reshape(-1, 3)
+        # floating obstacles (not connected to the ground): what makes the below / above gaps differ per column
+        fl = torch.rand(300, 3, generator=gc, device=dev) * torch.tensor([csize[0], csize[1], nz_total * res - 0.2], device=dev) + \
+            torch.tensor([ox, oy, 0.0], device=dev)
+        cc = torch.zeros(pp.shape[0] + fl.shape[0], 4, device=dev, dtype=torch.float32)
+        cc[:, :3] = torch.cat([pp, fl]).to(torch.float32)
+        cm.cloudCallback(cc, (0.0, 0.0, 1.0), point_step=16)
+        cstep, _, ckeep = make_step(cm, n_crop)
+        cstep()
+        torch.cuda.synchronize()
+        d_slab, _ = cm.device_fields()
+        occ_slab = torch.from_numpy(cm.inflate()).to(dev)
+        all_d = [torch.empty_like(d_slab) for _ in range(world)] if rank == 0 else None
+        all_o = [torch.empty_like(occ_slab) for _ in range(world)] if rank == 0 else None
+        dist.gather(d_slab.contiguous(), all_d, dst=0)
+        dist.gather(occ_slab, all_o, dst=0)
+        if rank == 0:
+            grid = torch.cat(all_o, dim=2).cpu().numpy()
+            got = torch.cat(all_d, dim=2).cpu().numpy()
+            om = po.OracleMap((ox, oy, -0.01), (csize[0], csize[1], nz_total * res), res)
+            om.set_inflate(grid)
+            want, _ = om.build_edt(d_safe=0.0, nthreads=nthreads)
+            if not np.array_equal(got, want):
+                crop_bad += 1
+                errors.append(f"C5 crop {c}: sharded EDT differs from the CPU lower envelope in {int((got != want).sum())} voxels")
+            del om
+        cm.close()
+        del ckeep
+    out["parity"] = {"slab_equals_unsharded_all_voxels": bool(same_d and same_c), "seam_planes_checked": seam_planes,
+                     "finite_voxels_in_slab": finite, "max_dist2_in_slab": far,
+                     "cpu_oracle_crops": {"crops": crops, "grid": [n_crop, n_crop, nz_total], "column_blocks_32x32": crops * 64,
+                                          "slabs": world, "mismatching_crops": crop_bad} if rank == 0 else None}
+    return out, errors
+
+
+def run_c1(b200, po, synth, device, errors):
+    """BASELINE config C1: one Theta* query (0,0,0)->(40,40,4) on the 250x250x50 @0.2 m forest; GPU latency of the
+    host-facing findPath next to the single-threaded CPU restatement (the reference itself is single-threaded)."""
+    c = synth.CONFIGS["C1"]
+    cloud = synth.pack_cloud(synth.config_cloud("C1"))
+    gm = b200.GridMap(c["size"], c["resolution"], origin=c["origin"], local_update_range=(1e3, 1e3, 1e3), ground_height=c["origin"][2], device=device)
+    gm.cloudCallback(cloud, (0.0, 0.0, 1.0))
+    om = None
+    if po is not None:
+        om = po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=(1e3, 1e3, 1e3), ground_height=c["origin"][2])
+        om.update_cloud(cloud, (0.0, 0.0, 1.0))
+    out = {"query": "(0,0,0)->(40,40,4)", "grid": list(gm.dims), "resolution": 0.2}
+    s, g = (0.0, 0.0, 0.0), (40.0, 40.0, 4.0)
+    for algo in ("thetastar", "astar", "lazythetastar"):
+        for sem in (("faithful", "canonical") if algo != "lazythetastar" else ("canonical",)):
+            pl = b200.Planner(algo, resolution=0.2, lambda_heuristic=5.0, allocate_num=1000000, semantics=sem)
+            pl.setGridMap(gm)
+            pl.findPath(s, g)
+            ts, r = [], None
+            for _ in range(7):
+                gm.sync()
+                t0 = time.perf_counter()
+                r = pl.findPath(s, g)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            e = {"gpu_ms_per_query_e2e": float(np.median(ts)), "gpu_kernel_ms": r["time_spent"] * 1e-3, "solved": bool(r["solved"]),
+                 "expansions": r["iter_num"], "explored_nodes": r["explored_nodes"], "los_checks": r["line_of_sight_checks"],
+                 "los_samples": r["los_samples"], "path_length": r["path_length"], "n_path": len(pl.getPath())}
+            if om is not None:
+                op = po.OraclePlanner(algo, om, 0.2, 5.0, 1000000, mode=oracle_mode(po, sem))
+                tc, ro = [], None
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ro, pth = op.find_path(s, g)
+                    tc.append((time.perf_counter() - t0) * 1e3)
+                e["cpu_1_thread_ms_per_query"] = float(np.median(tc))
+                same = (int(ro["explored_nodes"]) == r["explored_nodes"] and float(ro["g_final"]) == r["g_final_node"] and
+                        float(ro["path_length"]) == r["path_length"] and np.array_equal(pth, pl.getPath()))
+                e["identical_to_oracle"] = bool(same)
+                if not same:
+                    errors.append(f"C1 {algo}/{sem}: result differs from the oracle")
+            out[f"{algo}_{sem}"] = e
+            pl.close()
+    gm.close()
+    return out
+
+
+def run_c3(b200, po, synth, torch, dev, device, host_threads, errors):
+    """BASELINE config C3: 10 000 random costlazythetastar queries with safety cost on the 256x256x64 forest (+ thetastar,
+    the reference-pinned LoS-heavy algorithm, on the same queries)."""
+    c = synth.CONFIGS["C3"]
+    cloud = synth.pack_cloud(synth.config_cloud("C3"))
+    gm = b200.GridMap(c["size"], c["resolution"], origin=c["origin"], local_update_range=(1e3, 1e3, 1e3), ground_height=c["origin"][2], device=device)
+    gm.cloudCallback(cloud, (0.0, 0.0, 1.0))
+    gm.build_edt(1.0)
+    om = None
+    if po is not None:
+        om = po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=(1e3, 1e3, 1e3), ground_height=c["origin"][2])
+        om.update_cloud(cloud, (0.0, 0.0, 1.0))
+        om.build_edt(1.0, nthreads=host_threads)
+    nq = 10000
+    s, g = synth.random_queries(5, gm.getInflateOccupancy, c["origin"], c["size"], nq)
+    ds, dg = torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
+    out = {"grid": list(gm.dims), "queries": nq, "d_safe_m": 1.0, "cost_weight": 1.0}
+    for algo, sem in (("costlazythetastar", "canonical"), ("thetastar", "faithful"), ("thetastar", "canonical")):
+        pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=1.0, semantics=sem)
+        pl.setGridMap(gm)
+        dres = torch.empty(nq * 128, dtype=torch.uint8, device=dev)
+        pl.findPaths(ds, dg, results=dres)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pl.findPaths(ds, dg, results=dres)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        t0 = time.perf_counter()
+        res, _ = pl.findPaths(s, g)
+        ms_h = (time.perf_counter() - t0) * 1e3
+        e = {"queries_per_s": nq / (ms * 1e-3), "queries_per_s_e2e": nq / (ms_h * 1e-3), "solved": int(res["solved"].sum()),
+             "expansions_per_query": float(res["iter_num"].mean()), "los_checks_per_query": float(res["los_checks"].mean()),
+             "los_samples_per_query": float(res["los_samples"].mean()), "query_time": percentile_block(res["time_us"])}
+        if om is not None:
+            op = po.OraclePlanner(algo, om, 0.1, 5.0, 1000000, mode=oracle_mode(po, sem), cost_weight=1.0)
+            n_nt, n_1t = 2048, 128
+            t0 = time.perf_counter()
+            ro, _ = op.find_paths(s[:n_nt], g[:n_nt], nthreads=host_threads)
+            t_nt = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            op.find_paths(s[:n_1t], g[:n_1t], nthreads=1)
+            t_1t = time.perf_counter() - t0
+            bad = [f for f in PARITY_FIELDS if not np.array_equal(res[f][:n_nt], ro[f])]
+            e.update({"cpu_queries_per_s_all_threads": n_nt / t_nt, "cpu_threads": host_threads, "cpu_queries_per_s_1_thread": n_1t / t_1t,
+                      "cpu_sample": [n_nt, n_1t], "identical_to_oracle_on_sample": not bad})
+            if bad:
+                errors.append(f"C3 {algo}/{sem}: fields {bad} differ from the oracle")
+        out[f"{algo}_{sem}"] = e
+        pl.close()
+    gm.close()
+    return out
+
+
+def percentile_block(t_us):
+    t = np.asarray(t_us, dtype=np.float64)
+    return {"p50_us": float(np.percentile(t, 50)), "p99_us": float(np.percentile(t, 99)), "max_us": float(t.max()),
+            "max_over_p99": float(t.max() / max(np.percentile(t, 99), 1e-9))}
 
 
 def main():
@@ -217,7 +442,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the query-throughput extras")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -245,6 +470,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    po = None
+    if not args.no_cpu or world > 1:
+        from oracle import pyoracle as po  # the checker / CPU baseline; never on the measured path
+    host_threads = po.max_threads() if po else (os.cpu_count() or 1)
+    check_threads = max(1, host_threads // world)  # every rank runs its own checker at N > 1
+    errors = []  # parity failures found by the untimed checks: reported in the line AND turned into a non-zero exit code
 
     c, blob = build_world(synth)
     n_pts = blob.shape[0]
@@ -255,14 +486,15 @@ def main():
     d_cloud = torch.from_numpy(blob).to(dev)
     h_cloud = torch.from_numpy(blob).pin_memory()
     h_cloud_np = h_cloud.numpy()
+    pageable_np = blob.copy()  # what cloudCallback(const sensor_msgs::PointCloud2ConstPtr&) really hands over: pageable memory
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def frame_device():
         gm.cloudCallback(d_cloud, cam, point_step=16)
         gm.build_edt(D_SAFE)
 
-    def frame_host():
-        gm.cloudCallback(h_cloud_np, cam, point_step=16)
+    def frame_host(buf):
+        gm.cloudCallback(buf, cam, point_step=16)
         gm.build_edt(D_SAFE)
         return gm.local_bounds()  # D2H read-back of the frame's result (6 x int64 keys)
 
@@ -273,12 +505,13 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
-    sampler.start()  # runs through warm-up, the timed region and the e2e region (the timed region alone is ~20 ms)
+    sampler.start()  # runs through warm-up, the timed region and the e2e region (the timed region alone is ~15 ms)
     gm.set_profiling(True)
     for _ in range(args.warmup):
         flush.fill_(1)
         frame_device()
     torch.cuda.synchronize()
+    fused = gm.edt_pipeline_used() == "fused"
 
     # ---- timed region: EXACTLY `steps` frames, L2 flushed (untimed) before each, CUDA events per frame
     barrier()
@@ -301,61 +534,104 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
 
-    # ---- e2e: host cloud through the C-ABI, H2D inside, bounds read back
-    for _ in range(3):
-        frame_host()
-    barrier()
-    e2e_t = []
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        frame_host()
-        torch.cuda.synchronize()
-        e2e_t.append((time.perf_counter() - t0) * 1e3)
-    e2e_total = float(np.sum(e2e_t))
-    if world > 1:
-        t = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_total = float(t.item())
-    e2e_ms = e2e_total / args.steps
+    # ---- e2e: host cloud through the C-ABI, H2D inside, bounds read back (pinned = the headline; pageable beside it)
+    def time_e2e(buf):
+        for _ in range(3):
+            frame_host(buf)
+        barrier()
+        ts = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            frame_host(buf)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        tot = float(np.sum(ts))
+        if world > 1:
+            t = torch.tensor([tot], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t.item())
+        return tot / args.steps, float(np.median(ts))
+
+    e2e_ms, e2e_p50 = time_e2e(h_cloud_np)
+    e2e_pageable_ms, e2e_pageable_p50 = time_e2e(pageable_np)
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel (per-launch CUDA-event durations from the timed region)
+    # ---- roofline (per-launch CUDA-event durations from the timed region).
+    # The dominant unit of the frame is the EDT stage.  With the fused pipeline it is TWO kernels of nearly equal length
+    # coupled through a 2 B/voxel intermediate that is designed to stay in L2, so neither kernel's own DRAM bytes mean much
+    # alone (ncu, which flushes L2 around every kernel, sees 19 MB for the first and misses the write-back of the second):
+    # the roofline entry is therefore the STAGE, with SURVEY 8d's algorithmic bytes (N/8 bit grid in, 4N dist2 out) plus
+    # the 2N costq the stage also writes; intermediates, stacks and scratch are never counted.  `traffic` = the two
+    # kernels' ncu DRAM bytes summed (profiles/traffic.json); per-kernel interface bytes and times are listed beside it.
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    st = stage.mean(axis=0)  # [clear, scatter, z, scan_y, cross_y, fill_y, scan_x, cross_x, fill_x]
-    # algorithmic bytes per launch (DESIGN.md "Kernels"): what each kernel must move at minimum given its interface
-    kernels = {
-        "clear(memset)": (st[0], nvox / 8),
-        "scatter_kernel": (st[1], 16 * n_pts + nvox / 8),
-        "edt_z_kernel": (st[2], nvox / 8 + nvox),                       # read bits, write u8 z distance
-        "edt_scan_y_kernel": (st[3], nvox + 8 * nvox),                  # read u8, write (s,t,g) stacks
-        "edt_cross_kernel(y)": (st[4], 0),                              # latency-bound search, no streaming traffic
-        "edt_fill_y_kernel": (st[5], 8 * nvox + 4 * nvox),              # read stacks, write d_zy^2
-        "edt_scan_x_kernel": (st[6], 4 * nvox + 8 * nvox),              # read d_zy^2, write stacks
-        "edt_cross_kernel(x)": (st[7], 0),
-        "edt_fill_x_kernel": (st[8], 8 * nvox + 4 * nvox + 2 * nvox),   # read stacks, write dist2 + costq
-    }
-    dom = max(kernels, key=lambda k: kernels[k][0])
-    dom_ms, dom_bytes = kernels[dom]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                "stage_ms": {k: float(v[0]) for k, v in kernels.items()}}
+    st = stage.mean(axis=0)
+    if fused:
+        kernels = {  # name: (ms, bytes the kernel reads + writes through its interface)
+            "clear(memset)": (st[0], nvox / 8),
+            "scatter_kernel": (st[1], 16 * n_pts + nvox / 8),
+            "edt_fused_y_kernel": (st[9], nvox / 8 + 2 * nvox),               # bit grid in, 16-bit (dy, dz) intermediate out
+            "edt_fused_x_kernel": (st[10], 2 * nvox + 4 * nvox + 2 * nvox),   # intermediate in, dist2 (int32) + costq (uint16) out
+        }
+        edt_names = ["edt_fused_y_kernel", "edt_fused_x_kernel"]
+        edt_ms = float(st[9] + st[10])
+    else:
+        kernels = {
+            "clear(memset)": (st[0], nvox / 8), "scatter_kernel": (st[1], 16 * n_pts + nvox / 8),
+            "edt_z_kernel": (st[2], nvox / 8 + nvox), "edt_scan_y_kernel": (st[3], nvox + 8 * nvox), "edt_cross_kernel(y)": (st[4], 0),
+            "edt_fill_y_kernel": (st[5], 8 * nvox + 4 * nvox), "edt_scan_x_kernel": (st[6], 4 * nvox + 8 * nvox), "edt_cross_kernel(x)": (st[7], 0),
+            "edt_fill_x_kernel": (st[8], 8 * nvox + 4 * nvox + 2 * nvox),
+        }
+        edt_names = [k for k in kernels if k.startswith("edt_")]
+        edt_ms = float(st[2:9].sum())
+    stage_bytes = nvox / 8 + 4 * nvox + 2 * nvox
+    achieved = stage_bytes / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "EDT stage = " + " + ".join(edt_names), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes,
+                "kernel_ms": edt_ms, "share_of_frame": edt_ms / ms_per_step,
+                "algorithmic_bytes_definition": "SURVEY 8d: N/8 (bit grid in) + 4N (int32 dist2 out), + 2N (uint16 costq out); "
+                                                "intermediates, stacks and scratch are not counted",
+                "per_kernel": {k: {"ms": float(v[0]), "interface_bytes": float(v[1]),
+                                   "interface_gbs": float(v[1] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else 0.0} for k, v in kernels.items()}}
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
-        roofline["traffic"] = json.load(open(tr_path)).get(dom)
-    edt_ms = float(st[2:9].sum())
-    edt_gbs = (nvox / 8 + 4 * nvox) / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0
+        tr = json.load(open(tr_path))
+        per = {k: tr.get(k) for k in kernels if tr.get(k) is not None}
+        roofline["traffic_per_kernel"] = per
+        if all(k in per for k in edt_names):
+            roofline["traffic"] = float(sum(per[k] for k in edt_names))
+            roofline["algorithmic_le_traffic"] = bool(stage_bytes <= roofline["traffic"])
+    # the stage figures SURVEY 8d / BASELINE.json's "EDT HBM GB/s" name
+    edt_bytes_survey = nvox / 8 + 4 * nvox
+    edt_bytes_with_cost = edt_bytes_survey + 2 * nvox
+    frame_bytes = (nvox / 8 + 16 * n_pts + nvox / 8) + edt_bytes_with_cost
+    extra = {"edt_pipeline": "fused (2 kernels, hull stacks in shared memory)" if fused else "hbm-stack (7 kernels)",
+             "edt_ms": float(edt_ms),
+             "edt_hbm_gbs_survey_def": edt_bytes_survey / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0,
+             "edt_hbm_frac_survey_def": edt_bytes_survey / (edt_ms * 1e-3) / 1e9 / peak if edt_ms > 0 else 0.0,
+             "edt_hbm_gbs_with_costq": edt_bytes_with_cost / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0,
+             "frame_hbm_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+             "wall_ms_timed_region": wall_ms,
+             "e2e_pageable_host_cloud": {"ms_per_step": e2e_pageable_ms, "p50_ms_per_step": e2e_pageable_p50,
+                                         "note": "same call with a pageable (non-pinned) host cloud, as a ROS PointCloud2::data is"}}
+    if world > 1:
+        extra["multi_gpu_note"] = ("map build: replicas only — every rank rebuilds the same replica, so ms/frame is flat in N by "
+                                   "construction; what scales is the sharded query throughput in extra.scaling")
 
     # ---- extras: batched query throughput on this map (sharded over ranks, no collective)
-    extra = {"edt_hbm_gbs_survey_def": edt_gbs, "edt_ms": float(edt_ms), "wall_ms_timed_region": wall_ms}
+    scaling = {}
     if not args.no_extra:
         occ = lambda p: gm.getInflateOccupancy(p)
+        gm.build_edt(D_SAFE)
+        om = None
+        if po is not None:
+            om = po.OracleMap(c["origin"], c["size"], c["resolution"], local_update_range=(60.0, 60.0, 20.0), ground_height=c["origin"][2])
+            om.update_cloud(blob, cam, point_step=16, nthreads=check_threads)
         # fastLOS batch: 1M segments between random free points (device-resident in/out)
         nseg = 1 << 20
         sa, sb = synth.random_queries(60 + rank, occ, c["origin"], c["size"], nseg, min_dist=1.0, z_range=(0.3, 3.0))
@@ -379,6 +655,9 @@ def main():
         extra["fastlos_segments_per_s"] = float(t[1]) / (los_ms * 1e-3)
         extra["fastlos_samples_per_s"] = float(t[2]) / (los_ms * 1e-3)
         extra["fastlos_visible_frac"] = float(vis.float().mean().item())
+        if om is not None:  # untimed check: 20 000 of the segments against the CPU restatement of fastLOS
+            if not np.array_equal(vis[:20000].cpu().numpy(), om.los_batch(sa[:20000], sb[:20000], nthreads=check_threads)):
+                errors.append(f"rank {rank}: fastLOS booleans differ from the oracle")
         # the same segments through the voxel-traversal line of sight (rank-local number)
         vis2 = torch.empty(nseg, dtype=torch.uint8, device=dev)
         ncell = torch.empty(nseg, dtype=torch.int32, device=dev)
@@ -392,11 +671,14 @@ def main():
         extra["ddalos_segments_per_s_per_gpu"] = nseg / (dda_ms * 1e-3)
         extra["ddalos_cells_per_s_per_gpu"] = float(ncell.sum().item()) / (dda_ms * 1e-3)
         extra["ddalos_agrees_with_fastlos_frac"] = float((vis2 == vis).float().mean().item())
+        del da, db, vis, vis2, nsmp, ncell
+
+        cpu_q = {}
         for algo, sem, nq in QUERY_ALGOS:
             # every rank draws the same global batch and takes its contiguous shard (map replicated, no collective)
-            s, g = synth.random_queries(6, occ, c["origin"], c["size"], nq * world, min_dist=5.0, z_range=(0.3, 3.0))
+            s_all, g_all = synth.random_queries(6, occ, c["origin"], c["size"], nq * world, min_dist=5.0, z_range=(0.3, 3.0))
             lo, hi = shard.query_shard(nq * world, rank, world)
-            s, g = np.ascontiguousarray(s[lo:hi]), np.ascontiguousarray(g[lo:hi])
+            s, g = np.ascontiguousarray(s_all[lo:hi]), np.ascontiguousarray(g_all[lo:hi])
             pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0, semantics=sem)
             pl.setGridMap(gm)
             ds, dg = torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
@@ -408,38 +690,98 @@ def main():
             pl.findPaths(ds, dg, results=dres)
             b.record()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
+            ms_own = a.elapsed_time(b)
             t0 = time.perf_counter()
             res, _ = pl.findPaths(s, g)  # host-facing (H2D + D2H inside)
             ms_h = (time.perf_counter() - t0) * 1e3
-            tot = torch.tensor([ms, ms_h, float(nq), float(res["solved"].sum()), float(res["iter_num"].sum())], device=dev,
+            tot = torch.tensor([ms_own, ms_h, float(nq), float(res["solved"].sum()), float(res["iter_num"].sum())], device=dev,
                                dtype=torch.float64)
+            ms, own_rates = ms_own, [nq / (ms_own * 1e-3)]
             if world > 1:
                 mx = tot.clone()
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(tot, op=dist.ReduceOp.SUM)
                 ms, ms_h = float(mx[0]), float(mx[1])
+                rates = torch.zeros(world, device=dev, dtype=torch.float64)
+                rates[rank] = own_rates[0]
+                dist.all_reduce(rates, op=dist.ReduceOp.SUM)
+                own_rates = [float(x) for x in rates.cpu()]
             key = f"{algo}_{sem}"
-            extra[f"{key}_queries_per_s"] = float(tot[2]) / (ms * 1e-3)
+            qps = float(tot[2]) / (ms * 1e-3)
+            extra[f"{key}_queries_per_s"] = qps
             extra[f"{key}_queries_per_s_e2e"] = float(tot[2]) / (ms_h * 1e-3)
             extra[f"{key}_queries"] = int(tot[2])
             extra[f"{key}_solved"] = int(tot[3])
             extra[f"{key}_expansions_per_query"] = float(tot[4]) / float(tot[2])
+            extra[f"{key}_query_time"] = percentile_block(res["time_us"])
+            # weak scaling as measured in THIS run: aggregate rate against n_gpus x the mean rate a rank reaches on its own shard
+            scaling[key] = {"queries_per_s": qps, "per_rank_queries_per_s": own_rates,
+                            "efficiency_vs_mean_rank_rate": qps / (world * float(np.mean(own_rates))),
+                            "slowest_over_fastest_rank_time": float(max(own_rates) / min(own_rates))}
+            # ---- untimed multi-GPU correctness: (a) a slice of this rank's shard against the CPU oracle; (b) rank 0 recomputes
+            # a slice of EVERY rank's shard on its own GPU and compares it bit for bit with what that rank reported
+            nchk = 256
+            if om is not None and (world > 1 or not args.no_cpu):
+                bad = compare_with_oracle(po, b200, om, algo, sem, s[:nchk], g[:nchk], res, 0.1, check_threads)
+                if bad:
+                    errors.append(f"rank {rank}: {key}: fields {bad} differ from the oracle on its shard")
+            if world > 1:
+                mine = np.zeros((nchk, 4), dtype=np.float64)
+                for j, f in enumerate(("g_final", "path_length", "explored_nodes", "n_path")):
+                    mine[:, j] = res[f][:nchk]
+                allr = torch.zeros(world, nchk, 4, device=dev, dtype=torch.float64)
+                allr[rank] = torch.from_numpy(mine).to(dev)
+                dist.all_reduce(allr, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    for r in range(1, world):
+                        rlo, _ = shard.query_shard(nq * world, r, world)
+                        rr, _ = pl.findPaths(np.ascontiguousarray(s_all[rlo:rlo + nchk]), np.ascontiguousarray(g_all[rlo:rlo + nchk]))
+                        want = np.stack([rr[f].astype(np.float64) for f in ("g_final", "path_length", "explored_nodes", "n_path")], 1)
+                        if not np.array_equal(want, allr[r].cpu().numpy()):
+                            errors.append(f"{key}: rank {r}'s shard results differ from rank 0's recomputation")
+            # ---- CPU baseline for this configuration (rank 0 at N = 1): oracle, all threads on 4096 queries, one thread on 256
+            if rank == 0 and world == 1 and not args.no_cpu:
+                op = po.OraclePlanner(algo, om, 0.1, 5.0, 1000000, mode=oracle_mode(po, sem))
+                n_nt, n_1t = min(4096, nq), 256
+                t0 = time.perf_counter()
+                op.find_paths(s[:n_nt], g[:n_nt], nthreads=host_threads)
+                t_nt = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                op.find_paths(s[:n_1t], g[:n_1t], nthreads=1)
+                t_1t = time.perf_counter() - t0
+                cpu_q[key] = {"queries_per_s_all_threads": n_nt / t_nt, "threads": host_threads, "sample_all_threads": n_nt,
+                              "queries_per_s_1_thread": n_1t / t_1t, "sample_1_thread": n_1t,
+                              "gpu_over_cpu_all_threads": qps / (n_nt / t_nt)}
             pl.close()
+            del ds, dg, dres
+        extra["scaling"] = scaling
+        if cpu_q:
+            extra["cpu_baseline_queries"] = {"kind": "port (oracle/liboracle.so, same semantics as the GPU column)", "map": "C2", **cpu_q}
 
-    # ---- extra (N >= 2): BASELINE config 5 — 2048x2048x512 exact EDT, z-slab sharded, one NCCL all-gather of the
-    # per-column extents.  Every rank voxelises the same device-generated cloud into its own slab.
+        # ---- BASELINE config C1 (single Theta* query (0,0,0)->(40,40,4), 250x250x50 @0.2 m) and C3 (10 000 costlazythetastar
+        # queries, 256x256x64, LoS-heavy): rank 0 only, N = 1 only
+        if rank == 0 and world == 1:
+            try:
+                extra["c1_single_query"] = run_c1(b200, po if not args.no_cpu else None, synth, local_rank, errors)
+                extra["c3_costlazythetastar"] = run_c3(b200, po if not args.no_cpu else None, synth, torch, dev, local_rank, host_threads, errors)
+            except Exception as e:  # never let an extra take the headline down
+                extra["c1_c3_error"] = repr(e)[:300]
+
+    # ---- extra (N >= 2): BASELINE config 5 — 2048x2048x512 exact EDT, z-slab sharded
     if world >= 2 and not args.no_extra and 512 % world == 0:
+        gm_keep = gm
         try:
-            extra["edt_slab_c5"] = run_slab_edt(b200, shard, torch, dist, dev, rank, world, local_rank)
-        except Exception as e:  # never let the extra take the headline down
-            extra["edt_slab_c5"] = {"error": repr(e)[:200]}
+            extra["edt_slab_c5"], errs = run_slab_edt(b200, po, torch, dist, dev, rank, world, local_rank, check_threads)
+            errors.extend(errs)
+        except Exception as e:
+            extra["edt_slab_c5"] = {"error": repr(e)[:300]}
+            errors.append(f"rank {rank}: C5 slab EDT raised {repr(e)[:200]}")
+        gm = gm_keep
 
     # ---- extra (rank 0, N = 1): the depth-image fusion path — 640x480 frames with the reference's default
     # intrinsics into a second C2-sized map, host image in, fused grids resident; the sequential CPU restatement beside it
     if rank == 0 and world == 1 and not args.no_extra:
         try:
-            from oracle import pyoracle as po
             rng_ = (5.5, 5.5, 4.5)
             gd = b200.GridMap(c["size"], c["resolution"], origin=c["origin"], local_update_range=rng_, ground_height=c["origin"][2],
                               device=local_rank)
@@ -450,7 +792,7 @@ def main():
                 od.set_depth_params()
             dpp = b200.DEPTH_DEFAULTS
             boxes = synth.pillar_boxes(c["seed"], c["origin"], c["size"], c["n_pillars"])
-            tg, tc, st = [], [], {}
+            tg, tc, stt = [], [], {}
             for f in range(7):
                 pos = np.array([-3.0 + 0.12 * f, 2.0 - 0.05 * f, 1.2])
                 R, _ = synth.look_at(0.7 + 0.03 * f, 0.15)
@@ -465,11 +807,13 @@ def main():
                     t0 = time.perf_counter()
                     od.update_depth(img, pos, R)
                     tc.append((time.perf_counter() - t0) * 1e3)
-                st = gd.depth_stats()
+                stt = gd.depth_stats()
+            if od is not None and not (np.array_equal(gd.occupancy(), od.occupancy()) and np.array_equal(gd.inflate(), od.inflate())):
+                errors.append("depth fusion: grids differ from the oracle after 7 frames")
             extra["depth_fusion"] = {"frame": "640x480 CV_16UC1, reference default intrinsics and filter (skip_pixel 2)",
                                      "gpu_ms_per_frame_e2e": float(np.median(tg[2:])), "frames": len(tg),
                                      "cpu_sequential_ms_per_frame": float(np.median(tc[2:])) if tc else None,
-                                     "last_frame": st, "h2d_bytes_per_frame": 480 * 640 * 2}
+                                     "last_frame": stt, "h2d_bytes_per_frame": 480 * 640 * 2}
             gd.close()
         except Exception as e:  # never let the extra take the headline down
             extra["depth_fusion"] = {"error": repr(e)[:200]}
@@ -497,22 +841,39 @@ def main():
                "sample": f"{reps} full C2 frames (cloud update + EDT + cost) with {nthreads} threads; single-thread frame: {cpu_ms_1t:.0f} ms",
                "single_thread_ms": cpu_ms_1t}
 
+    # parity failures anywhere -> every rank learns about it, the line carries them, the exit code is non-zero
+    n_err = len(errors)
+    if world > 1:
+        t = torch.tensor([float(n_err)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_err = int(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, errors)
+        errors = [e for part in gathered for e in part]
     if rank == 0:
+        kernels_per_step = (["scatter_kernel", "cost_lut_kernel", "edt_fused_y_kernel", "edt_fused_x_kernel"] if fused else
+                            ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_cross_kernel", "edt_fill_y_kernel",
+                             "edt_scan_x_kernel", "edt_cross_kernel", "edt_fill_x_kernel"])
         line = {
-            "metric": "map rebuild ms/frame", "value": ms_per_step / world, "unit": "ms/frame", "n_gpus": world,
+            "metric": "map rebuild ms/frame", "value": ms_per_step, "unit": "ms/frame", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": "C2: 1M-point PointCloud2 -> 512x512x128 inflated occupancy + exact squared EDT + cost field",
                        "grid": list(gm.dims), "points": int(n_pts), "d_safe_m": D_SAFE, "l2": "flushed (256 MiB write) before every timed frame",
-                       "multi_gpu": "map replicated: every rank rebuilds its replica (value = ms/frame / n_gpus); query batches sharded, no collective"},
-            "e2e": {"value": e2e_ms / world, "unit": "ms/frame", "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": 48,
-                    "ms_per_step": e2e_ms, "p50_ms_per_step": float(np.median(e2e_t))},
-            "gpu_launches": int(args.steps * 9), "kernels_per_step": ["scatter_kernel", "cost_lut_kernel", "edt_z_kernel", "edt_scan_y_kernel", "edt_cross_kernel", "edt_fill_y_kernel", "edt_scan_x_kernel", "edt_cross_kernel", "edt_fill_x_kernel", "(+1 cudaMemsetAsync clear)"],
+                       "multi_gpu": "replicas only: every rank rebuilds the same map replica (value = that frame time, NOT divided by n_gpus); "
+                                    "query batches are sharded with no collective (extra.scaling)"},
+            "e2e": {"value": e2e_ms, "unit": "ms/frame", "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": 48,
+                    "ms_per_step": e2e_ms, "p50_ms_per_step": e2e_p50, "host_buffer": "pinned",
+                    "d2h_note": "the fields stay resident for the planners; only the 6 local-bound keys are read back"},
+            "gpu_launches": int(args.steps * len(kernels_per_step)), "kernels_per_step": kernels_per_step + ["(+1 cudaMemsetAsync clear)"],
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+            "parity_checks": {"failed": n_err, "errors": errors[:20]},
         }
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if n_err:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -183,6 +183,12 @@ int b200_map_edt_pipeline_used(const b200_map_t* map);
  * b200_map_column_extents publishes a slab's lowest / highest occupied z per column (-1 = empty column); the host
  * all-gathers those (NCCL/NVLink) and derives the gaps (shard.py: slab_gaps). NULL gap arrays = no neighbour. */
 int b200_map_column_extents(b200_map_t* map, int32_t* lowest_z, int32_t* highest_z, int32_t on_device);
+/* The exchange in 4 bytes per column: lo_hi = [Nx*Ny][2] int16 (lowest, highest occupied z; -1 = empty column), the
+ * buffer the slabs all-gather; b200_map_slab_gaps then derives THIS slab's two gap arrays on the device from the
+ * gathered [n_slabs][Nx*Ny][2] tensor (device pointers; slab_nz = the slabs' heights in voxels, host array). */
+int b200_map_column_extents16(b200_map_t* map, int16_t* lo_hi, int32_t on_device);
+int b200_map_slab_gaps(b200_map_t* map, const int16_t* gathered_lo_hi, const int32_t* slab_nz, int32_t n_slabs, int32_t rank,
+                       int32_t* below_gap, int32_t* above_gap);
 /* Optional hint for the slab build: the height (voxels) of the whole stacked grid, i.e. a bound on every gap + slab
  * height.  It only selects narrower hull entries (32 instead of 64 bits) in the shared-memory kernels; results do not
  * depend on it as long as the bound holds.  0 = unknown (default). */
@@ -190,6 +196,9 @@ int b200_map_set_slab_extent(b200_map_t* map, int32_t total_nz);
 int b200_map_build_edt_slab(b200_map_t* map, double d_safe, const int32_t* below_gap, const int32_t* above_gap,
                             int32_t on_device);
 int b200_map_download_dist2(b200_map_t* map, int32_t* dst);
+/* Device pointers of the resident fields ([Nx][Ny][Nz] int32 squared distance, uint16 quantised cost; NULL when not
+ * built) for consumers that stay on the GPU (the planners read them this way; bench.py compares slabs with them). */
+int b200_map_device_fields(b200_map_t* map, void** dist2, void** costq);
 /* The distance-to-obstacle statistics GetPath.srv:20-23 carries (min/max/mean/std_dev; the reference leaves them 0
  * because its EDT hook is commented out): d_i = sqrt(dist2[voxel(p_i)]) * resolution at every path point (index clamped
  * into the map, grid_map.h:267-274), then out = {mean, std_dev, min, max} with the element order and arithmetic of

@@ -98,7 +98,7 @@ static int run(int Nx, int Ny, int Nz, double density, unsigned seed, int pillar
         }
         LineHull<TrY> L{&st[lane], &rg[lane], W, SBy, BL};
         int u = u0;
-        hull_fill<TrY>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, typename TrY::X v) {
+        hull_fill<TrY>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, int32_t v) {
           const size_t a = ((size_t)x * Ny + u) * Nz + z;
           if (PACKED) tmp16[a] = (uint16_t)((d < 0 ? -d : d) | (p << DYB));
           else tmp32[a] = (int)v;
@@ -144,7 +144,7 @@ static int run(int Nx, int Ny, int Nz, double density, unsigned seed, int pillar
         if (T == 0) { for (int u = u0; u < u1; ++u) out[((size_t)u * Ny + y) * Nz + z] = kInf; continue; }
         LineHull<TrX> L{&st[lane], &rg[lane], W, SBx, BL};
         int u = u0;
-        hull_fill<TrX>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, typename TrX::X v) { out[((size_t)u * Ny + y) * Nz + z] = (int)v; ++u; });
+        hull_fill<TrX>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) { out[((size_t)u * Ny + y) * Nz + z] = (int)v; ++u; });
       }
     }
   }
@@ -158,7 +158,7 @@ int main(int argc, char** argv) {
   int rc = 0;
   using SY = PassY<uint16_t, int32_t>; using SX = PassX<uint32_t, int32_t>;
   using GY = PassY<uint32_t, long long>; using GX = PassX<uint64_t, long long>;
-  using LX = PassX<uint32_t, long long>;
+  using LX = PassX<uint32_t, long long>; using GY2 = PassY<uint16_t, long long>;
   unsigned seed = argc > 1 ? atoi(argv[1]) : 1;
   for (unsigned s = seed; s < seed + 3; ++s) {
     rc |= run<8, 32, SY, SX, true>(40, 70, 50, 0.002, s, 0);
@@ -172,6 +172,7 @@ int main(int argc, char** argv) {
     rc |= run<32, 8, GY, GX, false>(30, 60, 24, 0.0, s, 5);
     rc |= run<32, 8, GY, LX, false>(70, 200, 24, 0.0003, s, 0);
     rc |= run<16, 16, GY, LX, false>(100, 50, 36, 0.0, s, 4);
+    rc |= run<32, 8, GY2, LX, false>(40, 300, 20, 0.0004, s, 0);
   }
   printf(rc ? "FAILED\n" : "ALL OK\n");
   return rc;

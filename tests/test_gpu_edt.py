@@ -210,3 +210,31 @@ def test_distance_field_is_invalidated_by_grid_writes(b200, po, synth):
         gm.build_edt(d_safe=1.0)
         mutate()
         assert not gm.has_distance_field(1.0)
+
+
+def test_slab_gap_kernel_matches_host_derivation(b200):
+    """b200_map_column_extents16 + b200_map_slab_gaps (device path of the C5 exchange) == shard.slab_gaps on the host."""
+    import torch
+    from astar_planners_b200 import shard
+    rng = np.random.default_rng(3)
+    dims, splits, res = (50, 37, 160), (32, 64, 32, 32), 0.5
+    grid = _sparse_grid(rng, dims, 500)
+    grid[:, :, 40:120] *= (rng.random((dims[0], dims[1], 1)) < 0.1)   # most columns empty across two whole slabs
+    slabs, z0 = [], 0
+    for nz in splits:
+        m = b200.GridMap((dims[0] * res, dims[1] * res, nz * res), res, origin=(0, 0, z0 * res))
+        m.set_inflate(np.ascontiguousarray(grid[:, :, z0:z0 + nz]))
+        slabs.append(m)
+        z0 += nz
+    ext = [m.column_extents() for m in slabs]
+    packed = [m.column_extents16() for m in slabs]
+    for e, p in zip(ext, packed):
+        assert np.array_equal(p[..., 0], e[0]) and np.array_equal(p[..., 1], e[1])
+    gathered = torch.from_numpy(np.stack(packed)).cuda()
+    for r, m in enumerate(slabs):
+        below = torch.empty(dims[:2], dtype=torch.int32, device="cuda")
+        above = torch.empty(dims[:2], dtype=torch.int32, device="cuda")
+        m.slab_gaps(gathered, splits, r, below, above)
+        m.sync()
+        wb, wa = shard.slab_gaps([e[0] for e in ext], [e[1] for e in ext], list(splits), r)
+        assert np.array_equal(below.cpu().numpy(), wb) and np.array_equal(above.cpu().numpy(), wa)
