@@ -1257,7 +1257,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   P.starts = d_starts; P.goals = d_goals; P.qlist = nullptr; P.nq = nq;
   if (nq > 2 * (int64_t)pl->tier[0].slots) {  // more than two waves: issue the expected-longest queries first
     if (pl->q_order.ensure(query_order_bytes((int)nq))) return fail(B200_ERR_NOMEM, "query order");
-    P.qlist = launch_query_order(d_starts, d_goals, (int)nq, pl->q_order.p, st);
+    P.qlist = launch_query_order(P.map, d_starts, d_goals, (int)nq, pl->q_order.p, st);
   }
   P.results = d_res; P.path_pool = d_path; P.path_cap = path_cap; P.path_cursor = path_cursor;
   P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;

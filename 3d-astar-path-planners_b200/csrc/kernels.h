@@ -160,6 +160,6 @@ int search_threads_per_block(int algo);
 int search_slots_per_sm(int algo, int faithful);
 void launch_search(const SearchParams& p, int slots, cudaStream_t st);
 size_t query_order_bytes(int nq);
-const int* launch_query_order(const double* starts, const double* goals, int nq, void* buf, cudaStream_t st);
+const int* launch_query_order(const MapDev& m, const double* starts, const double* goals, int nq, void* buf, cudaStream_t st);
 
 }  // namespace b200
