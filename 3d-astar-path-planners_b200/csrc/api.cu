@@ -65,6 +65,8 @@ struct b200_map {
   uint8_t* d_plane_empty;  // fused EDT: planes of pass 1 without any obstacle (edt_fused.cu)
   bool edt_fused;          // which pipeline the last build_edt ran
   int edt_mode;            // 0 automatic, 1 always the seven-kernel pipeline
+  EdtOverlap ov;           // auxiliary streams / events of the fused EDT (created on first use)
+  bool ov_ready, ov_used;
   int slab_total_nz;       // z-slab sharding: height of the whole stacked grid (bounds the halo distances), 0 = unknown
   uint16_t* d_lut;
   int lut_cap;
@@ -192,6 +194,8 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->edt_fused = false;
   m->edt_mode = 0;
   m->slab_total_nz = 0;
+  m->ov_ready = false;
+  m->ov_used = false;
   m->d_lut = nullptr;
   m->lut_cap = 0;
   m->has_edt = false;
@@ -223,6 +227,10 @@ int b200_map_destroy(b200_map_t* m) {
   if (m->d_counts) cudaFree(m->d_counts);
   if (m->d_cross) cudaFree(m->d_cross);
   if (m->d_plane_empty) cudaFree(m->d_plane_empty);
+  if (m->ov_ready) {
+    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(m->ov.s[i]); cudaEventDestroy(m->ov.y_done[i]); cudaEventDestroy(m->ov.x_done[i]); }
+    cudaEventDestroy(m->ov.fork);
+  }
   if (m->d_lut) cudaFree(m->d_lut);
   cudaFree(m->d_dk);
   cudaFree(m->d_bounds);
@@ -434,8 +442,19 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   }
   // two shared-memory-staged kernels when a line's hull stack fits in shared memory (edt_fused.cu) ...
   static const bool force_legacy = getenv("B200_EDT_LEGACY") != nullptr;
+  static const bool no_overlap = getenv("B200_EDT_NO_OVERLAP") != nullptr;
+  if (!m->ov_ready && !no_overlap) {
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaStreamCreateWithFlags(&m->ov.s[i], cudaStreamNonBlocking));
+      CK(cudaEventCreate(&m->ov.y_done[i]));
+      CK(cudaEventCreate(&m->ov.x_done[i]));
+    }
+    CK(cudaEventCreateWithFlags(&m->ov.fork, cudaEventDisableTiming));
+    m->ov_ready = true;
+  }
   m->edt_fused = !force_legacy && m->edt_mode == 0 && launch_edt_fused(m->d, m->d_tmp, m->d_plane_empty, m->d.dist2, d_safe > 0 ? m->d.costq : nullptr, m->d_lut,
-                                                   lut_n, d_below, d_above, m->slab_total_nz, m->stream, m->profiling ? &m->ev[3] : nullptr);
+                                                   lut_n, d_below, d_above, m->slab_total_nz, m->stream, m->profiling ? &m->ev[3] : nullptr,
+                                                   m->ov_ready ? &m->ov : nullptr);
   if (m->edt_fused) m->launches += 2;
   else {
     // ... else the seven-kernel pipeline with its stacks in HBM (edt_kernels.cu)
@@ -1006,8 +1025,18 @@ int b200_map_get_stage_ms(b200_map_t* m, double out[16]) {
   if (cudaEventElapsedTime(&t, m->ev[0], m->ev[1]) == cudaSuccess) out[0] = t;
   if (cudaEventElapsedTime(&t, m->ev[1], m->ev[2]) == cudaSuccess) out[1] = t;
   if (m->edt_fused) {
-    for (int i = 0; i < 2; ++i)
-      if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[9 + i] = t;
+    // with the two-stream overlap the split is: pass 1 = until BOTH halves' first kernels are done, pass 2 = the rest
+    float y0 = -1.f, y1 = -1.f, all = -1.f;
+    if (m->ov_ready && cudaEventElapsedTime(&y0, m->ev[3], m->ov.y_done[0]) == cudaSuccess &&
+        cudaEventElapsedTime(&y1, m->ev[3], m->ov.y_done[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&all, m->ev[3], m->ev[5]) == cudaSuccess && y0 >= 0 && y1 >= 0 && std::max(y0, y1) <= all) {
+      out[9] = std::max(y0, y1);
+      out[10] = all - out[9];
+    } else {
+      cudaGetLastError();
+      for (int i = 0; i < 2; ++i)
+        if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[9 + i] = t;
+    }
   } else {
     for (int i = 0; i < 7; ++i)
       if (cudaEventElapsedTime(&t, m->ev[3 + i], m->ev[4 + i]) == cudaSuccess) out[2 + i] = t;

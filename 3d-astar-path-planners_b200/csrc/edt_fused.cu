@@ -76,28 +76,28 @@ __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(siz
 // pass 1: bits -> z distance (on the fly, per site) -> hull along y -> packed (dy, dz) or int32 squared distance
 // ---------------------------------------------------------------------------------------------------
 template <int NB, int W, class Tr, class TmpT, bool BULK>
-__global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
+__global__ void __launch_bounds__(NB* W, 5)
     edt_fused_y_kernel(MapDev m, const int32_t* __restrict__ below_gap, const int32_t* __restrict__ above_gap, TmpT* __restrict__ tmp,
-                       uint8_t* __restrict__ plane_empty, int SB, int BL, int DYB) {
+                       uint8_t* __restrict__ plane_empty, int SB, int BL, int DYB, int zt0, int nzt) {
   using E = typename Tr::E;
   constexpr bool PACKED = sizeof(TmpT) == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Ny = m.Ny, Nz = m.Nz, wz = m.wz;
   E* st = reinterpret_cast<E*>(smem_raw);
-  // BULK: all the plane's bit words [Ny][wz]; else only the tile's own word of every column [Ny]
-  uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw + align16((size_t)NB * BL * W * sizeof(E)));
-  int2* outside = reinterpret_cast<int2*>(bits + (((size_t)Ny * (BULK ? wz : 1) + 3) & ~(size_t)3));  // per column: nearest z below / above the own word
+  // BULK: the plane's bit words [Ny][wz] land in the (not yet used) stack region; what the scan needs of them — the
+  // tile's own word of every column and the nearest occupied z outside it — is copied out before the stack is built
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* own = reinterpret_cast<uint32_t*>(smem_raw + align16((size_t)NB * BL * W * sizeof(E)));
+  int2* outside = reinterpret_cast<int2*>(own + (((size_t)Ny + 3) & ~(size_t)3));  // per column: nearest z below / above the own word
   uint32_t* rng = reinterpret_cast<uint32_t*>(outside + Ny);
   uint16_t* off = reinterpret_cast<uint16_t*>(rng + NB * W);
   int* total = reinterpret_cast<int*>(off + NB * W);
   __shared__ __align__(8) uint64_t bar;
 
-  const int ztiles = (Nz + W - 1) / W;
-  const int x = blockIdx.x / ztiles, z0 = (blockIdx.x % ztiles) * W;
+  const int x = blockIdx.x / nzt, z0 = (zt0 + blockIdx.x % nzt) * W;  // this launch covers the z-tiles [zt0, zt0 + nzt)
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
   const int wi = z0 >> 5;
   const uint32_t* plane_bits = m.occ + (size_t)x * Ny * wz;
-  const int bstride = BULK ? wz : 1, boff = BULK ? wi : 0;
   if (BULK) {  // one bulk async copy of the plane's words (TMA engine), completion on an mbarrier
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
@@ -112,10 +112,12 @@ __global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
     const size_t col = (size_t)x * Ny + y;
     const int bg = below_gap ? __ldg(below_gap + col) : 0, ag = above_gap ? __ldg(above_gap + col) : 0;
     int lo, hi;
-    if (BULK) column_outside(bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
-    else {  // planes too large to stage whole: the other words of the column come straight from L2
+    if (BULK) {
+      column_outside(bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
+      own[y] = bits[(size_t)y * wz + wi];
+    } else {  // planes too large to stage whole: the other words of the column come straight from L2
       column_outside(plane_bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
-      bits[y] = __ldg(plane_bits + (size_t)y * wz + wi);
+      own[y] = __ldg(plane_bits + (size_t)y * wz + wi);
     }
     outside[y] = make_int2(lo, hi);
   }
@@ -127,10 +129,9 @@ __global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
     HullBuilder<Tr> hb;
     hb.init(st + (size_t)band * BL * W + lane, W, SB, u0);
     if (active) {
-      const uint32_t* wp = bits + (size_t)u0 * bstride + boff;
-      for (int u = u0; u < u1; ++u, wp += bstride) {
+      for (int u = u0; u < u1; ++u) {
         const int2 o = outside[u];
-        const int d = site_dz(*wp, bi, z, o.x, o.y);
+        const int d = site_dz(own[u], bi, z, o.x, o.y);
         if (d < kDzNone) hb.push(u, (uint32_t)d);
       }
     }
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(NB* W, (NB * W <= 256 ? 4 : 3))
   }
   const int T = merge_bands<NB, W, Tr>(st, rng, off, total, SB, BL, band, lane);
   if (!active) return;
-  if (PACKED && blockIdx.x % ztiles == 0 && tid == 0) plane_empty[x] = T == 0;
+  if (PACKED && blockIdx.x % nzt == 0 && tid == 0) plane_empty[x] = T == 0;  // the same value from every z-tile
   TmpT* o = tmp + ((size_t)x * Ny + u0) * Nz + z;
   if (T == 0) {
     if (!PACKED)
@@ -161,7 +162,7 @@ constexpr int kSmemLut = 2048;  // cost-table entries kept in shared memory (d_s
 template <int NB, int W, class Tr, class TmpT>
 __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const TmpT* __restrict__ tmp, const uint8_t* __restrict__ plane_empty,
                                                            int32_t* __restrict__ dist2, uint16_t* __restrict__ costq,
-                                                           const uint16_t* __restrict__ lut, int lut_n, int SB, int BL, int DYB) {
+                                                           const uint16_t* __restrict__ lut, int lut_n, int SB, int BL, int DYB, int zt0, int nzt) {
   using E = typename Tr::E;
   constexpr bool PACKED = sizeof(TmpT) == 2;
   constexpr int PF = 8;
@@ -174,8 +175,7 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
   uint16_t* slut = reinterpret_cast<uint16_t*>(total + W);  // [min(lut_n, kSmemLut) + 1], last entry 0
   uint8_t* pe = reinterpret_cast<uint8_t*>(slut + kSmemLut + 2);
 
-  const int ztiles = (Nz + W - 1) / W;
-  const int y = blockIdx.x / ztiles, z0 = (blockIdx.x % ztiles) * W;
+  const int y = blockIdx.x / nzt, z0 = (zt0 + blockIdx.x % nzt) * W;
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
   const bool smem_lut = costq != nullptr && lut_n <= kSmemLut;
   int any_empty = 0;
@@ -260,12 +260,15 @@ Cfg cfg_of(size_t smem, int threads) {
   if (smem <= kMaxSmem) c.blocks_per_sm = (int)std::min<size_t>((228 * 1024) / (smem + 1024), 2048 / threads);
   return c;
 }
-bool bulk_ok(const MapDev& m) { return ((size_t)m.Ny * m.wz) % 4 == 0 && (size_t)m.Ny * m.wz * 4 <= 16 * 1024; }
+template <int NB, int W, class E>
+bool bulk_ok(const MapDev& m) {  // 16-byte granularity of the bulk copy, and the plane has to fit in the stack region it lands in
+  const int BL = (m.Ny + NB - 1) / NB;
+  return ((size_t)m.Ny * m.wz) % 4 == 0 && (size_t)m.Ny * m.wz * 4 <= (size_t)NB * BL * W * sizeof(E);
+}
 template <int NB, int W, class E>
 size_t smem_y(const MapDev& m) {
   const int BL = (m.Ny + NB - 1) / NB;
-  const size_t words = (((size_t)m.Ny * (bulk_ok(m) ? m.wz : 1)) + 3) & ~(size_t)3;
-  return align16((size_t)NB * BL * W * sizeof(E)) + words * 4 + (size_t)m.Ny * 8 + (size_t)NB * W * 6 + (size_t)W * 4 + 16;
+  return align16((size_t)NB * BL * W * sizeof(E)) + ((((size_t)m.Ny) + 3) & ~(size_t)3) * 4 + (size_t)m.Ny * 8 + (size_t)NB * W * 6 + (size_t)W * 4 + 16;
 }
 template <int NB, int W, class E>
 size_t smem_x(const MapDev& m) {
@@ -274,9 +277,10 @@ size_t smem_x(const MapDev& m) {
 }
 
 template <int NB, int W, class Tr, class TmpT>
-bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* below_gap, const int32_t* above_gap, cudaStream_t stream) {
+bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* below_gap, const int32_t* above_gap, int zt0, int nzt,
+              cudaStream_t stream) {
   const size_t sy = smem_y<NB, W, typename Tr::E>(m);
-  const bool bulk = bulk_ok(m);
+  const bool bulk = bulk_ok<NB, W, typename Tr::E>(m);
   auto k = bulk ? edt_fused_y_kernel<NB, W, Tr, TmpT, true> : edt_fused_y_kernel<NB, W, Tr, TmpT, false>;
   static size_t configured[64][2] = {};  // per instantiation and device: the opt-in is a driver call, pay it once per size
   int dev = 0;
@@ -285,14 +289,14 @@ bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* b
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sy) != cudaSuccess) { cudaGetLastError(); return false; }
     configured[dev & 63][bulk] = sy;
   }
-  const int ztiles = (m.Nz + W - 1) / W, BL = (m.Ny + NB - 1) / NB;
-  k<<<(unsigned)(m.Nx * ztiles), NB * W, sy, stream>>>(m, below_gap, above_gap, (TmpT*)tmp, plane_empty, bits_of((unsigned)(BL - 1)), BL,
-                                                        bits_of((unsigned)(m.Ny - 1)));
+  const int BL = (m.Ny + NB - 1) / NB;
+  k<<<(unsigned)(m.Nx * nzt), NB * W, sy, stream>>>(m, below_gap, above_gap, (TmpT*)tmp, plane_empty, bits_of((unsigned)(BL - 1)), BL,
+                                                     bits_of((unsigned)(m.Ny - 1)), zt0, nzt);
   return true;
 }
 template <int NB, int W, class Tr, class TmpT>
 bool launch_x(const MapDev& m, const void* tmp, const uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-              cudaStream_t stream) {
+              int zt0, int nzt, cudaStream_t stream) {
   const size_t sx = smem_x<NB, W, typename Tr::E>(m);
   auto k = edt_fused_x_kernel<NB, W, Tr, TmpT>;
   static size_t configured[64] = {};
@@ -302,9 +306,9 @@ bool launch_x(const MapDev& m, const void* tmp, const uint8_t* plane_empty, int3
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx) != cudaSuccess) { cudaGetLastError(); return false; }
     configured[dev & 63] = sx;
   }
-  const int ztiles = (m.Nz + W - 1) / W, BL = (m.Nx + NB - 1) / NB;
-  k<<<(unsigned)(m.Ny * ztiles), NB * W, sx, stream>>>(m, (const TmpT*)tmp, plane_empty, dist2, costq, lut, lut_n, bits_of((unsigned)(BL - 1)), BL,
-                                                        bits_of((unsigned)(m.Ny - 1)));
+  const int BL = (m.Nx + NB - 1) / NB;
+  k<<<(unsigned)(m.Ny * nzt), NB * W, sx, stream>>>(m, (const TmpT*)tmp, plane_empty, dist2, costq, lut, lut_n, bits_of((unsigned)(BL - 1)), BL,
+                                                     bits_of((unsigned)(m.Ny - 1)), zt0, nzt);
   return true;
 }
 // The three tile shapes (bands x lanes, 256 threads): the one that keeps the most blocks resident per SM (the kernels are
@@ -333,7 +337,7 @@ size_t edt_fused_plane_flags_bytes(const MapDev& m) { return (size_t)m.Nx + 16; 
 // tmp: 4 B/voxel scratch (2 B/voxel used in the packed case); ev (optional): 3 events before y, between, after x.
 // dz_bound: with a halo, an upper bound on any z distance (the stacked grid's total height), 0 when unknown.
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev) {
+                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev, EdtOverlap* ov) {
   if (m.Nx < 2 || m.Ny < 2 || m.Nx > 32768 || m.Ny > 32768) return false;
   const bool halo = below_gap || above_gap;
   const unsigned long long ny1 = m.Ny - 1, nx1 = m.Nx - 1, nz1 = m.Nz - 1;
@@ -344,14 +348,38 @@ bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t*
   const bool small = !halo && bits_of(ny1) + bits_of(nz1) <= 16 && sby8 + bits_of(nz1) <= 16 && sbx8 + bits_of(g1) <= 32 &&
                      (ny1 * ny1 + nz1 * nz1) * ny1 < (1ull << 31) && (nx1 * nx1 + g1) * nx1 < (1ull << 31) &&
                      cfg_of(smem_y<8, 32, uint16_t>(m), 256).blocks_per_sm >= 2 && cfg_of(smem_x<8, 32, uint32_t>(m), 256).blocks_per_sm >= 2;
+  // Two halves of the z range on two streams: pass 2 of a z-tile only needs pass 1 of the same z-tile, so the last,
+  // partly filled wave of one kernel overlaps the first wave of the next instead of idling the SMs (4 launches, each
+  // kernel's tail hidden but the last one's).  ov == nullptr or a single z-tile: one stream, two launches.
+  auto run = [&](auto&& launch_y_fn, auto&& launch_x_fn, int W) -> bool {
+    const int ztiles = (m.Nz + W - 1) / W;
+    if (!ov || ztiles < 2) {
+      bool ok = launch_y_fn(0, ztiles, stream);
+      if (ev) cudaEventRecord(ev[1], stream);
+      return ok && launch_x_fn(0, ztiles, stream);
+    }
+    const int h = (ztiles + 1) / 2;
+    cudaEventRecord(ov->fork, stream);
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) {
+      cudaStreamWaitEvent(ov->s[i], ov->fork, 0);
+      ok = ok && launch_y_fn(i ? h : 0, i ? ztiles - h : h, ov->s[i]);
+      cudaEventRecord(ov->y_done[i], ov->s[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ok = ok && launch_x_fn(i ? h : 0, i ? ztiles - h : h, ov->s[i]);
+      cudaEventRecord(ov->x_done[i], ov->s[i]);
+      cudaStreamWaitEvent(stream, ov->x_done[i], 0);
+    }
+    return ok;
+  };
   if (ev) cudaEventRecord(ev[0], stream);
   bool ok;
   if (small) {
     using TY = PassY<uint16_t, int32_t>;
     using TX = PassX<uint32_t, int32_t>;
-    ok = launch_y<8, 32, TY, uint16_t>(m, tmp, plane_empty, nullptr, nullptr, stream);
-    if (ev) cudaEventRecord(ev[1], stream);
-    ok = ok && launch_x<8, 32, TX, uint16_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream);
+    ok = run([&](int z0, int nz, cudaStream_t st) { return launch_y<8, 32, TY, uint16_t>(m, tmp, plane_empty, nullptr, nullptr, z0, nz, st); },
+             [&](int z0, int nz, cudaStream_t st) { return launch_x<8, 32, TX, uint16_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st); }, 32);
   } else {
     // "large" family: int32 intermediate, 64-bit cross products, 32-bit (s, dz) entries (z distances < 65535, as in the
     // seven-kernel pipeline's wide mode), (s, g) entries of 32 bits when 6..8 bits of band-relative site + g fit, else 64;
@@ -372,26 +400,38 @@ bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t*
     const unsigned long long gmax = !halo ? g1 : (dz_bound > 0 ? std::min<unsigned long long>(dzb * dzb + ny1 * ny1, (1ull << 29) - 1) : (1ull << 29) - 1);
     auto sbx = [&](int nb) { return bits_of((unsigned)((m.Nx + nb - 1) / nb - 1)); };
     int shx = pick_shape<uint32_t, false>(m);
-    bool x32 = shx != 0 && sbx(shx == 1 ? 8 : shx == 2 ? 16 : 32) + bits_of(gmax) <= 32;
+    const bool x32 = shx != 0 && sbx(shx == 1 ? 8 : shx == 2 ? 16 : 32) + bits_of(gmax) <= 32;
     if (!x32) shx = pick_shape<uint64_t, false>(m);
     if (!shy || !shx) return false;
-    if (y16)
-      ok = shy == 1   ? launch_y<8, 32, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-           : shy == 2 ? launch_y<16, 16, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-                      : launch_y<32, 8, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
-    else
-      ok = shy == 1   ? launch_y<8, 32, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-           : shy == 2 ? launch_y<16, 16, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream)
-                      : launch_y<32, 8, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, stream);
-    if (ev) cudaEventRecord(ev[1], stream);
-    if (x32)
-      ok = ok && (shx == 1   ? launch_x<8, 32, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
-                  : shx == 2 ? launch_x<16, 16, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
-                             : launch_x<32, 8, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream));
-    else
-      ok = ok && (shx == 1   ? launch_x<8, 32, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
-                  : shx == 2 ? launch_x<16, 16, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream)
-                             : launch_x<32, 8, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, stream));
+    auto ly = [&](int z0, int nz, cudaStream_t st) -> bool {
+      if (y16)
+        return shy == 1   ? launch_y<8, 32, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st)
+               : shy == 2 ? launch_y<16, 16, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st)
+                          : launch_y<32, 8, GY2, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st);
+      return shy == 1   ? launch_y<8, 32, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st)
+             : shy == 2 ? launch_y<16, 16, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st)
+                        : launch_y<32, 8, GY, int32_t>(m, tmp, plane_empty, below_gap, above_gap, z0, nz, st);
+    };
+    auto lx = [&](int z0, int nz, cudaStream_t st) -> bool {
+      if (x32)
+        return shx == 1   ? launch_x<8, 32, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st)
+               : shx == 2 ? launch_x<16, 16, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st)
+                          : launch_x<32, 8, GX4, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st);
+      return shx == 1   ? launch_x<8, 32, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st)
+             : shx == 2 ? launch_x<16, 16, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st)
+                        : launch_x<32, 8, GX8, int32_t>(m, tmp, plane_empty, dist2, costq, lut, lut_n, z0, nz, st);
+    };
+    // the two passes may use different lane widths: split on the coarser tile so both launches cover the same z range
+    const int wy = shy == 1 ? 32 : shy == 2 ? 16 : 8, wx = shx == 1 ? 32 : shx == 2 ? 16 : 8;
+    if (wy == wx) ok = run(ly, lx, wy);
+    else {
+      EdtOverlap* keep = ov;
+      ov = nullptr;  // different tilings: keep it simple, one stream
+      ok = ly(0, (m.Nz + wy - 1) / wy, stream);
+      if (ev) cudaEventRecord(ev[1], stream);
+      ok = ok && lx(0, (m.Nz + wx - 1) / wx, stream);
+      ov = keep;
+    }
   }
   if (ev) cudaEventRecord(ev[2], stream);
   return ok;

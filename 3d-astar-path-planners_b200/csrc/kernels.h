@@ -34,9 +34,13 @@ void launch_edt(const MapDev& m, void* dzbuf, int32_t* tmp, uint2* st, int* coun
                 cudaEvent_t* ev);
 void launch_cost_lut(uint16_t* lut, int lut_n, double res, double d_safe, cudaStream_t stream);
 // ---- edt_fused.cu: two shared-memory-staged kernels; false when no configuration fits the grid
+struct EdtOverlap {  // optional: two auxiliary streams + events so the z range can be processed as two overlapping halves
+  cudaStream_t s[2];
+  cudaEvent_t fork, y_done[2], x_done[2];
+};
 size_t edt_fused_plane_flags_bytes(const MapDev& m);
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
-                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev);
+                      const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev, EdtOverlap* ov);
 void launch_column_extents(const MapDev& m, int32_t* lowest, int32_t* highest, cudaStream_t stream);
 constexpr int kMaxSlabs = 64;
 void launch_column_extents16(const MapDev& m, short2* lo_hi, cudaStream_t stream);
