@@ -588,19 +588,22 @@ int b200_map_update_depth(b200_map_t* m, const uint16_t* depth, int32_t rows, in
   }
   const long long n_rays = (long long)rows_s * cols_s;
   if (n_rays == 0) return B200_OK;  // raycastProcess :320: nothing projected, nothing happens
-  REQUIRE(n_rays < 0x7fffffff, "depth image too large");
+  REQUIRE(n_rays < (1LL << 24), "depth image too large (more than 2^24 sampled pixels)");  // 8 bits of round stamp remain
   const uint16_t* d_img = depth;
   if (!on_device) {
     if (m->depth_img.ensure((size_t)rows * cols * 2)) return fail(B200_ERR_NOMEM, "depth image staging");
     CK(cudaMemcpyAsync(m->depth_img.p, depth, (size_t)rows * cols * 2, cudaMemcpyHostToDevice, st));
     d_img = (const uint16_t*)m->depth_img.p;
   }
-  if (m->depth_rays.ensure((size_t)n_rays * 40)) return fail(B200_ERR_NOMEM, "ray records");
+  if (m->depth_rays.ensure((size_t)n_rays * 44)) return fail(B200_ERR_NOMEM, "ray records");
   D.ray_pt = (double*)m->depth_rays.p;
   D.ray_addr = (uint32_t*)((char*)m->depth_rays.p + (size_t)n_rays * 24);
   D.cast_id = D.ray_addr + n_rays;
   D.path_off = D.cast_id + n_rays;
   D.path_len = D.path_off + n_rays;
+  D.stop = D.path_len + n_rays;
+  D.id_bits = 1;
+  while ((1LL << D.id_bits) < n_rays) ++D.id_bits;  // < 31 (n_rays < 2^31): at least two stamp bits... checked below
   D.rows = rows; D.cols = cols; D.cols_s = cols_s; D.n_rays = (int)n_rays;
   for (int i = 0; i < 3; ++i) D.cam[i] = cam_pos[i];
   for (int i = 0; i < 9; ++i) D.R[i] = cam_rot[i];

@@ -28,6 +28,7 @@
 #include <cooperative_groups.h>
 #include <cstdint>
 
+#include <cstdlib>
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -233,25 +234,46 @@ __global__ void __launch_bounds__(128) depth_path_fill_kernel(DepthDev D, MapDev
     out[k] = a < 0 ? kNone : (uint32_t)a;
   }
 }
-// One cast ray handled by one warp, 32 path voxels per step.  MODE 0: a round of the ordering iteration (reads F, writes
-// Fnew); MODE 1: the counting walk under the converged F.
+// One cast ray handled by one warp, 32 path voxels per step.  MODE 0: a round of the ordering iteration; MODE 1: the
+// counting walk under the converged state.  Returns the number of path voxels the ray visits (warp-uniform).
+//
+// The two per-voxel arrays F / Fnew alternate as "written this round" / "written last round" WITHOUT ever being cleared
+// inside a frame: an entry is (stamp << id_bits) | ray id with stamp = kMaxStamp - round, so under atomicMin an entry of
+// the current round always beats whatever an older round left in the same array, and a reader only accepts entries that
+// carry the previous round's stamp.  0xffffffff (the between-frames value) carries a stamp no round ever has.
+struct StampCode {
+  int idb;
+  uint32_t idmask, max_stamp;
+  __device__ __forceinline__ explicit StampCode(int id_bits) : idb(id_bits), idmask((1u << id_bits) - 1u), max_stamp((1u << (32 - id_bits)) - 2u) {}
+  __device__ __forceinline__ uint32_t key(unsigned round, uint32_t id) const { return ((max_stamp - round) << idb) | id; }
+  // ray id stored for `round` in v, kNone when v is from another round (or empty)
+  __device__ __forceinline__ uint32_t id_of(uint32_t v, unsigned round) const { return (v >> idb) == max_stamp - round ? (v & idmask) : kNone; }
+};
+constexpr int kOrderThreads = 1024;  // few, large blocks: the grid barrier is what a round costs, and its price grows with the block count
 template <int MODE>
-__device__ __forceinline__ void walk_path(const DepthDev& D, unsigned slot, int lane, bool first_round) {
+__device__ __forceinline__ unsigned walk_path(const DepthDev& D, unsigned slot, int lane, unsigned round) {
+  const StampCode sc(D.id_bits);
   const uint32_t id = D.cast_id[slot];
   const uint32_t* path = D.paths + D.path_off[slot];
   const unsigned len = D.path_len[slot];
+  // MODE 0 reads what round - 1 wrote (nothing in round 0) and writes the other array; MODE 1 reads what `round` wrote
+  const unsigned rd_round = MODE == 0 ? round - 1u : round;
+  const uint32_t* rd = (rd_round & 1u) ? D.Fnew : D.F;
+  uint32_t* wr = (round & 1u) ? D.Fnew : D.F;
+  const bool have_prev = MODE == 1 || round > 0;
   unsigned steps = len;
   for (unsigned base = 0; base < len; base += 32) {
     const unsigned k = base + lane;
     const uint32_t a = k < len ? path[k] : kNone;
     // :410 flag_traverse_[v] == raycast_num_ at the moment ray `id` arrives
-    const bool taken = a != kNone && (D.flagT[a] == D.round || D.F[a] < id);
+    bool taken = false;
+    if (a != kNone) taken = D.flagT[a] == D.round || (have_prev && sc.id_of(rd[a], rd_round) < id);
     const unsigned tm = __ballot_sync(0xffffffffu, taken);
     const int first = tm ? __ffs(tm) - 1 : 32;
     if (MODE == 0) {
       if (a != kNone && lane < first) {
-        const uint32_t old = atomicMin(&D.Fnew[a], id);
-        if (first_round && old == kNone) append(D.walked, &D.ctl->n_walked, a);
+        const uint32_t old = atomicMin(&wr[a], sc.key(round, id));
+        if (round == 0 && old == kNone) append(D.walked, &D.ctl->n_walked, a);
       }
     } else {
       // :406 the voxel the ray stops at is counted too (the count comes before the stop test)
@@ -263,43 +285,90 @@ __device__ __forceinline__ void walk_path(const DepthDev& D, unsigned slot, int 
     atomicAdd(&D.ctl->n_cast, 1ull);
     atomicAdd(&D.ctl->n_steps, (unsigned long long)steps);
   }
+  return steps;
 }
 __global__ void __launch_bounds__(128) depth_count_kernel(DepthDev D) {
   const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slot < D.ctl->n_cast_rays) walk_path<1>(D, slot, threadIdx.x & 31, false);
+  if (slot < D.ctl->n_cast_rays) walk_path<1>(D, slot, threadIdx.x & 31, D.ctl->rounds - 1u);
 }
-// The whole fixed-point iteration in one cooperative launch: per round every cast ray walks under F into Fnew, after
-// which Fnew becomes F on the voxels the first round walked (a superset of every later round's), until a round
-// changes nothing.
-__global__ void __launch_bounds__(128) depth_order_kernel(DepthDev D) {
+// The whole fixed-point iteration in one cooperative launch, ONE grid barrier per round: every cast ray walks under what
+// the previous round wrote and writes this round's entries into the other array.  The state of a round is determined by
+// where each ray stops, so "no ray stopped anywhere else than in the previous round" is the fixed point — no per-voxel
+// comparison or copy pass (the first version had both, and two barriers per round: 12 us per round instead of 6).
+__global__ void __launch_bounds__(kOrderThreads) depth_order_kernel(DepthDev D) {
   cg::grid_group grid = cg::this_grid();
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
   const unsigned n_cast = D.ctl->n_cast_rays;
+  const StampCode sc(D.id_bits);
+  const unsigned round_limit = min(n_cast + 2u, sc.max_stamp - 1u);
+  // Usual case (a 640x480 frame casts ~3 000 rays of ~8 voxels): every ray has a warp of its own and its path fits one
+  // 32-voxel step, so everything that does not change between rounds — ray id, path voxels, the persistent
+  // flag_traverse_ test — is read ONCE into registers and a round is one load, one ballot, one atomicMin and the barrier
+  // (a round cost 12 us when the ray record, path and flags were re-read through L2 every time).
+  const unsigned slot0 = tid >> 5;
+  const bool one_ray_per_warp = n_cast <= (nthreads >> 5);
+  uint32_t c_id = 0, c_len = 0, c_a = kNone;
+  bool c_short = false, c_flag = false;
+  if (one_ray_per_warp && slot0 < n_cast) {
+    c_id = D.cast_id[slot0];
+    c_len = D.path_len[slot0];
+    c_short = c_len <= 32u;
+    if (c_short) {
+      c_a = (unsigned)lane < c_len ? D.paths[D.path_off[slot0] + lane] : kNone;
+      c_flag = c_a != kNone && D.flagT[c_a] == D.round;
+    }
+  }
+  unsigned my_stop = 0xffffffffu;
   unsigned round = 0;
   for (;; ++round) {
-    for (unsigned slot = tid >> 5; slot < n_cast; slot += nthreads >> 5) walk_path<0>(D, slot, threadIdx.x & 31, round == 0);
+    bool changed = false;
+    if (one_ray_per_warp) {
+      if (slot0 < n_cast) {
+        unsigned steps;
+        if (c_short) {
+          const uint32_t* rd = ((round - 1u) & 1u) ? D.Fnew : D.F;
+          uint32_t* wr = (round & 1u) ? D.Fnew : D.F;
+          bool taken = c_flag;
+          if (!taken && round > 0 && c_a != kNone) taken = sc.id_of(rd[c_a], round - 1u) < c_id;
+          const unsigned tm = __ballot_sync(0xffffffffu, taken);
+          const int first = tm ? __ffs(tm) - 1 : 32;
+          if (c_a != kNone && lane < first) {
+            const uint32_t old = atomicMin(&wr[c_a], sc.key(round, c_id));
+            if (round == 0 && old == kNone) append(D.walked, &D.ctl->n_walked, c_a);
+          }
+          steps = tm ? (unsigned)first + 1u : c_len;
+        } else {
+          steps = walk_path<0>(D, slot0, lane, round);
+        }
+        changed = steps != my_stop;
+        my_stop = steps;
+      }
+    } else {
+      for (unsigned slot = slot0; slot < n_cast; slot += nthreads >> 5) {  // a slot is always handled by the same warp
+        const unsigned steps = walk_path<0>(D, slot, lane, round);
+        if (round == 0 || D.stop[slot] != steps) changed = true;
+        if (lane == 0) D.stop[slot] = steps;
+      }
+    }
+    if (changed && lane == 0) D.ctl->changed[round % 3] = 1u;
     if (tid == 0) D.ctl->changed[(round + 1) % 3] = 0u;  // three slots: the one read at the end of the previous round is left alone
     grid.sync();
-    const unsigned n = D.ctl->n_walked;
-    bool any = false;
-    for (unsigned i = tid; i < n; i += nthreads) {
-      const uint32_t a = D.walked[i];
-      const uint32_t f = D.Fnew[a];
-      if (f != D.F[a]) { D.F[a] = f; any = true; }
-      D.Fnew[a] = kNone;
-    }
-    if (any) D.ctl->changed[round % 3] = 1u;
-    grid.sync();
-    if (D.ctl->changed[round % 3] == 0u || round > n_cast + 2u) break;
+    if (D.ctl->changed[round % 3] == 0u || round >= round_limit) break;
   }
-  if (tid == 0) D.ctl->rounds = round + 1u;
+  // the last round's array holds the converged state; 0xffffffff = no fixed point within the stamp range (the host fails the call)
+  if (tid == 0) D.ctl->rounds = D.ctl->changed[round % 3] == 0u ? round + 1u : 0xffffffffu;
 }
 // end of frame: the persistent flags take this frame's number, the per-frame ray ids go back to "none"
 __global__ void __launch_bounds__(256) depth_reset_kernel(DepthDev D) {
   const unsigned n = D.ctl->n_walked, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const StampCode sc(D.id_bits);
+  const unsigned last = D.ctl->rounds - 1u;
+  const uint32_t* fin = (last & 1u) ? D.Fnew : D.F;
   for (unsigned i = t0; i < n; i += stride) {
     const uint32_t a = D.walked[i];
-    if (D.F[a] != kNone) D.flagT[a] = D.round;  // :416: every voxel some ray reached keeps this frame's number
+    // :416: every voxel some ray reached (in the converged state = the last round's entries) keeps this frame's number
+    if (sc.id_of(fin[a], last) != kNone) D.flagT[a] = D.round;
     D.F[a] = kNone; D.Fnew[a] = kNone;
   }
   for (unsigned i = t0; i < (unsigned)D.n_rays; i += stride) {
@@ -493,14 +562,16 @@ void launch_depth_path_fill(const DepthDev& D, const MapDev& m, unsigned n_cast,
 int launch_depth_order(const DepthDev& D, unsigned n_cast, int sm_count, cudaStream_t st) {
   if (n_cast == 0) return 0;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_order_kernel, 128, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_order_kernel, kOrderThreads, 0);
   if (e != cudaSuccess) return (int)e;
-  const unsigned want = blocks_for((long long)n_cast * 32, 128);  // a warp per cast ray
-  unsigned grid = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)sm_count;
+  const unsigned want = blocks_for((long long)n_cast * 32, kOrderThreads);  // a warp per cast ray
+  static const int cap_env = getenv("B200_DEPTH_ORDER_BLOCKS") ? atoi(getenv("B200_DEPTH_ORDER_BLOCKS")) : 0;
+  unsigned grid = cap_env > 0 ? (unsigned)cap_env : (unsigned)sm_count;  // one block per SM at most
+  if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
   if (grid > want) grid = want;
   DepthDev d = D;
   void* args[] = {&d};
-  return (int)cudaLaunchCooperativeKernel((void*)depth_order_kernel, dim3(grid), dim3(128), args, 0, st);
+  return (int)cudaLaunchCooperativeKernel((void*)depth_order_kernel, dim3(grid), dim3(kOrderThreads), args, 0, st);
 }
 void launch_depth_count(const DepthDev& D, unsigned n_cast, cudaStream_t st) {
   if (n_cast) depth_count_kernel<<<blocks_for((long long)n_cast * 32, 128), 128, 0, st>>>(D);

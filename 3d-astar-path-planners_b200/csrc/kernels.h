@@ -132,12 +132,15 @@ struct DepthDev {
   // state in HBM (per voxel unless noted)
   double* occ;                    // occupancy_buffer_ (log-odds)
   uint32_t *cnt_all, *cnt_hit;    // count_hit_and_miss_, count_hit_ (exact totals; the reference's shorts are their low 16 bits)
-  uint32_t *F, *Fnew, *E;         // this frame: smallest ray id reaching / ending in the voxel (0xffffffff = none)
+  uint32_t *F, *Fnew, *E;         // this frame: E = smallest ray id ending in the voxel; F / Fnew = (round stamp | smallest ray
+                                  // id reaching the voxel), written alternately by the ordering rounds (0xffffffff = none)
   int8_t *flagT, *flagE;          // flag_traverse_, flag_rayend_: raycast_num_ of the last frame that set them (never cleared)
   uint32_t *touched, *walked;     // voxel lists: counted this frame / reached in the first round
   double* ray_pt;                 // [n_rays][3] clamped ray end points
   uint32_t* ray_addr;             // [n_rays] end voxel address
   uint32_t *cast_id, *path_off, *path_len;  // [n_cast_rays] the rays that are cast: id, and their slice of `paths`
+  uint32_t* stop;                 // [n_cast_rays] path voxels the ray visited in the last ordering round
+  int id_bits;                    // bits of a ray id inside an F / Fnew entry (the rest is the round stamp)
   uint32_t* paths;                // voxel address sequences of the cast rays (0xffffffff = cell outside the buffer)
   DepthCtl* ctl;
 };
