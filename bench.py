@@ -625,7 +625,12 @@ def main():
 
     # ---- extras: batched query throughput on this map (sharded over ranks, no collective)
     scaling = {}
+    qsampler = None
     if not args.no_extra:
+        # every rank samples ITS GPU's clocks over the query phase: per-rank rates differ when eight GPUs of one box do
+        # not hold the same clock under load, and the scaling block should show that next to the rates
+        qsampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+        qsampler.start()
         occ = lambda p: gm.getInflateOccupancy(p)
         gm.build_edt(D_SAFE)
         om = None
@@ -754,6 +759,13 @@ def main():
                               "gpu_over_cpu_all_threads": qps / (n_nt / t_nt)}
             pl.close()
             del ds, dg, dres
+        qclk = qsampler.stop()
+        if world > 1:
+            allclk = [None] * world
+            dist.all_gather_object(allclk, {"sm_mhz": qclk.get("sm_mhz"), "sm_min_mhz": qclk.get("sm_min_mhz"), "reasons": qclk.get("reasons")})
+        else:
+            allclk = [{"sm_mhz": qclk.get("sm_mhz"), "sm_min_mhz": qclk.get("sm_min_mhz"), "reasons": qclk.get("reasons")}]
+        scaling["per_rank_clocks_during_queries"] = allclk
         extra["scaling"] = scaling
         if cpu_q:
             extra["cpu_baseline_queries"] = {"kind": "port (oracle/liboracle.so, same semantics as the GPU column)", "map": "C2", **cpu_q}
