@@ -1,0 +1,67 @@
+"""-m gpu: the N > 1 query path on real kernels — `shard.find_paths_sharded` run by two "ranks" on ONE GPU (two map
+replicas + two planner handles, each on its own CUDA stream, the ranks in two threads joined by a stand-in for
+torch.distributed.all_gather_object).  The assembled result must equal the unsharded run and the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+from util import assert_results_equal, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+class _ThreadDist:
+    """all_gather_object for `world` threads of one process (what torch.distributed does across ranks)."""
+
+    def __init__(self, world):
+        self.world, self.slots = world, {}
+        self.barrier = threading.Barrier(world)
+        self.tls = threading.local()
+
+    def all_gather_object(self, out, obj):
+        self.slots[self.tls.rank] = obj
+        self.barrier.wait()
+        for r in range(self.world):
+            out[r] = self.slots[r]
+        self.barrier.wait()
+
+
+@pytest.mark.parametrize("algo,sem", [("lazythetastar", "canonical"), ("thetastar", "faithful")])
+def test_sharded_queries_on_two_handles_equal_the_unsharded_run(b200, po, synth, algo, sem):
+    import torch
+    from astar_planners_b200 import shard
+    world, nq = 2, 600
+    maps, planners, streams = [], [], []
+    om = c = None
+    for r in range(world):
+        gm, om, c = make_pair(b200, po, synth, "C3")       # every rank rebuilds the replica from the same cloud
+        st = torch.cuda.Stream()
+        gm.set_stream(st.cuda_stream)
+        pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=200000, semantics=sem)
+        pl.setGridMap(gm)
+        maps.append(gm); planners.append(pl); streams.append(st)
+    s, g = synth.random_queries(9, om.get_inflate_occupancy, c["origin"], c["size"], nq, min_dist=3.0)
+    dist = _ThreadDist(world)
+    out, errs = [None] * world, []
+
+    def rank_main(r):
+        try:
+            dist.tls.rank = r
+            out[r] = shard.find_paths_sharded(lambda a, b: planners[r].findPaths(a, b)[0], s, g, r, world, dist)
+        except Exception as e:  # surface failures of a rank thread in the test
+            errs.append(e)
+            dist.barrier.abort()
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    whole, _ = planners[0].findPaths(s, g)
+    mode = po.FAITHFUL if sem == "faithful" else po.CANONICAL
+    ro, _ = po.OraclePlanner(algo, om, 0.1, 5.0, 200000, mode=mode).find_paths(s, g, nthreads=8)
+    for r in range(world):
+        assert len(out[r]) == nq
+        for f in ("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length", "goal_coords"):
+            assert np.array_equal(out[r][f], whole[f]), (r, f)
+        assert_results_equal(out[r], ro)
