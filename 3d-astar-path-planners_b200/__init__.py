@@ -116,6 +116,7 @@ ABI = [
     ("b200_los_batch", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
     ("b200_los_batch_dda", C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
     ("b200_map_set_profiling", C.c_int, [_vp, _i32]),
+    ("b200_map_launch_count", C.c_int, [_vp, C.POINTER(_i64)]),
     ("b200_map_get_stage_ms", C.c_int, [_vp, C.POINTER(_dbl)]),
     ("b200_planner_create", C.c_int, [C.c_char_p, C.POINTER(PlannerParams), _pp]),
     ("b200_planner_destroy", C.c_int, [_vp]),
@@ -498,6 +499,11 @@ class GridMap:
 
     def sync(self):
         _ck(lib().b200_map_sync(self.h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        _ck(lib().b200_map_launch_count(self.h, C.byref(n)))
+        return int(n.value)
 
     def set_profiling(self, on=True):
         _ck(lib().b200_map_set_profiling(self.h, 1 if on else 0))

@@ -70,6 +70,8 @@ struct b200_map {
   int slab_total_nz;       // z-slab sharding: height of the whole stacked grid (bounds the halo distances), 0 = unknown
   uint16_t* d_lut;
   int lut_cap;
+  int lut_n;          // entries and d_safe the table currently holds
+  double lut_d_safe;
   double* d_dk;
   double d_safe;
   bool has_edt;
@@ -198,6 +200,8 @@ int b200_map_create(const b200_map_params_t* p, b200_map_t** out) {
   m->ov_used = false;
   m->d_lut = nullptr;
   m->lut_cap = 0;
+  m->lut_n = 0;
+  m->lut_d_safe = -1.0;
   m->has_edt = false;
   m->d_safe = 0;
   m->profiling = false;
@@ -275,7 +279,8 @@ int b200_map_clear_box(b200_map_t* m, const double mn[3], const double mx[3]) {
   }
   launch_clear_box(m->d, a, b, m->sm_count, m->stream);
   m->has_edt = false;  // the distance / cost field describes the previous grid
-  m->launches++;
+  const bool whole = a[0] == 0 && a[1] == 0 && a[2] == 0 && b[0] == m->N[0] - 1 && b[1] == m->N[1] - 1 && b[2] == m->N[2] - 1;
+  if (!whole) m->launches++;  // the whole map is one cudaMemsetAsync, not a kernel of ours
   CK(cudaGetLastError());
   return B200_OK;
 }
@@ -436,9 +441,14 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
       m->d_lut = nullptr;
       if (!need((void**)&m->d_lut, (size_t)lut_n * 2)) return fail(B200_ERR_NOMEM, "cost table");
       m->lut_cap = lut_n;
+      m->lut_d_safe = -1.0;
     }
-    launch_cost_lut(m->d_lut, lut_n, m->prm.resolution, d_safe, m->stream);
-    m->launches++;
+    if (m->lut_d_safe != d_safe || m->lut_n != lut_n) {  // the table only depends on (resolution, d_safe)
+      launch_cost_lut(m->d_lut, lut_n, m->prm.resolution, d_safe, m->stream);
+      m->launches++;
+      m->lut_d_safe = d_safe;
+      m->lut_n = lut_n;
+    }
   }
   // two shared-memory-staged kernels when a line's hull stack fits in shared memory (edt_fused.cu) ...
   static const bool force_legacy = getenv("B200_EDT_LEGACY") != nullptr;
@@ -455,7 +465,7 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   m->edt_fused = !force_legacy && m->edt_mode == 0 && launch_edt_fused(m->d, m->d_tmp, m->d_plane_empty, m->d.dist2, d_safe > 0 ? m->d.costq : nullptr, m->d_lut,
                                                    lut_n, d_below, d_above, m->slab_total_nz, m->stream, m->profiling ? &m->ev[3] : nullptr,
                                                    m->ov_ready ? &m->ov : nullptr);
-  if (m->edt_fused) m->launches += 2;
+  if (m->edt_fused) m->launches += (m->ov_ready && m->N[2] > 32) ? 4 : 2;  // two z halves on two streams when there are >= 2 z-tiles
   else {
     // ... else the seven-kernel pipeline with its stacks in HBM (edt_kernels.cu)
     const int dz_bytes = edt_dz_is_wide(m->d, halo) ? 2 : 1;
@@ -1014,6 +1024,11 @@ int b200_map_export_occupancy_cloud(b200_map_t* m, int32_t which, int32_t margin
   return B200_OK;
 }
 
+int b200_map_launch_count(const b200_map_t* m, int64_t* n) {
+  REQUIRE(m && n, "NULL argument");
+  *n = m->launches;
+  return B200_OK;
+}
 int b200_map_set_profiling(b200_map_t* m, int32_t enable) {
   REQUIRE(m, "NULL map");
   m->profiling = enable != 0;

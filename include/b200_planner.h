@@ -229,6 +229,8 @@ int b200_los_batch_dda(b200_map_t* map, const double* seg_start_xyz, const doubl
  * [5] fill y, [6] scan x, [7] band crossovers x, [8] fill x (+cost); fused EDT: [9] pass z+y, [10] pass x (+cost);
  * [11..15] reserved. */
 int b200_map_set_profiling(b200_map_t* map, int32_t enable);
+/* Kernel launches this map has issued since it was created (for bench accounting; memsets and copies not counted). */
+int b200_map_launch_count(const b200_map_t* map, int64_t* n_launches);
 int b200_map_get_stage_ms(b200_map_t* map, double out_ms[16]);
 
 /* ---------------------------------------------------------------------------------------------------- */
