@@ -357,6 +357,7 @@ search_kernel(const SearchParams P) {
 
     // ---------------- search loop (AStar.cpp:103-173) ----------------
     int cur = 0;
+    int bypass = -1;  // node that skips the heap: see the push-then-pop bypass below
     double cx = 0, cy = 0, cz = 0, cg = 0, cpen = 0;
     bool cmotion = false;
     int cpar = -1;
@@ -368,13 +369,20 @@ search_kernel(const SearchParams P) {
       bool valid = false;
       if (warp == 0) {
         bool done = false;
-        if (s.heap_n == 0) {  // AStar.cpp:175-178
+        if (s.heap_n == 0 && bypass < 0) {  // AStar.cpp:175-178
           status = ST_OPEN_EMPTY; last = cur; done = true;
         } else {
-          open_peak = max(open_peak, s.heap_n);
-          const HeapEnt top = s.top[0];
-          NodeRec c = s.nodes[top.idx];  // in flight while the root is being replaced
-          cur = (int)heap_pop(s, lane, top);
+          open_peak = max(open_peak, s.heap_n + (bypass >= 0 ? 1 : 0));
+          NodeRec c;
+          if (bypass >= 0) {  // the previous expansion's best new node is the open list's minimum: it never entered the heap
+            cur = bypass;
+            bypass = -1;
+            c = s.nodes[cur];
+          } else {
+            const HeapEnt top = s.top[0];
+            c = s.nodes[top.idx];  // in flight while the root is being replaced
+            cur = (int)heap_pop(s, lane, top);
+          }
           if (IS_LAZY && c.parent >= 0 && c.parent != c.via) {
             // SetVertex: verify the optimistic parent with one fastLOS; fall back to the best closed neighbour
             const NodeRec pr = s.nodes[c.parent];
@@ -589,7 +597,31 @@ search_kernel(const SearchParams P) {
         __syncwarp();
         // open-list updates.  (f, index) is a total order, so the pop sequence does not depend on the heap's layout:
         // any valid heap holding the same entries will do.
-        heap_update_batch(s, improved, nb_hpos, fkey(new_f), (uint32_t)nb_idx, lane);
+        // Push-then-pop bypass.  With a weighted heuristic the best node generated by an expansion is usually the open
+        // list's new minimum: pushing it (a climb to the root, the longest one) only to pop it next (a full sift-down)
+        // is ~20 % of an expansion's instructions.  If the smallest (f, index) among this expansion's updates is a NEW
+        // entry and beats the current root, it is handed straight to the next iteration instead — the same node the heap
+        // would have returned, since every other update of this expansion and every old entry compares greater.
+        bool to_heap = improved;
+        if (status != ST_POOL_EXHAUSTED) {
+          const unsigned long long k = improved ? fkey(new_f) : ~0ULL;
+          const uint32_t hi = (uint32_t)(k >> 32);
+          const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+          const uint32_t lo = (improved && hi == mhi) ? (uint32_t)k : 0xffffffffu;
+          const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+          const uint32_t id = (improved && hi == mhi && lo == mlo) ? (uint32_t)nb_idx : 0xffffffffu;
+          const uint32_t mid = __reduce_min_sync(0xffffffffu, id);
+          if (mid != 0xffffffffu) {
+            const bool mine = improved && id == mid;
+            const unsigned wm = __ballot_sync(0xffffffffu, mine && nb_hpos < 0);
+            const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+            if (wm && (s.heap_n == 0 || key_less(mkey, mid, s.top[0].key, s.top[0].idx))) {
+              bypass = (int)mid;
+              if (mine) to_heap = false;
+            }
+          }
+        }
+        heap_update_batch(s, to_heap, nb_hpos, fkey(new_f), (uint32_t)nb_idx, lane);
         if (status == ST_POOL_EXHAUSTED) {
           if (lane == 0) sh.stop2 = 1;
         }
