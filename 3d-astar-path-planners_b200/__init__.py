@@ -103,6 +103,7 @@ ABI = [
     ("b200_map_set_occupied", C.c_int, [_vp, _vp, _i64, _i32]),
     ("b200_map_set_occupancy", C.c_int, [_vp, _vp, _vp, _i64, _i32]),
     ("b200_map_path_distance_metrics", C.c_int, [_vp, _vp, _i64, C.POINTER(_dbl), _vp]),
+    ("b200_distance_metrics", C.c_int, [_vp, _i64, C.POINTER(_dbl)]),
     ("b200_map_edt_pipeline_used", C.c_int, [_vp]),
     ("b200_map_column_extents", C.c_int, [_vp, _vp, _vp, _i32]),
     ("b200_map_build_edt_slab", C.c_int, [_vp, _dbl, _vp, _vp, _i32]),
@@ -602,6 +603,14 @@ class Planner:
         out = C.c_int32()
         _ck(lib().b200_planner_last_launches(self.h, C.byref(out)))
         return out.value
+
+
+def distance_metrics(distances):
+    """{mean, std, min, max} with the arithmetic of the reference's calculateDistancesMetrics (host only, no GPU)."""
+    d = np.ascontiguousarray(distances, dtype=np.float64)
+    out = (C.c_double * 4)()
+    _ck(lib().b200_distance_metrics(_ptr(d), len(d), out))
+    return dict(mean=out[0], std=out[1], min=out[2], max=out[3])
 
 
 def path_of(results, path, i):

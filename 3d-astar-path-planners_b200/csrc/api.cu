@@ -859,6 +859,21 @@ int b200_map_download_dist2(b200_map_t* m, int32_t* dst) {
   REQUIRE(m && dst && m->has_edt, "no distance field (call b200_map_build_edt)");
   return download_field(m, m->d.dist2, dst, (size_t)m->N[0] * m->N[1] * m->N[2] * 4);
 }
+// calculateDistancesMetrics / getAverage / getStdDev (src/utils/metrics.cpp:62-97): pure host arithmetic, same element
+// order and operations (std::accumulate from 0.0, pow(x - mean, 2), sqrt(sum / n), minmax_element)
+int b200_distance_metrics(const double* d, int64_t n, double out[4]) {
+  REQUIRE(out && (n == 0 || d) && n >= 0, "b200_distance_metrics: bad argument");
+  out[0] = out[1] = out[2] = out[3] = 0.0;  // metrics.cpp:77
+  if (n == 0) return B200_OK;
+  double sum = 0.0, mn = d[0], mx = d[0];
+  for (int64_t i = 0; i < n; ++i) { sum += d[i]; if (d[i] < mn) mn = d[i]; if (!(d[i] < mx)) mx = d[i]; }
+  const double mean = sum / (double)n;
+  double sd = 0.0;
+  for (int64_t i = 0; i < n; ++i) sd += std::pow(d[i] - mean, 2);
+  sd = std::sqrt(sd / (double)n);
+  out[0] = mean; out[1] = sd; out[2] = mn; out[3] = mx;
+  return B200_OK;
+}
 // distance-to-obstacle statistics of a path: distances = sqrt(dist2[voxel(p_i)]) * resolution gathered on the device,
 // then mean / population standard deviation / min / max accumulated on the host in the element order and arithmetic
 // of the reference's calculateDistancesMetrics / getAverage / getStdDev (src/utils/metrics.cpp:62-97)
@@ -876,13 +891,7 @@ int b200_map_path_distance_metrics(b200_map_t* m, const double* path_xyz, int64_
   std::vector<double> d((size_t)n);
   CK(cudaMemcpyAsync(d.data(), m->stage_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  double sum = 0.0, mn = d[0], mx = d[0];
-  for (int64_t i = 0; i < n; ++i) { sum += d[i]; if (d[i] < mn) mn = d[i]; if (mx < d[i]) mx = d[i]; }
-  const double mean = sum / (double)n;
-  double sd = 0.0;
-  for (int64_t i = 0; i < n; ++i) sd += std::pow(d[i] - mean, 2);
-  sd = std::sqrt(sd / (double)n);
-  out[0] = mean; out[1] = sd; out[2] = mn; out[3] = mx;
+  b200_distance_metrics(d.data(), n, out);
   if (distances) memcpy(distances, d.data(), (size_t)n * 8);
   return B200_OK;
 }

@@ -206,6 +206,9 @@ int b200_map_device_fields(b200_map_t* map, void** dist2, void** costq);
  * zeros (:77).  distances (optional, n doubles) receives the d_i.  path_xyz is a host pointer. */
 int b200_map_path_distance_metrics(b200_map_t* map, const double* path_xyz, int64_t n, double out_mean_std_min_max[4],
                                    double* distances);
+/* The host half of it on its own (no GPU): {mean, std_dev, min, max} of n distances exactly as
+ * calculateDistancesMetrics (src/utils/metrics.cpp:62-97) computes them. */
+int b200_distance_metrics(const double* distances, int64_t n, double out_mean_std_min_max[4]);
 int b200_map_download_costq(b200_map_t* map, uint16_t* dst);
 int b200_map_download_cost(b200_map_t* map, float* dst);
 

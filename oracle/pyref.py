@@ -53,6 +53,7 @@ def lib():
         L.ref_map_set_raycast_num.argtypes = [vp, C.c_int]
         L.ref_map_get_occupancy.argtypes = [vp, vp, i64, vp]
         L.ref_map_set_occupied.argtypes = [vp, vp, i64]
+        L.ref_distance_metrics.argtypes = [vp, i64, vp]
         L.ref_map_set_occupancy.argtypes = [vp, vp, vp, i64]
         L.ref_map_publish_occupancy.argtypes = [vp, C.c_int, vp, i64]
         L.ref_map_publish_occupancy.restype = i64
@@ -68,6 +69,14 @@ def lib():
         L.ref_planner_visited.restype = i64
         _LIB = L
     return _LIB
+
+
+def distance_metrics(distances):
+    """The reference's own calculateDistancesMetrics (src/utils/metrics.cpp:62-78) -> (mean, std_dev, min, max)."""
+    d = np.ascontiguousarray(distances, dtype=np.float64)
+    out = np.zeros(4)
+    lib().ref_distance_metrics(_ptr(d), len(d), _ptr(out))
+    return tuple(out)
 
 
 def ray_cells(a, b, cap=4096):

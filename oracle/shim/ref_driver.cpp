@@ -31,6 +31,7 @@
 #define private public
 #define protected public
 #include "plan_env/grid_map.h"
+#include "utils/metrics.hpp"
 #include "Planners/AStar.hpp"
 #include "Planners/ThetaStar.hpp"
 #include "Planners/ThetaStarAGR.hpp"
@@ -208,6 +209,13 @@ void ref_map_set_occupied(void* h, const double* pos, int64_t n) {
 void ref_map_set_occupancy(void* h, const double* pos, const double* occ, int64_t n) {
   GridMap& g = *((RefMap*)h)->gm;
   for (int64_t i = 0; i < n; ++i) g.setOccupancy(Eigen::Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), occ[i]);
+}
+// calculateDistancesMetrics (src/utils/metrics.cpp:62-78): {mean, std_dev, min, max} of the distances
+void ref_distance_metrics(const double* d, int64_t n, double out[4]) {
+  std::vector<std::pair<Eigen::Vector3i, double>> v;
+  for (int64_t i = 0; i < n; ++i) v.push_back({Eigen::Vector3i(0, 0, 0), d[i]});
+  const auto r = Planners::utils::metrics::calculateDistancesMetrics(v);
+  out[0] = std::get<0>(r); out[1] = std::get<1>(r); out[2] = std::get<2>(r); out[3] = std::get<3>(r);
 }
 void ref_map_is_in_map(void* h, const double* pos, int64_t n, uint8_t* out) {
   GridMap& g = *((RefMap*)h)->gm;

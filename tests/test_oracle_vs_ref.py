@@ -104,3 +104,15 @@ def test_set_occupied_and_set_occupancy_match_reference(po):
     om.set_occupancy(pos, occ)
     a, b = rm.occupancy(), om.occupancy()
     assert np.array_equal(a, b) and (a == 1.0).sum() > 500 and (a == 0.0).sum() > 200
+
+
+def test_path_distance_metrics_arithmetic_matches_reference():
+    """GetPath.srv:20-23: the product's host arithmetic (b200_distance_metrics, pure host code in the C-ABI library) against
+    the reference's own calculateDistancesMetrics on random, constant, single-element and empty inputs."""
+    import astar_planners_b200 as b200
+    rng = np.random.default_rng(4)
+    cases = [rng.random(n) * s for n, s in ((1, 3.0), (2, 1.0), (7, 0.3), (300, 5.0), (5000, 12.0))]
+    cases += [np.full(40, 0.7), np.array([]), np.sqrt(rng.integers(0, 5000, 900).astype(np.float64)) * 0.1]
+    for d in cases:
+        m = b200.distance_metrics(d)
+        assert (m["mean"], m["std"], m["min"], m["max"]) == pr.distance_metrics(d)
