@@ -35,6 +35,15 @@ struct TreeStore {
   TreeNode* s;   // shared part: ids [0, kt)
   uint32_t kt;
   __device__ __forceinline__ TreeNode& operator[](uint32_t x) const { return x < kt ? s[x] : g[x]; }
+  // the whole node as ONE 16-byte load that the optimiser cannot split into per-field loads and sink below the uses
+  // (it does that to `TreeNode n = t[x]`: vc, then the key, then — after the compare — left OR right: three dependent
+  // round trips per level of a descent instead of two)
+  __device__ __forceinline__ TreeNode load(uint32_t x) const {
+    TreeNode n;
+    if (x < kt) { n = s[x]; return n; }
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.parent), "=r"(n.left), "=r"(n.right), "=r"(n.vc) : "l"(g + x) : "memory");
+    return n;
+  }
 };
 struct KeyStore {  // compact copy of NodeRec::f — the comparator's only input
   double* g;
@@ -256,13 +265,23 @@ struct RbSet {
     // the descent is the hot loop of the faithful kernels (one lane, ~15 levels per insert): per level ONE 16-byte load of
     // the tree node and one load of its key; the inserted node's key cannot change during the descent and stays in a register
     const double fv = fk.get(v);
-    while (x != RB_NIL) {
-      y = x;
-      const TreeNode n = t[x];
-      const uint32_t xv = n.vc & ~RB_RED;
-      const double fx = fk.get(xv);
-      comp = (fv != fx) ? fv < fx : v < xv;
-      x = comp ? n.left : n.right;
+    if (x != RB_NIL) {
+      // Per level the key of the node and BOTH child nodes are requested together (all three addresses come from the node
+      // in hand), so a level costs one memory round trip instead of two dependent ones; the child not taken is a wasted
+      // load on a lane that is waiting anyway.
+      TreeNode n = t.load(x);
+      for (;;) {
+        y = x;
+        const uint32_t xv = n.vc & ~RB_RED;
+        const double fx = fk.get(xv);
+        TreeNode nl = n, nr = n;
+        if (n.left != RB_NIL) nl = t.load(n.left);
+        if (n.right != RB_NIL) nr = t.load(n.right);
+        comp = (fv != fx) ? fv < fx : v < xv;
+        x = comp ? n.left : n.right;
+        if (x == RB_NIL) break;
+        n = comp ? nl : nr;
+      }
     }
     uint32_t j = y;
     bool do_insert = false;
@@ -298,7 +317,7 @@ struct RbSet {
     auto less_than_k = [&](uint32_t a, double fa) { return (fa != fkk) ? fa < fkk : a < k; };   // key(a) < key(k)
     auto k_less_than = [&](uint32_t a, double fa) { return (fkk != fa) ? fkk < fa : k < a; };   // key(k) < key(a)
     while (x != RB_NIL) {
-      const TreeNode n = t[x];
+      const TreeNode n = t.load(x);
       const uint32_t xv = n.vc & ~RB_RED;
       const double fx = fk.get(xv);
       if (less_than_k(xv, fx)) x = n.right;
@@ -307,12 +326,12 @@ struct RbSet {
         uint32_t xu = n.right, yu = y;
         y = x; x = n.left;
         while (x != RB_NIL) {  // lower bound
-          const TreeNode m = t[x];
+          const TreeNode m = t.load(x);
           const uint32_t mv = m.vc & ~RB_RED;
           if (!less_than_k(mv, fk.get(mv))) { y = x; x = m.left; } else x = m.right;
         }
         while (xu != RB_NIL) {  // upper bound
-          const TreeNode m = t[xu];
+          const TreeNode m = t.load(xu);
           const uint32_t mv = m.vc & ~RB_RED;
           if (k_less_than(mv, fk.get(mv))) { yu = xu; xu = m.left; } else xu = m.right;
         }
