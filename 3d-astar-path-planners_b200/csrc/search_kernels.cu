@@ -297,9 +297,12 @@ __device__ __forceinline__ AgrCand agrpp_candidate(const SearchParams& P, double
 #ifndef SEARCH_MINB4
 #define SEARCH_MINB4 6
 #endif
+#ifndef SEARCH_MINB_LAZY
+#define SEARCH_MINB_LAZY 32
+#endif
 template <int ALGO, int NW>
 __global__ void __launch_bounds__(NW * 32, NW != 1 ? SEARCH_MINB4
-                                           : (ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR) ? 32 : SEARCH_MINB1)
+                                           : (ALGO == ALGO_LAZYTHETASTAR || ALGO == ALGO_COSTLAZYTHETASTAR) ? SEARCH_MINB_LAZY : SEARCH_MINB1)
 search_kernel(const SearchParams P) {
   constexpr bool IS_AGR = ALGO == ALGO_THETASTARAGR, IS_AGRPP = ALGO == ALGO_THETASTARAGRPP;
   constexpr bool IS_THETA = ALGO == ALGO_THETASTAR || IS_AGR || IS_AGRPP;  // one fastLOS per generated neighbour
