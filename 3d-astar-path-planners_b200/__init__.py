@@ -122,6 +122,7 @@ ABI = [
     ("b200_planner_create", C.c_int, [C.c_char_p, C.POINTER(PlannerParams), _pp]),
     ("b200_planner_destroy", C.c_int, [_vp]),
     ("b200_planner_set_map", C.c_int, [_vp, _vp]),
+    ("b200_planner_set_stream", C.c_int, [_vp, _vp]),
     ("b200_planner_set_cost_factor", C.c_int, [_vp, _dbl]),
     ("b200_planner_detect_collision", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i32)]),
     ("b200_planner_find_path", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _i64]),
@@ -546,6 +547,10 @@ class Planner:
 
     def setCostFactor(self, w):
         _ck(lib().b200_planner_set_cost_factor(self.h, float(w)))
+
+    def set_stream(self, cuda_stream_ptr):
+        """Own CUDA stream for this planner (None/0 = the map's stream): batches of planners on different streams overlap."""
+        _ck(lib().b200_planner_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def detectCollision(self, pos):
         out = C.c_int32()

@@ -1179,6 +1179,7 @@ struct b200_planner {
   Tier tier[2];
   DevBuf q_in, q_res, q_path, q_order, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
   int last_launches;
+  cudaStream_t stream;         // nullptr = the map's stream; own stream = batches of several planners on one map overlap
   const NodeRec* last_nodes;   // node records of the last single query (slot 0 of the tier that ran it), else nullptr
   int64_t last_used;           // use_node_num_ of that query
 };
@@ -1239,6 +1240,7 @@ int b200_planner_create(const char* algorithm, const b200_planner_params_t* p, b
   pl->faithful = has_reference && p->semantics != B200_SEMANTICS_CANONICAL && !(p->max_los > 0);
   pl->map = nullptr;
   pl->last_launches = 0;
+  pl->stream = nullptr;
   // the neighbour offsets exactly as `for (double dx = -r; dx <= r + 1e-3; dx += r)` produces them (AStar.cpp:131)
   int nd = 0;
   double dv[8];
@@ -1261,6 +1263,11 @@ int b200_planner_destroy(b200_planner_t* pl) {
 int b200_planner_set_map(b200_planner_t* pl, b200_map_t* m) {
   REQUIRE(pl && m, "NULL argument");
   pl->map = m;
+  return B200_OK;
+}
+int b200_planner_set_stream(b200_planner_t* pl, void* st) {
+  REQUIRE(pl, "NULL planner");
+  pl->stream = (cudaStream_t)st;
   return B200_OK;
 }
 int b200_planner_set_cost_factor(b200_planner_t* pl, double w) {
@@ -1296,7 +1303,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   if (cost_algo && !(m->has_edt && m->d_safe > 0 && m->d.costq))
     return fail(B200_ERR_INVALID, "cost-aware planner needs b200_map_build_edt(map, d_safe > 0) first");
   CK(cudaSetDevice(m->prm.device));
-  cudaStream_t st = m->stream;
+  cudaStream_t st = pl->stream ? pl->stream : m->stream;
   if (!path_xyz) path_cap = 0;
 
   // workspace tiers: a small one for the common query, the full allocate_num one for the rare big query
@@ -1405,7 +1412,7 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
       CK(cudaStreamSynchronize(st));
     }
   }
-  m->launches += pl->last_launches;
+  __atomic_fetch_add(&m->launches, (long long)pl->last_launches, __ATOMIC_RELAXED);  // planners on their own streams may run on several host threads
   return B200_OK;
 }
 
@@ -1418,8 +1425,9 @@ int b200_planner_get_visited_nodes(b200_planner_t* pl, double* xyz, int64_t cap,
   const int64_t take = std::min(n, cap);
   if (take > 0) {
     CK(cudaSetDevice(pl->map->prm.device));
-    CK(cudaMemcpy2DAsync(xyz, 24, pl->last_nodes, sizeof(NodeRec), 24, (size_t)take, cudaMemcpyDeviceToHost, pl->map->stream));
-    CK(cudaStreamSynchronize(pl->map->stream));
+    cudaStream_t st = pl->stream ? pl->stream : pl->map->stream;
+    CK(cudaMemcpy2DAsync(xyz, 24, pl->last_nodes, sizeof(NodeRec), 24, (size_t)take, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
   }
   return B200_OK;
 }

@@ -291,6 +291,12 @@ int b200_planner_create(const char* algorithm, const b200_planner_params_t* para
 int b200_planner_destroy(b200_planner_t* planner);
 /* AlgorithmBase::setGridMap (AlgorithmBase.cpp:10-13) */
 int b200_planner_set_map(b200_planner_t* planner, b200_map_t* map);
+/* NEW (no reference counterpart: the reference plans one query at a time on the caller's thread).  Give this planner its
+ * own cudaStream_t (void*; NULL = back to the map's stream).  Planners bound to the same map but to different streams may be
+ * driven from different host threads, and their batches overlap on the device: the straggling queries of one batch run
+ * beside the first queries of the next instead of leaving the SMs idle.  The caller orders the stream after the map's
+ * last write (b200_map_sync, or an event on the map's stream). */
+int b200_planner_set_stream(b200_planner_t* planner, void* cuda_stream);
 /* AlgorithmBase::setCostFactor (AlgorithmBase.hpp:39) */
 int b200_planner_set_cost_factor(b200_planner_t* planner, double cost_weight);
 /* AlgorithmBase::detectCollision (AlgorithmBase.cpp:38-44): *collides = bool(getInflateOccupancy(pos)). */
