@@ -513,7 +513,7 @@ static int build_edt_impl(b200_map_t* m, double d_safe, const int32_t* below_gap
   m->edt_fused = !force_legacy && m->edt_mode == 0 && launch_edt_fused(m->d, m->d_tmp, m->d_plane_empty, m->d.dist2, d_safe > 0 ? m->d.costq : nullptr, m->d_lut,
                                                    lut_n, d_below, d_above, m->slab_total_nz, m->stream, m->profiling ? &m->ev[3] : nullptr,
                                                    m->ov_ready ? &m->ov : nullptr);
-  if (m->edt_fused) m->launches += (m->ov_ready && m->N[2] > 32) ? 4 : 2;  // two z halves on two streams when there are >= 2 z-tiles
+  if (m->edt_fused) m->launches += m->ov_ready ? 2 * std::max(1, m->ov.parts_used) : 2;  // z parts alternate between two streams
   else {
     // ... else the seven-kernel pipeline with its stacks in HBM (edt_kernels.cu)
     const int dz_bytes = edt_dz_is_wide(m->d, halo) ? 2 : 1;

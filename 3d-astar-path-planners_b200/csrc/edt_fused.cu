@@ -339,6 +339,7 @@ size_t edt_fused_plane_flags_bytes(const MapDev& m) { return (size_t)m.Nx + 16; 
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
                       const int32_t* below_gap, const int32_t* above_gap, int dz_bound, cudaStream_t stream, cudaEvent_t* ev, EdtOverlap* ov) {
   if (m.Nx < 2 || m.Ny < 2 || m.Nx > 32768 || m.Ny > 32768) return false;
+  if (ov) ov->parts_used = 1;
   const bool halo = below_gap || above_gap;
   const unsigned long long ny1 = m.Ny - 1, nx1 = m.Nx - 1, nz1 = m.Nz - 1;
   const unsigned long long g1 = nz1 * nz1 + ny1 * ny1;  // largest finite value after pass 1 (no halo)
@@ -348,26 +349,33 @@ bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t*
   const bool small = !halo && bits_of(ny1) + bits_of(nz1) <= 16 && sby8 + bits_of(nz1) <= 16 && sbx8 + bits_of(g1) <= 32 &&
                      (ny1 * ny1 + nz1 * nz1) * ny1 < (1ull << 31) && (nx1 * nx1 + g1) * nx1 < (1ull << 31) &&
                      cfg_of(smem_y<8, 32, uint16_t>(m), 256).blocks_per_sm >= 2 && cfg_of(smem_x<8, 32, uint32_t>(m), 256).blocks_per_sm >= 2;
-  // Two halves of the z range on two streams: pass 2 of a z-tile only needs pass 1 of the same z-tile, so the last,
-  // partly filled wave of one kernel overlaps the first wave of the next instead of idling the SMs (4 launches, each
-  // kernel's tail hidden but the last one's).  ov == nullptr or a single z-tile: one stream, two launches.
+  // The z range is cut into parts that alternate between two streams: pass 2 of a z-tile only needs pass 1 of the same
+  // z-tile, so the last, partly filled wave of one kernel overlaps the first wave of the next instead of idling the SMs
+  // (each kernel's tail hidden but the last one's).  B200_EDT_PARTS = number of parts (default 2; 1 = one stream, two
+  // launches).  ov == nullptr or a single z-tile: one stream.
+  static const int want_parts = getenv("B200_EDT_PARTS") ? std::max(1, atoi(getenv("B200_EDT_PARTS"))) : 2;
   auto run = [&](auto&& launch_y_fn, auto&& launch_x_fn, int W) -> bool {
     const int ztiles = (m.Nz + W - 1) / W;
-    if (!ov || ztiles < 2) {
+    const int parts = std::min(ztiles, want_parts);
+    if (ov) ov->parts_used = 1;
+    if (!ov || parts < 2) {
       bool ok = launch_y_fn(0, ztiles, stream);
       if (ev) cudaEventRecord(ev[1], stream);
       return ok && launch_x_fn(0, ztiles, stream);
     }
-    const int h = (ztiles + 1) / 2;
+    ov->parts_used = parts;
+    auto lo = [&](int i) { return (int)((long long)ztiles * i / parts); };
     cudaEventRecord(ov->fork, stream);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(ov->s[i], ov->fork, 0);
     bool ok = true;
-    for (int i = 0; i < 2; ++i) {
-      cudaStreamWaitEvent(ov->s[i], ov->fork, 0);
-      ok = ok && launch_y_fn(i ? h : 0, i ? ztiles - h : h, ov->s[i]);
-      cudaEventRecord(ov->y_done[i], ov->s[i]);
+    for (int r = 0; r < parts; r += 2) {  // rounds of two parts: Y_r (s0), Y_r+1 (s1), X_r (s0), X_r+1 (s1)
+      for (int i = r; i < std::min(parts, r + 2); ++i) {
+        ok = ok && launch_y_fn(lo(i), lo(i + 1) - lo(i), ov->s[i & 1]);
+        if (i + 2 >= parts) cudaEventRecord(ov->y_done[i & 1], ov->s[i & 1]);  // the stream's last pass-1 launch
+      }
+      for (int i = r; i < std::min(parts, r + 2); ++i) ok = ok && launch_x_fn(lo(i), lo(i + 1) - lo(i), ov->s[i & 1]);
     }
     for (int i = 0; i < 2; ++i) {
-      ok = ok && launch_x_fn(i ? h : 0, i ? ztiles - h : h, ov->s[i]);
       cudaEventRecord(ov->x_done[i], ov->s[i]);
       cudaStreamWaitEvent(stream, ov->x_done[i], 0);
     }

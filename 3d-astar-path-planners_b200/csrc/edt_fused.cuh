@@ -207,6 +207,7 @@ struct HullCursor {
   const E* ep;      // its stack slot
   int before, after;  // surviving entries of its band below / above it
   int sbase;          // first site of its band
+  int band;           // that band
   // band of virtual index x: largest b with off[b] <= x (lands on a non-empty band for x < T)
   EDT_HD void seek(int x) {
     int lo_b = 0, hi_b = NB - 1;
@@ -219,17 +220,34 @@ struct HullCursor {
     const int i = rng_lo(r) + before;
     after = rng_hi(r) - i;
     sbase = lo_b * L->BL;
+    band = lo_b;
     ep = L->st + (sbase + i) * L->W;
     v = x;
   }
+  // entering a neighbouring band: the next / previous NON-EMPTY one (it exists: the callers check v against T / 0),
+  // almost always the adjacent band — a short linear scan instead of seek()'s bisection over the prefix table
+  EDT_HD void enter(uint32_t r, bool first) {
+    const int lo = rng_lo(r), hi = rng_hi(r);
+    sbase = band * L->BL;
+    const int i = first ? lo : hi;
+    before = i - lo;
+    after = hi - i;
+    ep = L->st + (sbase + i) * L->W;
+  }
   EDT_HD Vtx<Tr> cur() const { return unpack<Tr>(*ep, L->SB, sbase); }
   EDT_HD void next() {  // v + 1 < T
-    if (after > 0) { ep += L->W; --after; ++before; ++v; }
-    else seek(v + 1);
+    if (after > 0) { ep += L->W; --after; ++before; ++v; return; }
+    uint32_t r;
+    do { ++band; r = L->r(band); } while (rng_lo(r) > rng_hi(r));
+    enter(r, true);
+    ++v;
   }
   EDT_HD void prev() {  // v > 0
-    if (before > 0) { ep -= L->W; --before; ++after; --v; }
-    else seek(v - 1);
+    if (before > 0) { ep -= L->W; --before; ++after; --v; return; }
+    uint32_t r;
+    do { --band; r = L->r(band); } while (rng_lo(r) > rng_hi(r));
+    enter(r, false);
+    --v;
   }
 };
 

@@ -37,6 +37,7 @@ void launch_cost_lut(uint16_t* lut, int lut_n, double res, double d_safe, cudaSt
 struct EdtOverlap {  // optional: two auxiliary streams + events so the z range can be processed as two overlapping halves
   cudaStream_t s[2];
   cudaEvent_t fork, y_done[2], x_done[2];
+  int parts_used;  // set by launch_edt_fused: z parts the last build was cut into (launches = 2 * parts_used)
 };
 size_t edt_fused_plane_flags_bytes(const MapDev& m);
 bool launch_edt_fused(const MapDev& m, void* tmp, uint8_t* plane_empty, int32_t* dist2, uint16_t* costq, const uint16_t* lut, int lut_n,
