@@ -147,11 +147,12 @@ __global__ void __launch_bounds__(NB* W, 5)
     return;
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
-  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, int32_t v) {
-    if (PACKED) *o = (TmpT)((uint32_t)abs(d) | (p << DYB));
-    else *o = (TmpT)v;
-    o += Nz;
-  });
+  hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](uint32_t p) { return p << DYB; },  // shifted once per vertex
+                [&](int d, uint32_t ps, int32_t v) {
+                  if (PACKED) *o = (TmpT)((uint32_t)abs(d) | ps);
+                  else *o = (TmpT)v;
+                  o += Nz;
+                });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -228,16 +229,16 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
   }
   LineHull<Tr> L{st + lane, rng + lane, W, SB, BL};
   if (!cq) {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) { *o = (int32_t)v; o += plane; });
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [](uint32_t) { return 0; }, [&](int, int, int32_t v) { *o = (int32_t)v; o += plane; });
   } else if (smem_lut) {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [](uint32_t) { return 0; }, [&](int, int, int32_t v) {
       const int32_t d = (int32_t)v;
       *o = d;
       *cq = slut[min(d, lut_n)];
       o += plane; cq += plane;
     });
   } else {
-    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) {
+    hull_fill<Tr>(L, off + lane, NB, T, u0, u1, (int)off[band * W + lane], [](uint32_t) { return 0; }, [&](int, int, int32_t v) {
       const int32_t d = (int32_t)v;
       *o = d;
       *cq = d < lut_n ? __ldg(lut + d) : (uint16_t)0;

@@ -83,22 +83,26 @@ struct HullBuilder {
   int W, SB, sbase, q;
   int sB, dS;  // top entry's site, and its distance to the entry A below it (valid while q >= 2)
   int32_t cB, dC;  // likewise for c: A is recovered as (sB - dS, cB - dC), so a pop needs no copy of A
-  EDT_HD void init(E* st_, int W_, int SB_, int sbase_) { top = st_ - W_; W = W_; SB = SB_; sbase = sbase_; q = 0; sB = dS = 0; cB = dC = 0; }
+  // With fewer than two entries there is nothing to pop: (dS, dC) = (0, -1) makes the pop test  dC (u - sB) >= (cu - cB) dS
+  // read  -(u - sB) >= 0, false for every later site, so the loop needs no separate test of the count.
+  EDT_HD void init(E* st_, int W_, int SB_, int sbase_) { top = st_ - W_; W = W_; SB = SB_; sbase = sbase_; q = 0; sB = -1; dS = 0; cB = 0; dC = -1; }
   EDT_HD void push(int u, uint32_t p) {
     const int32_t cu = u * u + Tr::g_of(p);
     // B is on or above the segment A--C  <=>  (cB - cA) (u - sB) >= (cu - cB) (sB - sA)
-    while (q >= 2 && (X)dC * (X)(u - sB) >= (X)(cu - cB) * (X)dS) {
+    while ((X)dC * (X)(u - sB) >= (X)(cu - cB) * (X)dS) {
       --q;
       top -= W;
       sB -= dS; cB -= dC;
       if (q >= 2) {
         const Vtx<Tr> a = unpack<Tr>(top[-W], SB, sbase);
         dS = sB - a.s; dC = cB - a.c;
+      } else {
+        dS = 0; dC = -1;
       }
     }
     top += W;
     *top = (E)((E)(uint32_t)(u - sbase) | ((E)p << SB));
-    dS = u - sB; dC = cu - cB;
+    if (q >= 1) { dS = u - sB; dC = cu - cB; }
     sB = u; cB = cu;
     ++q;
   }
@@ -251,11 +255,12 @@ struct HullCursor {
   }
 };
 
-// emit(d, payload, value) is called once per site in increasing order, d = u - s for a minimising site s and
+// emit(d, prep(payload), value) is called once per site in increasing order, d = u - s for a minimising site s and
 // value = d^2 + g_of(payload) (int32); the caller keeps its own output cursor.  hint = virtual index to start the search for the
 // tangent vertex of u0 from (the junction of the caller's own band: the nearest obstacle is usually close).
-template <class Tr, class Emit>
-EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T, int u0, int u1, int hint, Emit&& emit) {
+// prep(payload) is evaluated once per vertex (not per site); its result is what emit receives as second argument.
+template <class Tr, class Prep, class Emit>
+EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T, int u0, int u1, int hint, Prep&& prep, Emit&& emit) {
   using X = typename Tr::X;
   HullCursor<Tr> cu;
   cu.L = &L; cu.off = off; cu.NB = NB; cu.T = T;
@@ -317,16 +322,16 @@ EDT_HD void hull_fill(const LineHull<Tr>& L, const uint16_t* off, int NB, int T,
     acc = step * (X)u0 - (X)(n.c - k.c);
   }
   int d = u0 - k.s;
-  uint32_t kp = k.p;
-  int32_t g = Tr::g_of(kp);
+  auto kp = prep(k.p);
+  int32_t g = Tr::g_of(k.p);
   for (int u = u0; u < u1; ++u) {
     while (acc >= 0) {
       const int ks = n.s;
       const int32_t kc = n.c;
-      kp = n.p;
+      kp = prep(n.p);
       --left;
       d = u - ks;
-      g = Tr::g_of(kp);
+      g = Tr::g_of(n.p);
       if (left > 0) {
         cu.next(); n = cu.cur();
         step = (X)(2 * (n.s - ks));

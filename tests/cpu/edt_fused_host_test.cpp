@@ -98,9 +98,9 @@ static int run(int Nx, int Ny, int Nz, double density, unsigned seed, int pillar
         }
         LineHull<TrY> L{&st[lane], &rg[lane], W, SBy, BL};
         int u = u0;
-        hull_fill<TrY>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int d, uint32_t p, int32_t v) {
+        hull_fill<TrY>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](uint32_t p) { return p << DYB; }, [&](int d, uint32_t ps, int32_t v) {
           const size_t a = ((size_t)x * Ny + u) * Nz + z;
-          if (PACKED) tmp16[a] = (uint16_t)((d < 0 ? -d : d) | (p << DYB));
+          if (PACKED) tmp16[a] = (uint16_t)((d < 0 ? -d : d) | ps);
           else tmp32[a] = (int)v;
           ++u;
         });
@@ -144,7 +144,7 @@ static int run(int Nx, int Ny, int Nz, double density, unsigned seed, int pillar
         if (T == 0) { for (int u = u0; u < u1; ++u) out[((size_t)u * Ny + y) * Nz + z] = kInf; continue; }
         LineHull<TrX> L{&st[lane], &rg[lane], W, SBx, BL};
         int u = u0;
-        hull_fill<TrX>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [&](int, uint32_t, int32_t v) { out[((size_t)u * Ny + y) * Nz + z] = (int)v; ++u; });
+        hull_fill<TrX>(L, &off[lane], NB, T, u0, u1, (int)off[band * W + lane], [](uint32_t) { return 0; }, [&](int, int, int32_t v) { out[((size_t)u * Ny + y) * Nz + z] = (int)v; ++u; });
       }
     }
   }
