@@ -65,3 +65,51 @@ def test_sharded_queries_on_two_handles_equal_the_unsharded_run(b200, po, synth,
         for f in ("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length", "goal_coords"):
             assert np.array_equal(out[r][f], whole[f]), (r, f)
         assert_results_equal(out[r], ro)
+
+
+@pytest.mark.parametrize("algo,sem", [("lazythetastar", "canonical"), ("astar", "faithful")])
+def test_planners_on_their_own_streams_overlap_on_one_map(b200, po, synth, algo, sem):
+    """b200_planner_set_stream: three planner handles on ONE map, each with its own CUDA stream and host thread, each
+    running the same batch twice (paths included) — every result equals the single-stream run and the oracle."""
+    import torch
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    nq = 1500
+    s, g = synth.random_queries(11, om.get_inflate_occupancy, c["origin"], c["size"], nq, min_dist=3.0)
+    mk = lambda: b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=200000, semantics=sem)
+    base = mk()
+    base.setGridMap(gm)
+    want, want_path = base.findPaths(s, g, path_cap=nq * 400)
+    gm.sync()
+    lanes = 3
+    streams = [torch.cuda.Stream() for _ in range(lanes)]
+    pls = []
+    for st in streams:
+        pl = mk()
+        pl.setGridMap(gm)
+        pl.set_stream(st.cuda_stream)
+        pls.append(pl)
+    got, errs = [None] * lanes, []
+
+    def lane(i):
+        try:
+            for _ in range(2):
+                got[i] = pls[i].findPaths(s, g, path_cap=nq * 400)
+        except Exception as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=lane, args=(i,)) for i in range(lanes)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    mode = po.FAITHFUL if sem == "faithful" else po.CANONICAL
+    ro, _ = po.OraclePlanner(algo, om, 0.1, 5.0, 200000, mode=mode).find_paths(s, g, nthreads=8)
+    for i in range(lanes):
+        res, path = got[i]
+        for f in ("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length", "goal_coords"):
+            assert np.array_equal(res[f], want[f]), (i, f)
+        for q in range(0, nq, 97):  # path blocks land at batch-dependent offsets: compare per query
+            assert np.array_equal(b200.path_of(res, path, q), b200.path_of(want, want_path, q)), (i, q)
+        assert_results_equal(res, ro)
+    pls[0].set_stream(None)  # back to the map's stream
+    again, _ = pls[0].findPaths(s, g)
+    assert np.array_equal(again["g_final"], want["g_final"])
