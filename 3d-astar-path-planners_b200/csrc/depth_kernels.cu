@@ -251,7 +251,7 @@ struct StampCode {
 };
 constexpr int kOrderThreads = 1024;  // few, large blocks: the grid barrier is what a round costs, and its price grows with the block count
 template <int MODE>
-__device__ __forceinline__ unsigned walk_path(const DepthDev& D, unsigned slot, int lane, unsigned round) {
+__device__ __forceinline__ unsigned walk_path(const DepthDev& D, unsigned slot, int lane, unsigned round, unsigned base0 = 0) {
   const StampCode sc(D.id_bits);
   const uint32_t id = D.cast_id[slot];
   const uint32_t* path = D.paths + D.path_off[slot];
@@ -262,7 +262,7 @@ __device__ __forceinline__ unsigned walk_path(const DepthDev& D, unsigned slot, 
   uint32_t* wr = (round & 1u) ? D.Fnew : D.F;
   const bool have_prev = MODE == 1 || round > 0;
   unsigned steps = len;
-  for (unsigned base = 0; base < len; base += 32) {
+  for (unsigned base = base0; base < len; base += 32) {
     const unsigned k = base + lane;
     const uint32_t a = k < len ? path[k] : kNone;
     // :410 flag_traverse_[v] == raycast_num_ at the moment ray `id` arrives
@@ -272,8 +272,9 @@ __device__ __forceinline__ unsigned walk_path(const DepthDev& D, unsigned slot, 
     const int first = tm ? __ffs(tm) - 1 : 32;
     if (MODE == 0) {
       if (a != kNone && lane < first) {
-        const uint32_t old = atomicMin(&wr[a], sc.key(round, id));
-        if (round == 0 && old == kNone) append(D.walked, &D.ctl->n_walked, a);
+        // only round 0 needs the old value (first visit of the frame -> walked list); later rounds use the fire-and-forget form
+        if (round == 0) { if (atomicMin(&wr[a], sc.key(round, id)) == kNone) append(D.walked, &D.ctl->n_walked, a); }
+        else atomicMin(&wr[a], sc.key(round, id));
       }
     } else {
       // :406 the voxel the ray stops at is counted too (the count comes before the stop test)
@@ -308,16 +309,15 @@ __global__ void __launch_bounds__(kOrderThreads) depth_order_kernel(DepthDev D) 
   // (a round cost 12 us when the ray record, path and flags were re-read through L2 every time).
   const unsigned slot0 = tid >> 5;
   const bool one_ray_per_warp = n_cast <= (nthreads >> 5);
+  // (a longer path keeps its first 32 voxels in registers too: rays almost always stop within them, and only a ray that
+  // does not goes on through the cached path in global memory)
   uint32_t c_id = 0, c_len = 0, c_a = kNone;
-  bool c_short = false, c_flag = false;
+  bool c_flag = false;
   if (one_ray_per_warp && slot0 < n_cast) {
     c_id = D.cast_id[slot0];
     c_len = D.path_len[slot0];
-    c_short = c_len <= 32u;
-    if (c_short) {
-      c_a = (unsigned)lane < c_len ? D.paths[D.path_off[slot0] + lane] : kNone;
-      c_flag = c_a != kNone && D.flagT[c_a] == D.round;
-    }
+    c_a = (unsigned)lane < c_len ? D.paths[D.path_off[slot0] + lane] : kNone;
+    c_flag = c_a != kNone && D.flagT[c_a] == D.round;
   }
   unsigned my_stop = 0xffffffffu;
   unsigned round = 0;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kOrderThreads) depth_order_kernel(DepthDev D) 
     if (one_ray_per_warp) {
       if (slot0 < n_cast) {
         unsigned steps;
-        if (c_short) {
+        {
           const uint32_t* rd = ((round - 1u) & 1u) ? D.Fnew : D.F;
           uint32_t* wr = (round & 1u) ? D.Fnew : D.F;
           bool taken = c_flag;
@@ -334,12 +334,10 @@ __global__ void __launch_bounds__(kOrderThreads) depth_order_kernel(DepthDev D) 
           const unsigned tm = __ballot_sync(0xffffffffu, taken);
           const int first = tm ? __ffs(tm) - 1 : 32;
           if (c_a != kNone && lane < first) {
-            const uint32_t old = atomicMin(&wr[c_a], sc.key(round, c_id));
-            if (round == 0 && old == kNone) append(D.walked, &D.ctl->n_walked, c_a);
+            if (round == 0) { if (atomicMin(&wr[c_a], sc.key(round, c_id)) == kNone) append(D.walked, &D.ctl->n_walked, c_a); }
+            else atomicMin(&wr[c_a], sc.key(round, c_id));  // result unused: fire-and-forget reduction
           }
-          steps = tm ? (unsigned)first + 1u : c_len;
-        } else {
-          steps = walk_path<0>(D, slot0, lane, round);
+          steps = tm ? (unsigned)first + 1u : (c_len <= 32u ? c_len : walk_path<0>(D, slot0, lane, round, 32u));
         }
         changed = steps != my_stop;
         my_stop = steps;
@@ -557,6 +555,35 @@ void launch_depth_path_count(const DepthDev& D, const MapDev& m, cudaStream_t st
 }
 void launch_depth_path_fill(const DepthDev& D, const MapDev& m, unsigned n_cast, cudaStream_t st) {
   if (n_cast) depth_path_fill_kernel<<<blocks_for(n_cast, 128), 128, 0, st>>>(D, m);
+}
+// the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
+// the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
+template <int R>
+static cudaError_t try_order_cluster(const DepthDev& D, int csize, cudaStream_t st) {
+  auto k = depth_order_cluster_kernel<R>;
+  static bool allowed[2] = {false, false};
+  if (csize > 8 && !allowed[0]) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return cudaGetLastError();
+    allowed[0] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(kOrderThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  static int placeable[17] = {};  // per cluster size: 0 = not asked yet, 1 = yes, -1 = no (the query is a driver call: once)
+  if (placeable[csize] == 0) {
+    int nclusters = 0;
+    placeable[csize] = (cudaOccupancyMaxActiveClusters(&nclusters, k, &cfg) == cudaSuccess && nclusters >= 1) ? 1 : -1;
+    cudaGetLastError();
+  }
+  if (placeable[csize] < 0) return cudaErrorLaunchOutOfResources;
+  return cudaLaunchKernelEx(&cfg, k, D);
 }
 // the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
 int launch_depth_order(const DepthDev& D, unsigned n_cast, int sm_count, cudaStream_t st) {

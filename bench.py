@@ -621,6 +621,18 @@ def main():
         return tot / args.steps, float(np.median(ts))
 
     e2e_ms, e2e_p50 = time_e2e(h_cloud_np)
+    # the link this e2e number was measured over: plain pinned 16 MB host-to-device copies of the same buffer (CUDA events).
+    # The frame cannot start its EDT before the last point has arrived, so e2e ~ 16 MB / link + EDT (+ ~0.05 ms); the boxes of
+    # this pool gave 23-54 GB/s for this copy on different days (profiles/diag_h2d.py)
+    ha, hb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d_ms = []
+    for _ in range(10):
+        ha.record()
+        d_cloud.copy_(h_cloud, non_blocking=True)
+        hb.record()
+        torch.cuda.synchronize()
+        h2d_ms.append(ha.elapsed_time(hb))
+    h2d_gbs = blob.nbytes / (float(np.median(h2d_ms)) * 1e-3) / 1e9
     e2e_pageable_ms, e2e_pageable_p50 = time_e2e(pageable_np)
     clocks = sampler.stop()
 
@@ -683,6 +695,8 @@ def main():
              "edt_hbm_gbs_with_costq": edt_bytes_with_cost / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0,
              "frame_hbm_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
              "wall_ms_timed_region": wall_ms,
+             "h2d_link": {"pinned_16MB_copy_gbs": h2d_gbs, "copy_ms": float(np.median(h2d_ms)),
+                          "note": "plain cudaMemcpyAsync of the e2e cloud buffer, measured right after the e2e region"},
              "e2e_pageable_host_cloud": {"ms_per_step": e2e_pageable_ms, "p50_ms_per_step": e2e_pageable_p50,
                                          "note": "same call with a pageable (non-pinned) host cloud, as a ROS PointCloud2::data is"}}
     if world > 1:
