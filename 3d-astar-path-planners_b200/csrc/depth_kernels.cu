@@ -557,35 +557,6 @@ void launch_depth_path_fill(const DepthDev& D, const MapDev& m, unsigned n_cast,
   if (n_cast) depth_path_fill_kernel<<<blocks_for(n_cast, 128), 128, 0, st>>>(D, m);
 }
 // the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
-// the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
-template <int R>
-static cudaError_t try_order_cluster(const DepthDev& D, int csize, cudaStream_t st) {
-  auto k = depth_order_cluster_kernel<R>;
-  static bool allowed[2] = {false, false};
-  if (csize > 8 && !allowed[0]) {
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return cudaGetLastError();
-    allowed[0] = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)csize);
-  cfg.blockDim = dim3(kOrderThreads);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  static int placeable[17] = {};  // per cluster size: 0 = not asked yet, 1 = yes, -1 = no (the query is a driver call: once)
-  if (placeable[csize] == 0) {
-    int nclusters = 0;
-    placeable[csize] = (cudaOccupancyMaxActiveClusters(&nclusters, k, &cfg) == cudaSuccess && nclusters >= 1) ? 1 : -1;
-    cudaGetLastError();
-  }
-  if (placeable[csize] < 0) return cudaErrorLaunchOutOfResources;
-  return cudaLaunchKernelEx(&cfg, k, D);
-}
-// the ray-order fixed point; D.ctl->changed[0] must be zero.  Returns a CUDA error code.
 int launch_depth_order(const DepthDev& D, unsigned n_cast, int sm_count, cudaStream_t st) {
   if (n_cast == 0) return 0;
   int per_sm = 0;
