@@ -75,6 +75,10 @@ __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(siz
 // ---------------------------------------------------------------------------------------------------
 // pass 1: bits -> z distance (on the fly, per site) -> hull along y -> packed (dy, dz) or int32 squared distance
 // ---------------------------------------------------------------------------------------------------
+// BULK: how a block learns its columns' bits — true: one bulk async copy of the plane into shared memory (mbarrier), every
+// thread then prepares columns of the whole line from it, block barrier; false (planes that do not fit the stack region,
+// or B200_EDT_Y_SETUP=2): the lanes of a band prepare only the band's OWN columns straight from global memory and a
+// warp-level sync follows.  Measured equal at C2 (169 vs 168 us): resident blocks hide the set-up either way.
 template <int NB, int W, class Tr, class TmpT, bool BULK>
 __global__ void __launch_bounds__(NB* W, 5)
     edt_fused_y_kernel(MapDev m, const int32_t* __restrict__ below_gap, const int32_t* __restrict__ above_gap, TmpT* __restrict__ tmp,
@@ -98,6 +102,9 @@ __global__ void __launch_bounds__(NB* W, 5)
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
   const int wi = z0 >> 5;
   const uint32_t* plane_bits = m.occ + (size_t)x * Ny * wz;
+  const int z = z0 + lane, bi = z & 31;
+  const bool active = z < Nz;
+  const int u0 = band * BL, u1 = min(Ny, u0 + BL);
   if (BULK) {  // one bulk async copy of the plane's words (TMA engine), completion on an mbarrier
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
@@ -108,23 +115,26 @@ __global__ void __launch_bounds__(NB* W, 5)
     }
     mbar_wait(&bar, 0);
   }
-  for (int y = tid; y < Ny; y += NB * W) {
+  auto column = [&](int y) {
     const size_t col = (size_t)x * Ny + y;
     const int bg = below_gap ? __ldg(below_gap + col) : 0, ag = above_gap ? __ldg(above_gap + col) : 0;
     int lo, hi;
     if (BULK) {
       column_outside(bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
       own[y] = bits[(size_t)y * wz + wi];
-    } else {  // planes too large to stage whole: the other words of the column come straight from L2
+    } else {  // the other words of the column come straight from L2 / L1
       column_outside(plane_bits + (size_t)y * wz, wz, Nz, wi, bg, ag, &lo, &hi);
       own[y] = __ldg(plane_bits + (size_t)y * wz + wi);
     }
     outside[y] = make_int2(lo, hi);
+  };
+  if (!BULK) {
+    for (int y = u0 + lane; y < u1; y += W) column(y);
+    __syncwarp();  // a band's columns are written and read by the band's own lanes only (a warp holds whole bands)
+  } else {
+    for (int y = tid; y < Ny; y += NB * W) column(y);
+    __syncthreads();
   }
-  __syncthreads();
-  const int z = z0 + lane, bi = z & 31;
-  const bool active = z < Nz;
-  const int u0 = band * BL, u1 = min(Ny, u0 + BL);
   {
     HullBuilder<Tr> hb;
     hb.init(st + (size_t)band * BL * W + lane, W, SB, u0);
@@ -174,21 +184,28 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
   uint16_t* off = reinterpret_cast<uint16_t*>(rng + NB * W);
   int* total = reinterpret_cast<int*>(off + NB * W);
   uint16_t* slut = reinterpret_cast<uint16_t*>(total + W);  // [min(lut_n, kSmemLut) + 1], last entry 0
-  uint8_t* pe = reinterpret_cast<uint8_t*>(slut + kSmemLut + 2);
 
   const int y = blockIdx.x / nzt, z0 = (zt0 + blockIdx.x % nzt) * W;
   const int tid = threadIdx.x, band = tid / W, lane = tid % W;
   const bool smem_lut = costq != nullptr && lut_n <= kSmemLut;
-  int any_empty = 0;
-  if (PACKED)
-    for (int i = tid; i < Nx; i += NB * W) { const uint8_t v = __ldg(plane_empty + i); pe[i] = v; any_empty |= v; }
-  if (smem_lut)
-    for (int i = tid; i <= lut_n; i += NB * W) slut[i] = i < lut_n ? __ldg(lut + i) : (uint16_t)0;
-  any_empty = __syncthreads_or(any_empty);
   const int z = z0 + lane;
   const bool active = z < Nz;
   const int u0 = band * BL, u1 = min(Nx, u0 + BL);
   const size_t plane = (size_t)Ny * Nz, base = (size_t)y * Nz + z;
+  // No block-wide barrier in front of the scan (loading the cost table and the empty-plane flags into shared memory behind
+  // a __syncthreads put two serial memory latencies at the start of every block): the cost table is only needed by the
+  // walk, so it is fetched after the scan and published by the merge's first barrier; the flags of a band are read by the
+  // band's own lanes straight from global memory and combined with one vote.
+  int any_empty = 0;
+  if (PACKED) {
+    if (active && u0 + PF <= u1) {  // the first rows of the scan start travelling before the flags are known
+#pragma unroll
+      for (int j = 0; j < PF; ++j) asm volatile("prefetch.global.L1 [%0];" ::"l"(tmp + base + (size_t)(u0 + j) * plane));
+    }
+    for (int u = u0 + lane; u < u1; u += W) any_empty |= __ldg(plane_empty + u);
+    const unsigned grp = W >= 32 ? 0xffffffffu : (((1u << (W & 31)) - 1u) << (((tid & 31) / W) * W));  // the lanes of this band
+    any_empty = (__ballot_sync(0xffffffffu, any_empty != 0) & grp) != 0u;
+  }
   {
     HullBuilder<Tr> hb;
     hb.init(st + (size_t)band * BL * W + lane, W, SB, u0);
@@ -212,10 +229,12 @@ __global__ void __launch_bounds__(NB* W, 3) edt_fused_x_kernel(MapDev m, const T
         }
       }
       for (; ub < u1; ++ub, in += plane)
-        if (!(PACKED && pe[ub])) site(ub, __ldg(in));
+        if (!(PACKED && __ldg(plane_empty + ub))) site(ub, __ldg(in));
     }
     rng[band * W + lane] = hb.range();
   }
+  if (smem_lut)
+    for (int i = tid; i <= lut_n; i += NB * W) slut[i] = i < lut_n ? __ldg(lut + i) : (uint16_t)0;
   const int T = merge_bands<NB, W, Tr>(st, rng, off, total, SB, BL, band, lane);
   if (!active) return;
   int32_t* o = dist2 + base + (size_t)u0 * plane;
@@ -274,14 +293,15 @@ size_t smem_y(const MapDev& m) {
 template <int NB, int W, class E>
 size_t smem_x(const MapDev& m) {
   const int BL = (m.Nx + NB - 1) / NB;
-  return align16((size_t)NB * BL * W * sizeof(E)) + (size_t)NB * W * 6 + (size_t)W * 4 + (size_t)(kSmemLut + 2) * 2 + (size_t)m.Nx + 32;
+  return align16((size_t)NB * BL * W * sizeof(E)) + (size_t)NB * W * 6 + (size_t)W * 4 + (size_t)(kSmemLut + 2) * 2 + 32;
 }
 
 template <int NB, int W, class Tr, class TmpT>
 bool launch_y(const MapDev& m, void* tmp, uint8_t* plane_empty, const int32_t* below_gap, const int32_t* above_gap, int zt0, int nzt,
               cudaStream_t stream) {
   const size_t sy = smem_y<NB, W, typename Tr::E>(m);
-  const bool bulk = bulk_ok<NB, W, typename Tr::E>(m);
+  static const bool no_bulk = getenv("B200_EDT_Y_SETUP") && atoi(getenv("B200_EDT_Y_SETUP")) == 2;  // tuning knob
+  const bool bulk = !no_bulk && bulk_ok<NB, W, typename Tr::E>(m);
   auto k = bulk ? edt_fused_y_kernel<NB, W, Tr, TmpT, true> : edt_fused_y_kernel<NB, W, Tr, TmpT, false>;
   static size_t configured[64][2] = {};  // per instantiation and device: the opt-in is a driver call, pay it once per size
   int dev = 0;
