@@ -1179,6 +1179,7 @@ struct b200_planner {
   Tier tier[2];
   DevBuf q_in, q_res, q_path, q_order, ctl;  // ctl: [0] q_counter u64, [1] path_cursor u64, [2] overflow_count int, then overflow list
   int last_launches;
+  int last_promoted;           // queries of the last call that moved into a promotion slot
   cudaStream_t stream;         // nullptr = the map's stream; own stream = batches of several planners on one map overlap
   const NodeRec* last_nodes;   // node records of the last single query (slot 0 of the tier that ran it), else nullptr
   int64_t last_used;           // use_node_num_ of that query
@@ -1348,7 +1349,21 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   unsigned long long* q_counter = (unsigned long long*)pl->ctl.p;
   unsigned long long* path_cursor = q_counter + 1;
   int* overflow_count = (int*)(q_counter + 2);
+  int* promo_count = overflow_count + 2;
   int* overflow_list = (int*)((char*)pl->ctl.p + 64);
+  // Promotion slots: the canonical 32-thread kernels move a query that outgrows tier 0 into a full-size workspace and go
+  // on (search_kernels.cu promote_slot) instead of reporting it for a re-run from scratch.  They are tier 1 allocated up
+  // front (<= 32 slots, <= a quarter of the free memory); without them everything works as before, through the re-run.
+  const bool can_promote = !pl->faithful && tpb == 32 && pl->tier[0].cap < pl->prm.allocate_num;
+  if (can_promote && !(pl->tier[1].base && pl->tier[1].cap == pl->prm.allocate_num)) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t slot_b = search_slot_bytes(pl->prm.allocate_num, factor, nullptr);
+    const char* cap_env = getenv("B200_PROMO_SLOTS");  // testing / tuning knob: upper bound on the promotion slots (0 = none)
+    const size_t max_promo = cap_env ? (size_t)std::max(0, atoi(cap_env)) : 32;
+    const int want = (int)std::min<size_t>({max_promo, (size_t)pl->tier[0].slots, (free_b / 4) / std::max<size_t>(slot_b, 1)});
+    if (want >= 1 && tier_alloc(pl->tier[1], pl->prm.allocate_num, want, factor)) cudaGetLastError();  // no memory: no promotion
+  }
 
   SearchParams P;
   memset(&P, 0, sizeof P);
@@ -1374,14 +1389,27 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   P.q_counter = q_counter; P.overflow_list = overflow_list; P.overflow_count = overflow_count;
   const Tier& t0 = pl->tier[0];
   P.nodes = t0.nodes; P.hash = t0.hash; P.heap = t0.heap; P.cap = t0.cap; P.hcap = t0.hcap; P.open_entries = t0.open_entries; P.fkey = t0.fkey;
+  P.promo_count = promo_count;
+  if (can_promote && pl->tier[1].base && pl->tier[1].cap == pl->prm.allocate_num) {
+    const Tier& t1 = pl->tier[1];
+    const char* cap_env = getenv("B200_PROMO_SLOTS");
+    P.promo_nodes = t1.nodes; P.promo_hash = t1.hash; P.promo_heap = t1.heap; P.promo_cap = t1.cap;
+    P.promo_slots = cap_env ? std::min(t1.slots, std::max(0, atoi(cap_env))) : t1.slots;
+    P.promo_open_entries = t1.open_entries; P.promo_hcap = t1.hcap;
+  }
   launch_search(P, std::min<int64_t>(t0.slots, nq), st);
   pl->last_launches++;
   CK(cudaGetLastError());
+  const int promo_slots_used = P.promo_slots;
+  P.promo_slots = 0;  // a re-run below uses tier 1 as its own workspace
 
+  pl->last_promoted = 0;
   if (t0.cap < pl->prm.allocate_num) {
-    int n_over = 0;
-    CK(cudaMemcpyAsync(&n_over, overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    int counts[3] = {0, 0, 0};  // overflow_count, (pad), promo_count
+    CK(cudaMemcpyAsync(counts, overflow_count, sizeof counts, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const int n_over = counts[0];
+    pl->last_promoted = std::min(counts[2], promo_slots_used);
     if (n_over > 0) {
       size_t free_b = 0, total_b = 0;
       CK(cudaMemGetInfo(&free_b, &total_b));
@@ -1446,7 +1474,8 @@ int b200_planner_find_path(b200_planner_t* pl, const double start[3], const doub
   }
   if (result->path_offset > 0) result->path_offset = 0;
   // slot 0 of the tier that produced the result still holds the node records (positions first, creation order)
-  const Tier& t = (pl->last_launches >= 2 && pl->tier[1].base) ? pl->tier[1] : pl->tier[0];
+  // (a promoted single query sits in promotion slot 0 = the start of tier 1)
+  const Tier& t = ((pl->last_launches >= 2 || pl->last_promoted > 0) && pl->tier[1].base) ? pl->tier[1] : pl->tier[0];
   pl->last_nodes = t.nodes;
   pl->last_used = result->explored_nodes;
   return B200_OK;

@@ -105,6 +105,13 @@ struct SearchParams {
   int cap;        // physical nodes per slot
   uint32_t open_entries;  // 16-byte open-list entries per slot (heap / red-black tree nodes)
   uint32_t hcap;  // hash entries per slot (power of two >= 2*cap)
+  // promotion slots (canonical 32-thread kernels): full-size workspaces a query moves into when it outgrows `cap`
+  NodeRec* promo_nodes;
+  uint32_t* promo_hash;
+  HeapEnt* promo_heap;
+  int promo_cap, promo_slots;
+  uint32_t promo_open_entries, promo_hcap;
+  int* promo_count;  // slots handed out by this launch
 };
 
 // Open-list region of a slot, in 16-byte entries.  The canonical heap needs cap + 32.  The faithful red-black

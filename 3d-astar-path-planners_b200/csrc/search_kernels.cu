@@ -202,8 +202,40 @@ __device__ __forceinline__ uint32_t hash_insert(const Slot& s, double x, double 
   }
 }
 
+// In-kernel promotion (32-thread kernels): a query that outgrows its tier-0 workspace moves — nodes, open list, a rebuilt
+// hash table — into one of the big promotion slots and simply goes on; registers and the shared-memory heap top carry the
+// rest of its state, so nothing is recomputed.  (The alternative, still used by the 128-thread and faithful kernels and when
+// the promotion slots run out, re-runs the query from scratch in a second launch: the BASELINE C3 batch of 10 000
+// costlazythetastar queries spent 300 of its 600 ms re-running its one 36 000-node query.)  Returns the promotion slot, -1
+// when none is left.  Called after the search loop has been left with ST_TIER_OVERFLOW (the interrupted expansion had no side
+// effects yet and is redone), so the loop itself only carries one extra warp-uniform flag.
+__device__ __forceinline__ int promote_slot(const NodeRec* nodes, uint32_t* hash, const HeapEnt* heap, int use, int heap_n, NodeRec* promo_nodes,
+                                         uint32_t* promo_hash, HeapEnt* promo_heap, int promo_cap, uint32_t promo_hcap,
+                                         uint32_t promo_open_entries, int promo_slots, int* promo_count, int lane) {
+  int t = 0;
+  if (lane == 0) t = atomicAdd(promo_count, 1);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t >= promo_slots) return -1;
+  NodeRec* n1 = promo_nodes + (size_t)t * promo_cap;
+  uint32_t* h1 = promo_hash + (size_t)t * promo_hcap;
+  HeapEnt* hp1 = promo_heap + (size_t)t * promo_open_entries;
+  for (int i = lane; i < use; i += 32) hash[nodes[i].slot] = 0u;  // leave the tier-0 table clean for the block's next query
+  const uint4* src = reinterpret_cast<const uint4*>(nodes);
+  uint4* dst = reinterpret_cast<uint4*>(n1);
+  for (int i = lane; i < use * 4; i += 32) dst[i] = src[i];
+  const int nh = heap_n + 32;  // physical entries: logical k >= kHeapTop lives at k + 31
+  for (int i = lane; i < nh; i += 32) hp1[i] = heap[i];
+  __syncwarp();
+  Slot s1;
+  s1.nodes = n1; s1.hash = h1; s1.heap = hp1; s1.top = nullptr; s1.hmask = promo_hcap - 1u; s1.heap_n = heap_n; s1.use = use;
+  for (int i = lane; i < use; i += 32) n1[i].slot = hash_insert(s1, n1[i].px, n1[i].py, n1[i].pz, i);
+  __syncwarp();
+  return t;
+}
+
 struct Shared {
   long long q;
+  int cap;         // physical node capacity of the workspace the current query lives in (tier 0, or a promotion slot)
   int state;       // 0 continue, 1 query finished (written by the control warp before the first barrier of an expansion)
   int stop2;       // 1: query finished in UpdateVertex.  A separate flag: the other warps may still be reading `state`
                    // when the control warp gets here (no barrier in between when the LoS phase is skipped)
@@ -318,6 +350,7 @@ search_kernel(const SearchParams P) {
   s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
   s.top = heap_top;
   s.hmask = P.hcap - 1;
+  if (threadIdx.x == 0) sh.cap = P.cap;
 
   // neighbour offset of this lane: L = 9a + 3b + c <-> (dx,dy,dz) = (dv[a],dv[b],dv[c])  (AStar.cpp:131-133)
   const int la = lane / 9, lb = (lane / 3) % 3, lc = lane % 3;
@@ -368,11 +401,14 @@ search_kernel(const SearchParams P) {
     int nb_idx = -1, nb_state = NODE_NEW, nb_hpos = -1;
     double nb_g = 0;
     double nx = 0, ny = 0, nz = 0;
+    bool redo = false;  // re-entering after a promotion: the interrupted expansion of `cur` is repeated from its neighbour phase
+    for (;;) {  // left once, or once more per promotion
     for (;;) {
       bool valid = false;
       if (warp == 0) {
         bool done = false;
-        if (s.heap_n == 0 && bypass < 0) {  // AStar.cpp:175-178
+        if (redo) {
+        } else if (s.heap_n == 0 && bypass < 0) {  // AStar.cpp:175-178
           status = ST_OPEN_EMPTY; last = cur; done = true;
         } else {
           open_peak = max(open_peak, s.heap_n + (bypass >= 0 ? 1 : 0));
@@ -453,8 +489,11 @@ search_kernel(const SearchParams P) {
           }
         }
         if (!done) {
-          if (lane == 0) s.nodes[cur].state = (s.nodes[cur].state & ~0xff) | NODE_CLOSED;  // AStar.cpp:122
-          ++iter_num;
+          if (!redo) {
+            if (lane == 0) s.nodes[cur].state = (s.nodes[cur].state & ~0xff) | NODE_CLOSED;  // AStar.cpp:122
+            ++iter_num;
+          }
+          redo = false;
           __syncwarp();
           // ---- neighbour resolution (AStar.cpp:131-169), one lane per offset ----
           nb_idx = -1; nb_state = NODE_NEW; nb_hpos = -1;
@@ -477,9 +516,10 @@ search_kernel(const SearchParams P) {
           bool oom = false, overflow = false;
           int fail_lane = 32;
           if (ncreate > 0) {
-            if (P.cap < P.allocate_num && s.use + ncreate > P.cap) {
-              overflow = true;  // physical tier too small: the host reruns this query in the big tier
-            } else if (s.use + ncreate >= P.allocate_num) {  // :165-168: the creation that makes use == allocate_num bails out
+            if (sh.cap < P.allocate_num && s.use + ncreate > sh.cap) {
+              overflow = true;  // physical tier too small: the query moves into a promotion slot (below, after the loop) or is re-run
+            }
+            if (!overflow && s.use + ncreate >= P.allocate_num) {  // :165-168: the creation that makes use == allocate_num bails out
               const int fail_rank = P.allocate_num - s.use - 1;
               const unsigned fm = __ballot_sync(0xffffffffu, need && rank == fail_rank);
               fail_lane = __ffs(fm) - 1;
@@ -489,7 +529,7 @@ search_kernel(const SearchParams P) {
           if (overflow) {
             status = ST_TIER_OVERFLOW; last = cur; done = true;
           } else {
-            if (need && lane <= fail_lane && s.use + rank < P.cap) {
+            if (need && lane <= fail_lane && s.use + rank < sh.cap) {
               const int ni = s.use + rank;
               NodeRec n;
               n.px = nx; n.py = ny; n.pz = nz;
@@ -502,7 +542,7 @@ search_kernel(const SearchParams P) {
             }
             if (oom) {
               if (lane >= fail_lane) valid = false;  // the failing neighbour and everything after it never reach UpdateVertex
-              s.use = min(P.allocate_num, P.cap);
+              s.use = min(P.allocate_num, sh.cap);
               status = ST_POOL_EXHAUSTED; last = cur;
             } else {
               s.use += ncreate;
@@ -632,6 +672,20 @@ search_kernel(const SearchParams P) {
       if (NW > 1) __syncthreads(); else __syncwarp();
       if (sh.stop2 == 1) break;
     }
+      // a 32-thread query that outgrew tier 0: move it into a promotion slot and re-enter the loop (else: reported for a re-run)
+      if (!(NW == 1 && status == ST_TIER_OVERFLOW && P.promo_slots > 0 && sh.cap < P.promo_cap)) break;
+      const int t = promote_slot(s.nodes, s.hash, s.heap, s.use, s.heap_n, P.promo_nodes, P.promo_hash, P.promo_heap, P.promo_cap, P.promo_hcap,
+                                 P.promo_open_entries, P.promo_slots, P.promo_count, lane);
+      if (t < 0) break;
+      s.nodes = P.promo_nodes + (size_t)t * P.promo_cap;
+      s.hash = P.promo_hash + (size_t)t * P.promo_hcap;
+      s.heap = P.promo_heap + (size_t)t * P.promo_open_entries;
+      s.hmask = P.promo_hcap - 1u;
+      if (lane == 0) { sh.cap = P.promo_cap; sh.state = 0; }
+      status = ST_OPEN_EMPTY;
+      redo = true;
+      __syncwarp();
+    }
 
     // ---------------- result (AlgorithmBase.cpp:123-175, :202-212; geometry_utils.cpp:10-20) -------------
     if (warp == 0) {
@@ -646,7 +700,7 @@ search_kernel(const SearchParams P) {
       long long off = -1;
       float plen = 0.f;
       int* chain = reinterpret_cast<int*>(s.heap);  // the open list is dead now: reuse it as scratch
-      float* seglen = reinterpret_cast<float*>(s.heap) + (size_t)P.cap + 8;
+      float* seglen = reinterpret_cast<float*>(s.heap) + (size_t)sh.cap + 8;
       if (status == ST_SOLVED) {
         if (lane == 0) {
           int c = term;
@@ -700,9 +754,17 @@ search_kernel(const SearchParams P) {
     }
     __syncthreads();
     // reset(): clear only the hash slots this query touched (AlgorithmBase.cpp:17-32 analogue)
-    const int used = min(sh.used, P.cap);
+    const int used = min(sh.used, sh.cap);
     for (int i = tid; i < used; i += NW * 32) s.hash[s.nodes[i].slot] = 0u;
     __syncthreads();
+    if (NW == 1 && sh.cap != P.cap) {  // the query ended in a promotion slot (left clean above): back to the block's own workspace
+      s.nodes = P.nodes + (size_t)blockIdx.x * P.cap;
+      s.hash = P.hash + (size_t)blockIdx.x * P.hcap;
+      s.heap = P.heap + (size_t)blockIdx.x * P.open_entries;
+      s.hmask = P.hcap - 1;
+      __syncthreads();  // every thread has read sh.cap
+      if (tid == 0) sh.cap = P.cap;
+    }
   }
 }
 

@@ -140,14 +140,54 @@ def test_pool_exhaustion_and_unreachable_goal(b200, po, synth, world):
         assert_results_equal(rg, ro)
 
 
-def test_big_queries_take_the_second_workspace_tier(b200, po, synth):
-    # lambda = 1 (plain A*) explores far more than 16384 nodes -> tier overflow -> rerun in the big tier
+def test_big_queries_take_the_second_workspace_tier(b200, po, synth, monkeypatch):
+    # lambda = 1 (plain A*) explores far more than 32768 nodes -> tier overflow -> rerun in the big tier (the path of the
+    # 128-thread and faithful kernels, and of the 32-thread ones once the promotion slots are used up: forced here)
+    monkeypatch.setenv("B200_PROMO_SLOTS", "0")
     gm, om, c = make_pair(b200, po, synth, "C3")
     s, g = synth.random_queries(8, om.get_inflate_occupancy, c["origin"], c["size"], 6, min_dist=12.0)
     pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, "astar", s, g, lam=1.0, allocate_num=200000)
     assert (ro["explored_nodes"] > 16384).any()
     assert_results_equal(rg, ro)
     _assert_paths_equal(b200, rg, pg, ro, pth)
+    assert pl.last_launches() == 2
+
+
+@pytest.mark.parametrize("algo", ["astar", "lazythetastar", "costastar"])
+def test_big_queries_move_into_a_promotion_slot_and_go_on(b200, po, synth, algo, monkeypatch):
+    """Canonical 32-thread kernels: a query that outgrows the 32 768-node tier is moved (nodes, open list, rebuilt hash) into
+    a full-size workspace inside the kernel and continues — one launch, results identical to the oracle; with fewer
+    promotion slots than big queries the rest takes the re-run path; a promoted single query still serves getVisitedNodes."""
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    if algo == "costastar":
+        gm.build_edt(1.0); om.build_edt(1.0)
+    s, g = synth.random_queries(8, om.get_inflate_occupancy, c["origin"], c["size"], 6, min_dist=12.0)
+    kw = dict(lam=1.0, allocate_num=200000, semantics="canonical")
+    if algo == "costastar":
+        kw["cost_weight"] = 1.0
+    pl, rg, pg, ro, pth = _run_both(b200, po, gm, om, algo, s, g, **kw)
+    big = int((ro["explored_nodes"] > 32768).sum())
+    assert big >= 2
+    assert_results_equal(rg, ro)
+    _assert_paths_equal(b200, rg, pg, ro, pth)
+    assert pl.last_launches() == 1
+    # a second batch on the same handle: the promotion slots were left clean
+    rg2, pg2 = pl.findPaths(s, g, path_cap=pg.shape[0])
+    assert_results_equal(rg2, ro)
+    # single promoted query: visited nodes come from the promotion slot
+    i = int(np.argmax(ro["explored_nodes"]))
+    r = pl.findPath(s[i], g[i])
+    assert r["explored_nodes"] == int(ro["explored_nodes"][i]) and pl.last_launches() == 1
+    assert len(pl.getVisitedNodes()) == r["explored_nodes"] - 1
+    # one promotion slot for `big` >= 2 big queries: the others are re-run in a second launch, same results
+    monkeypatch.setenv("B200_PROMO_SLOTS", "1")
+    rg3, pg3 = pl.findPaths(s, g, path_cap=pg.shape[0])
+    assert_results_equal(rg3, ro)
+    _assert_paths_equal(b200, rg3, pg3, ro, pth)
+    assert pl.last_launches() == 2
+    monkeypatch.setenv("B200_PROMO_SLOTS", "0")
+    rg4, _ = pl.findPaths(s, g)
+    assert_results_equal(rg4, ro)
     assert pl.last_launches() == 2
 
 
