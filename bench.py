@@ -430,47 +430,24 @@ def run_c3(b200, po, synth, torch, dev, device, host_threads, errors):
 
 
 def run_pipelined(b200, torch, gm, algo, sem, ds, dg, nq, dres_single, rounds=3, lanes=2):
-    """Steady-state serving form of the batched planners: `lanes` planner handles on the same map, each with its own
-    CUDA stream and host thread, each running `rounds` batches back to back.  A batch's last straggling queries then run
-    beside the next batch's first queries instead of leaving the SMs idle.  Device-timed: one start event, one end event per
-    lane, the longest span counts.  Returns (ms, queries, identical) — identical: every lane's last result block equals the
-    single-batch result bit for bit (status / lengths / costs; the per-query clock field excluded)."""
-    import threading
-    streams = [torch.cuda.Stream() for _ in range(lanes)]
-    pls, outs = [], []
-    for st in streams:
-        pl = b200.Planner(algo, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0, semantics=sem)
-        pl.setGridMap(gm)
-        pl.set_stream(st.cuda_stream)
-        out = torch.empty(nq * 128, dtype=torch.uint8, device=ds.device)
-        pl.findPaths(ds, dg, results=out)  # warm-up: workspace allocation
-        pls.append(pl)
-        outs.append(out)
+    """Steady-state serving form of the batched planners (`b200.PlannerPool`): `lanes` planner handles on the same map, each
+    with its own CUDA stream and host thread, each running `rounds` batches back to back.  A batch's last straggling queries
+    then run beside the next batch's first queries instead of leaving the SMs idle.  Device-timed: one start event, one end
+    event per lane, the longest span counts.  Returns (ms, queries, identical) — identical: every batch's result block equals
+    the single-batch result bit for bit (status / lengths / costs; the per-query clock field excluded)."""
+    pool = b200.PlannerPool(gm, algo, lanes=lanes, resolution=0.1, lambda_heuristic=5.0, allocate_num=1000000, cost_weight=0.0, semantics=sem)
+    outs = [torch.empty(nq * 128, dtype=torch.uint8, device=ds.device) for _ in range(lanes * rounds)]
+    pool.find_paths_many([(ds, dg, outs[i]) for i in range(lanes)])  # warm-up: workspace allocation of every lane
     torch.cuda.synchronize()
     start = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in pool.streams]
     start.record()
-    for st in streams:
+    for st in pool.streams:
         st.wait_event(start)
-    errs = []
-
-    def lane(i):
-        try:
-            torch.cuda.set_device(ds.device)
-            for _ in range(rounds):
-                pls[i].findPaths(ds, dg, results=outs[i])
-            ends[i].record(streams[i])
-        except Exception as e:  # surfaced by the caller
-            errs.append(repr(e))
-
-    th = [threading.Thread(target=lane, args=(i,)) for i in range(lanes)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
+    pool.find_paths_many([(ds, dg, outs[i]) for i in range(lanes * rounds)])
+    for e, st in zip(ends, pool.streams):
+        e.record(st)
     torch.cuda.synchronize()
-    if errs:
-        raise RuntimeError("; ".join(errs))
     ms = max(start.elapsed_time(e) for e in ends)
     ref = dres_single.cpu().numpy().view(b200.RESULT_DTYPE)
     same = True
@@ -478,8 +455,7 @@ def run_pipelined(b200, torch, gm, algo, sem, ds, dg, nq, dres_single, rounds=3,
         got = out.cpu().numpy().view(b200.RESULT_DTYPE)
         for f in ("solved", "status", "n_path", "explored_nodes", "iter_num", "g_final", "path_length"):
             same = same and np.array_equal(ref[f], got[f])
-    for pl in pls:
-        pl.close()
+    pool.close()
     return ms, lanes * rounds * nq, bool(same)
 
 

@@ -113,3 +113,23 @@ def test_planners_on_their_own_streams_overlap_on_one_map(b200, po, synth, algo,
     pls[0].set_stream(None)  # back to the map's stream
     again, _ = pls[0].findPaths(s, g)
     assert np.array_equal(again["g_final"], want["g_final"])
+
+
+def test_planner_pool_runs_batches_on_lanes_in_order(b200, po, synth):
+    """b200.PlannerPool: five different batches over two lanes, host arrays in — every batch equals its single-handle run."""
+    gm, om, c = make_pair(b200, po, synth, "C3")
+    batches = []
+    for k in range(5):
+        s, g = synth.random_queries(20 + k, om.get_inflate_occupancy, c["origin"], c["size"], 300 + 50 * k, min_dist=3.0)
+        batches.append((s, g))
+    kw = dict(resolution=0.1, lambda_heuristic=5.0, allocate_num=200000, semantics="canonical")
+    pool = b200.PlannerPool(gm, "lazythetastar", lanes=2, **kw)
+    got = pool.find_paths_many(batches)
+    pool.close()
+    single = b200.Planner("lazythetastar", **kw)
+    single.setGridMap(gm)
+    for (s, g), (res, _) in zip(batches, got):
+        want, _ = single.findPaths(s, g)
+        assert len(res) == len(s)
+        for f in ("solved", "status", "n_path", "explored_nodes", "iter_num", "los_checks", "g_final", "path_length", "goal_coords"):
+            assert np.array_equal(res[f], want[f]), f
