@@ -122,6 +122,7 @@ ABI = [
     ("b200_planner_create", C.c_int, [C.c_char_p, C.POINTER(PlannerParams), _pp]),
     ("b200_planner_destroy", C.c_int, [_vp]),
     ("b200_planner_set_map", C.c_int, [_vp, _vp]),
+    ("b200_odom_to_camera_pose", C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     ("b200_planner_set_stream", C.c_int, [_vp, _vp]),
     ("b200_planner_set_cost_factor", C.c_int, [_vp, _dbl]),
     ("b200_planner_detect_collision", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i32)]),
@@ -210,7 +211,7 @@ class GridMap:
         self.origin, self.size, self.resolution = tuple(p.origin), tuple(p.size), p.resolution
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # (module globals are gone when this runs at interpreter exit)
             lib().b200_map_destroy(self.h)
             self.h = None
 
@@ -263,6 +264,12 @@ class GridMap:
             rows, cols, dev = depth.shape[0], depth.shape[1], 0
         _ck(lib().b200_map_update_depth(self.h, _ptr(depth), rows, cols, _d3(cam_pos), rot, dev, C.byref(fused)))
         return bool(fused.value)
+
+    def depthOdomCallback(self, depth, body_pos, body_q_wxyz):
+        """depthOdomCallback (grid_map.cpp:965-994) + the occupancy timer body: the camera pose is the body odometry composed with
+        cam2body_ and passed through the reference's matrix -> quaternion -> matrix round trip (`odom_to_camera_pose`)."""
+        cam_pos, _, cam_rot = odom_to_camera_pose(body_pos, body_q_wxyz)
+        return self.depthPoseCallback(depth, cam_pos, cam_rot)
 
     def getOccupancy(self, pos):
         """getOccupancy(Vector3d) (grid_map.h:339-348) for an (n,3) batch -> int8 {-1,0,1}."""
@@ -535,7 +542,7 @@ class Planner:
         self.map = None
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().b200_planner_destroy(self.h)
             self.h = None
 
@@ -657,6 +664,15 @@ class PlannerPool:
         if errs:
             raise errs[0]
         return out
+
+
+def odom_to_camera_pose(body_pos, body_q_wxyz):
+    """(camera position, camera quaternion w x y z, rotation 3x3) exactly as GridMap::depthOdomCallback + projectDepthImage derive
+    them from a body odometry (grid_map.cpp:965-982, :208) — host only, no GPU."""
+    q = (C.c_double * 4)(*[float(x) for x in body_q_wxyz])
+    cp, cq, cr = (C.c_double * 3)(), (C.c_double * 4)(), (C.c_double * 9)()
+    _ck(lib().b200_odom_to_camera_pose(_d3(body_pos), q, cp, cq, cr))
+    return np.array(cp[:]), np.array(cq[:]), np.array(cr[:]).reshape(3, 3)
 
 
 def distance_metrics(distances):

@@ -127,6 +127,61 @@ static int per_position(b200_map_t* m, const double* pos, int64_t n, T* out, siz
 extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
+
+// Host-only pose algebra of GridMap::depthOdomCallback (grid_map.cpp:965-982): body quaternion -> matrix, body2world *
+// cam2body_ (grid_map.cpp:91), camera_q_ = Quaterniond(rotation block), and the rotation projectDepthImage then derives from
+// camera_q_ (:208).  Quaternion <-> matrix in the published operation order of Eigen's QuaternionBase::toRotationMatrix and
+// quaternionbase_assign_impl<Matrix3>; products as ((a0 b0 + a1 b1) + a2 b2) + a3 b3, every operation separately rounded.
+static void quat_to_matrix(const double q[4], double m[9]) {  // q = (w, x, y, z)
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  m[0] = 1.0 - (tyy + tzz); m[1] = txy - twz; m[2] = txz + twy;
+  m[3] = txy + twz; m[4] = 1.0 - (txx + tzz); m[5] = tyz - twx;
+  m[6] = txz - twy; m[7] = tyz + twx; m[8] = 1.0 - (txx + tyy);
+}
+static void matrix_to_quat(const double m[9], double q[4]) {
+  double t = m[0] + m[4] + m[8];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    q[0] = 0.5 * t;
+    t = 0.5 / t;
+    q[1] = (m[7] - m[5]) * t;
+    q[2] = (m[2] - m[6]) * t;
+    q[3] = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+    q[1 + i] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m[3 * k + j] - m[3 * j + k]) * t;
+    q[1 + j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    q[1 + k] = (m[3 * k + i] + m[3 * i + k]) * t;
+  }
+}
+int b200_odom_to_camera_pose(const double body_pos[3], const double body_q_wxyz[4], double cam_pos[3], double cam_q_wxyz[4],
+                             double cam_rot[9]) {
+  REQUIRE(body_pos && body_q_wxyz && cam_pos && cam_q_wxyz && cam_rot, "NULL argument");
+  static const double c2b[4][4] = {{0.0, 0.0, 1.0, 0.0}, {-1.0, 0.0, 0.0, 0.0}, {0.0, -1.0, 0.0, -0.02}, {0.0, 0.0, 0.0, 1.0}};  // :91
+  double B[9], R[9];
+  quat_to_matrix(body_q_wxyz, B);
+  for (int i = 0; i < 3; ++i) {
+    const double row[4] = {B[3 * i], B[3 * i + 1], B[3 * i + 2], body_pos[i]};  // body2world row i
+    for (int j = 0; j < 4; ++j) {
+      double acc = row[0] * c2b[0][j];
+      for (int k = 1; k < 4; ++k) acc = acc + row[k] * c2b[k][j];
+      if (j < 3) R[3 * i + j] = acc; else cam_pos[i] = acc;
+    }
+  }
+  matrix_to_quat(R, cam_q_wxyz);
+  quat_to_matrix(cam_q_wxyz, cam_rot);
+  return B200_OK;
+}
 const char* b200_version(void) { return "b200-planner 0.1 (sm_100a)"; }
 
 int b200_host_alloc(void** ptr, int64_t bytes) {

@@ -166,21 +166,15 @@ class GridMap {
     return fused != 0;
   }
   // depthOdomCallback (grid_map.cpp:965-994): the camera pose is the body odometry composed with cam2body_
-  // (grid_map.cpp:91: rows (0,0,1,0), (-1,0,0,0), (0,-1,0,-0.02), (0,0,0,1)).  The reference goes matrix -> quaternion
-  // -> matrix (Eigen) and fuses even when the camera is outside the map (undefined there); here the rotation is used
-  // as composed and such a frame is dropped like in depthPoseCallback.
+  // (grid_map.cpp:91) and then goes matrix -> quaternion -> matrix like the reference's md_.camera_q_ (:982, :208);
+  // b200_odom_to_camera_pose restates that algebra in Eigen's operation order (pinned to the reference's own
+  // depthOdomCallback in tests/test_oracle_vs_ref.py).  A frame whose camera is outside the map is dropped like in
+  // depthPoseCallback (the reference fuses it: undefined behaviour there).
   bool depthOdomCallback(const uint16_t* depth, int rows, int cols, const Vec3d& body_pos, double qw, double qx, double qy, double qz) {
-    const double B[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw),     2 * (qx * qz + qy * qw),
-                         2 * (qx * qy + qz * qw),     1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
-                         2 * (qx * qz - qy * qw),     2 * (qy * qz + qx * qw),     1 - 2 * (qx * qx + qy * qy)};
-    static const double C[9] = {0, 0, 1, -1, 0, 0, 0, -1, 0};  // rotation block of cam2body_
-    static const double tc[3] = {0.0, 0.0, -0.02};             // its translation column
-    double R[9], t[3];
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) R[3 * i + j] = B[3 * i] * C[j] + B[3 * i + 1] * C[3 + j] + B[3 * i + 2] * C[6 + j];
-      t[i] = B[3 * i] * tc[0] + B[3 * i + 1] * tc[1] + B[3 * i + 2] * tc[2] + body_pos(i);
-    }
-    return depthPoseCallback(depth, rows, cols, Vec3d(t[0], t[1], t[2]), R);
+    const double p[3] = {body_pos(0), body_pos(1), body_pos(2)}, q[4] = {qw, qx, qy, qz};
+    double cp[3], cq[4], R[9];
+    b200_check(b200_odom_to_camera_pose(p, q, cp, cq, R), "depthOdomCallback");
+    return depthPoseCallback(depth, rows, cols, Vec3d(cp[0], cp[1], cp[2]), R);
   }
 #ifdef B200_WITH_ROS
   void depthPoseCallback(const sensor_msgs::ImageConstPtr& img, const geometry_msgs::PoseStampedConstPtr& pose) {

@@ -780,10 +780,12 @@ def main():
                             "efficiency_vs_mean_rank_rate": qps / (world * float(np.mean(own_rates))),
                             "slowest_over_fastest_rank_time": float(max(own_rates) / min(own_rates))}
             # ---- the same batches in steady-state serving form: several planner handles / streams / host threads on the one map,
-            # so one batch's stragglers overlap other batches' work.  Canonical: 2 in flight, 3 batches each.  Faithful: 4 in
-            # flight, 1 each — there a batch lasts as long as its one reference-pathological query while 90 % of the slots idle.
+            # so one batch's stragglers overlap other batches' work.  Canonical: 4 in flight, 2 batches each (two lanes hide the
+            # tail of an ordinary batch, four also that of a shard whose longest query alone outlasts the rest of its batch).
+            # Faithful: 4 in flight, 1 each — there a batch lasts as long as its one reference-pathological query while 90 % of
+            # the slots idle.
             if True:
-                p_lanes, p_rounds = (2, 3) if sem == "canonical" else (4, 1)
+                p_lanes, p_rounds = (4, 2) if sem == "canonical" else (4, 1)  # lanes measured in profiles/prof_lanes.py
                 p_ms, p_q, p_same = run_pipelined(b200, torch, gm, algo, sem, ds, dg, nq, dres, rounds=p_rounds, lanes=p_lanes)
                 own_p = p_q / (p_ms * 1e-3)
                 p_rates = [own_p]

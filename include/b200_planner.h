@@ -209,6 +209,12 @@ int b200_map_path_distance_metrics(b200_map_t* map, const double* path_xyz, int6
 /* The host half of it on its own (no GPU): {mean, std_dev, min, max} of n distances exactly as
  * calculateDistancesMetrics (src/utils/metrics.cpp:62-97) computes them. */
 int b200_distance_metrics(const double* distances, int64_t n, double out_mean_std_min_max[4]);
+/* Host-only (no device work): the pose algebra of GridMap::depthOdomCallback (grid_map.cpp:965-982).  body odometry
+ * (position, quaternion w x y z) -> camera position, md_.camera_q_ (w x y z) and the row-major rotation projectDepthImage
+ * derives from it (:208) — body quaternion -> matrix, body2world * cam2body_ (:91), matrix -> quaternion -> matrix, in Eigen's
+ * published operation order.  Feed cam_pos / cam_rot to b200_map_update_depth. */
+int b200_odom_to_camera_pose(const double body_pos[3], const double body_q_wxyz[4], double cam_pos[3], double cam_q_wxyz[4],
+                             double cam_rot[9]);
 int b200_map_download_costq(b200_map_t* map, uint16_t* dst);
 int b200_map_download_cost(b200_map_t* map, float* dst);
 

@@ -45,6 +45,7 @@ def lib():
         L.ref_set_param.argtypes = [C.c_char_p, C.c_double]
         L.ref_map_update_depth.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, dp]
         L.ref_map_update_depth.restype = C.c_int
+        L.ref_map_depth_odom_pose.argtypes = [vp, dp, dp, dp, dp]
         L.ref_map_download_occupancy.argtypes = [vp, vp]
         L.ref_map_raycast_num.argtypes = [vp]
         L.ref_map_raycast_num.restype = C.c_int
@@ -147,6 +148,13 @@ class RefMap:
         r = lib().ref_map_update_depth(self.h, _ptr(depth), depth.shape[0], depth.shape[1], _d3(cam_pos), q,
                                        rot.ctypes.data_as(C.POINTER(C.c_double)))
         return bool(r), rot.reshape(3, 3)
+
+    def depth_odom_pose(self, body_pos, body_q_wxyz):
+        """depthOdomCallback's pose algebra (grid_map.cpp:965-982): (camera position, camera quaternion w x y z)."""
+        q = (C.c_double * 4)(*[float(x) for x in body_q_wxyz])
+        cp, cq = (C.c_double * 3)(), (C.c_double * 4)()
+        lib().ref_map_depth_odom_pose(self.h, _d3(body_pos), q, cp, cq)
+        return np.array(cp[:]), np.array(cq[:])
 
     def occupancy(self):
         out = np.empty(self.dims, dtype=np.float64)

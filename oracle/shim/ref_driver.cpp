@@ -186,6 +186,24 @@ int ref_map_update_depth(void* h, const uint16_t* depth, int rows, int cols, con
   g.updateOccupancyCallback(ros::TimerEvent());
   return fused;
 }
+// GridMap::depthOdomCallback (grid_map.cpp:965-994) with a 1x1 image: the camera pose the reference derives from a body
+// odometry (quaternion -> matrix, body2world * cam2body_, matrix -> quaternion).  Marks the map for an occupancy update with
+// that 1x1 image: use a scratch map.
+void ref_map_depth_odom_pose(void* h, const double body_pos[3], const double body_q_wxyz[4], double cam_pos[3], double cam_q_wxyz[4]) {
+  Silence s;
+  GridMap& g = *((RefMap*)h)->gm;
+  auto img = std::make_shared<sensor_msgs::Image>();
+  img->height = 1; img->width = 1;
+  img->encoding = sensor_msgs::image_encodings::TYPE_16UC1;
+  img->data.assign(2, 0);
+  auto odom = std::make_shared<nav_msgs::Odometry>();
+  odom->pose.pose.position.x = body_pos[0]; odom->pose.pose.position.y = body_pos[1]; odom->pose.pose.position.z = body_pos[2];
+  odom->pose.pose.orientation.w = body_q_wxyz[0]; odom->pose.pose.orientation.x = body_q_wxyz[1];
+  odom->pose.pose.orientation.y = body_q_wxyz[2]; odom->pose.pose.orientation.z = body_q_wxyz[3];
+  g.depthOdomCallback(img, odom);
+  for (int i = 0; i < 3; ++i) cam_pos[i] = g.md_.camera_pos_(i);
+  cam_q_wxyz[0] = g.md_.camera_q_.w_; cam_q_wxyz[1] = g.md_.camera_q_.x_; cam_q_wxyz[2] = g.md_.camera_q_.y_; cam_q_wxyz[3] = g.md_.camera_q_.z_;
+}
 void ref_map_download_occupancy(void* h, double* dst) {
   const auto& b = ((RefMap*)h)->gm->md_.occupancy_buffer_;
   std::memcpy(dst, b.data(), b.size() * sizeof(double));

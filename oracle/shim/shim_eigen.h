@@ -196,20 +196,46 @@ class Quaternion {
   T w_, x_, y_, z_;
   Quaternion() {}
   Quaternion(T w, T x, T y, T z) : w_(w), x_(x), y_(y), z_(z) {}
+  // matrix -> quaternion in the operation order of Eigen 3.3 / 3.4's quaternionbase_assign_impl<Other, 3, 3> (the published
+  // algorithm: trace branch with t = sqrt(trace + 1), w = t / 2, t = 0.5 / t, differences TIMES t; else the largest
+  // diagonal element i, j = (i + 1) % 3, k = (j + 1) % 3) — used by depthOdomCallback (grid_map.cpp:982)
   explicit Quaternion(const Matrix<T, 3, 3>& m) {
-    T tr = m(0, 0) + m(1, 1) + m(2, 2);
-    if (tr > 0) { T s = std::sqrt(tr + 1) * 2; w_ = s / 4; x_ = (m(2, 1) - m(1, 2)) / s; y_ = (m(0, 2) - m(2, 0)) / s; z_ = (m(1, 0) - m(0, 1)) / s; }
-    else if (m(0, 0) > m(1, 1) && m(0, 0) > m(2, 2)) { T s = std::sqrt(1 + m(0, 0) - m(1, 1) - m(2, 2)) * 2; w_ = (m(2, 1) - m(1, 2)) / s; x_ = s / 4; y_ = (m(0, 1) + m(1, 0)) / s; z_ = (m(0, 2) + m(2, 0)) / s; }
-    else if (m(1, 1) > m(2, 2)) { T s = std::sqrt(1 + m(1, 1) - m(0, 0) - m(2, 2)) * 2; w_ = (m(0, 2) - m(2, 0)) / s; x_ = (m(0, 1) + m(1, 0)) / s; y_ = s / 4; z_ = (m(1, 2) + m(2, 1)) / s; }
-    else { T s = std::sqrt(1 + m(2, 2) - m(0, 0) - m(1, 1)) * 2; w_ = (m(1, 0) - m(0, 1)) / s; x_ = (m(0, 2) + m(2, 0)) / s; y_ = (m(1, 2) + m(2, 1)) / s; z_ = s / 4; }
+    T t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > T(0)) {
+      t = std::sqrt(t + T(1.0));
+      w_ = T(0.5) * t;
+      t = T(0.5) / t;
+      x_ = (m(2, 1) - m(1, 2)) * t;
+      y_ = (m(0, 2) - m(2, 0)) * t;
+      z_ = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1.0));
+      T v[3];
+      v[i] = T(0.5) * t;
+      t = T(0.5) / t;
+      w_ = (m(k, j) - m(j, k)) * t;
+      v[j] = (m(j, i) + m(i, j)) * t;
+      v[k] = (m(k, i) + m(i, k)) * t;
+      x_ = v[0]; y_ = v[1]; z_ = v[2];
+    }
   }
   template <int R, int C>
   explicit Quaternion(const BlockRef<T, R, C, 3, 3>& b) : Quaternion((Matrix<T, 3, 3>)b) {}
+  // QuaternionBase::toRotationMatrix in Eigen's operation order (tx = 2x, twx = tx * w, ...); bit-equal to the textbook
+  // form 1 - 2 (yy + zz), 2 (xy - zw), ... because scaling by two is exact
   Matrix<T, 3, 3> toRotationMatrix() const {
     Matrix<T, 3, 3> m;
-    m(0, 0) = 1 - 2 * (y_ * y_ + z_ * z_); m(0, 1) = 2 * (x_ * y_ - z_ * w_); m(0, 2) = 2 * (x_ * z_ + y_ * w_);
-    m(1, 0) = 2 * (x_ * y_ + z_ * w_); m(1, 1) = 1 - 2 * (x_ * x_ + z_ * z_); m(1, 2) = 2 * (y_ * z_ - x_ * w_);
-    m(2, 0) = 2 * (x_ * z_ - y_ * w_); m(2, 1) = 2 * (y_ * z_ + x_ * w_); m(2, 2) = 1 - 2 * (x_ * x_ + y_ * y_);
+    const T tx = T(2) * x_, ty = T(2) * y_, tz = T(2) * z_;
+    const T twx = tx * w_, twy = ty * w_, twz = tz * w_;
+    const T txx = tx * x_, txy = ty * x_, txz = tz * x_;
+    const T tyy = ty * y_, tyz = tz * y_, tzz = tz * z_;
+    m(0, 0) = T(1) - (tyy + tzz); m(0, 1) = txy - twz; m(0, 2) = txz + twy;
+    m(1, 0) = txy + twz; m(1, 1) = T(1) - (txx + tzz); m(1, 2) = tyz - twx;
+    m(2, 0) = txz - twy; m(2, 1) = tyz + twx; m(2, 2) = T(1) - (txx + tyy);
     return m;
   }
   Quaternion inverse() const { T n = w_ * w_ + x_ * x_ + y_ * y_ + z_ * z_; return Quaternion(w_ / n, -x_ / n, -y_ / n, -z_ / n); }

@@ -116,3 +116,38 @@ def test_path_distance_metrics_arithmetic_matches_reference():
     for d in cases:
         m = b200.distance_metrics(d)
         assert (m["mean"], m["std"], m["min"], m["max"]) == pr.distance_metrics(d)
+
+
+def test_depth_odom_pose_algebra_matches_reference():
+    """depthOdomCallback (grid_map.cpp:965-982): body odometry -> camera position and md_.camera_q_ — the product's host
+    arithmetic (b200_odom_to_camera_pose, pure host code in the C-ABI library) against the reference's own callback on random
+    orientations, rotations near 180 degrees about every axis (the three non-trace branches of matrix -> quaternion),
+    axis-aligned ones and unnormalised quaternions; bit for bit."""
+    import astar_planners_b200 as b200
+    rm = pr.RefMap((4.0, 4.0, 2.0), 0.1)  # scratch map: the callback stores a 1x1 image in it
+    rng = np.random.default_rng(12)
+    quats = [q / np.linalg.norm(q) for q in rng.normal(size=(300, 4))]
+    for ax in range(3):  # near-pi rotations: trace <= 0, largest diagonal element = ax
+        for _ in range(40):
+            v = rng.normal(size=3) * 0.05
+            v[ax] = 1.0
+            v /= np.linalg.norm(v)
+            ang = np.pi - abs(rng.normal()) * 0.02
+            quats.append(np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * v]))
+    quats += [np.array(q, dtype=np.float64) for q in ((1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (0.5, 0.5, 0.5, 0.5),
+                                                      (np.sqrt(0.5), 0, 0, np.sqrt(0.5)), (0.9, 0.1, -0.3, 0.2), (2.0, 0.0, 0.0, 0.1))]
+    branches = set()
+    for q in quats:
+        pos = rng.normal(size=3) * 3.0
+        cp, cq = rm.depth_odom_pose(pos, q)
+        gp, gq, gr = b200.odom_to_camera_pose(pos, q)
+        assert np.array_equal(cp.view(np.uint64), gp.view(np.uint64)), (q, cp, gp)
+        assert np.array_equal(cq.view(np.uint64), gq.view(np.uint64)), (q, cq, gq)
+        w, x, y, z = gq  # the rotation projectDepthImage derives (:208): Eigen's toRotationMatrix order, restated here
+        tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+        twx, twy, twz, txx, txy, txz, tyy, tyz, tzz = tx * w, ty * w, tz * w, tx * x, ty * x, tz * x, ty * y, tz * y, tz * z
+        want = np.array([[1.0 - (tyy + tzz), txy - twz, txz + twy], [txy + twz, 1.0 - (txx + tzz), tyz - twx],
+                         [txz - twy, tyz + twx, 1.0 - (txx + tyy)]])
+        assert np.array_equal(want.view(np.uint64), gr.view(np.uint64))
+        branches.add("trace" if gq[0] >= 0.5 * np.sqrt(1e-30) and abs(gq[0]) == max(abs(gq)) else int(np.argmax(np.abs(gq[1:]))))
+    assert {0, 1, 2} <= branches and "trace" in branches
