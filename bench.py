@@ -571,6 +571,10 @@ def main():
         # Untimed warm-up until the frame time has settled: on these (virtualised) boxes the first ~50 DMA reads of a freshly
         # pinned buffer run at 15-25 GB/s and only then at the link's 54 GB/s (profiles/diag_h2d.py), so three warm-up frames
         # would time the host's page-mapping warm-up, not the path.  At least max(warmup, 5) frames, at most 200 (~0.2 s).
+        if buf is h_cloud_np:  # plain copies first: they warm the buffer's DMA path without running the frame
+            for _ in range(64):
+                d_cloud.copy_(h_cloud, non_blocking=True)
+            torch.cuda.synchronize()
         hist = []
         for i in range(200):
             torch.cuda.synchronize()
@@ -578,7 +582,7 @@ def main():
             frame_host(buf)
             torch.cuda.synchronize()
             hist.append(time.perf_counter() - t0)
-            if i + 1 >= max(args.warmup, 10) and max(hist[-5:]) <= 1.03 * min(hist):
+            if i + 1 >= max(args.warmup, 20) and max(hist[-8:]) <= 1.03 * min(hist):
                 break
         barrier()
         ts = []
