@@ -1408,7 +1408,8 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   int* overflow_list = (int*)((char*)pl->ctl.p + 64);
   // Promotion slots: the canonical 32-thread kernels move a query that outgrows tier 0 into a full-size workspace and go
   // on (search_kernels.cu promote_slot) instead of reporting it for a re-run from scratch.  They are tier 1 allocated up
-  // front (<= 32 slots, <= a quarter of the free memory); without them everything works as before, through the re-run.
+  // front (<= 32 slots, <= 4 GB and a quarter of the free memory, at least one); without them everything works as before,
+  // through the re-run.
   const bool can_promote = !pl->faithful && tpb == 32 && pl->tier[0].cap < pl->prm.allocate_num;
   if (can_promote && !(pl->tier[1].base && pl->tier[1].cap == pl->prm.allocate_num)) {
     size_t free_b = 0, total_b = 0;
@@ -1416,7 +1417,8 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
     const size_t slot_b = search_slot_bytes(pl->prm.allocate_num, factor, nullptr);
     const char* cap_env = getenv("B200_PROMO_SLOTS");  // testing / tuning knob: upper bound on the promotion slots (0 = none)
     const size_t max_promo = cap_env ? (size_t)std::max(0, atoi(cap_env)) : 32;
-    const int want = (int)std::min<size_t>({max_promo, (size_t)pl->tier[0].slots, (free_b / 4) / std::max<size_t>(slot_b, 1)});
+    const size_t budget = std::min<size_t>(free_b / 4, (size_t)4 << 30);  // 32 slots of a 1 M-node workspace are 3.6 GB
+    const int want = (int)std::min<size_t>({max_promo, (size_t)pl->tier[0].slots, std::max<size_t>(1, budget / std::max<size_t>(slot_b, 1))});
     if (want >= 1 && tier_alloc(pl->tier[1], pl->prm.allocate_num, want, factor)) cudaGetLastError();  // no memory: no promotion
   }
 
