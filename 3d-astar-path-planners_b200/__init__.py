@@ -124,6 +124,8 @@ ABI = [
     ("b200_planner_set_map", C.c_int, [_vp, _vp]),
     ("b200_odom_to_camera_pose", C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     ("b200_planner_set_stream", C.c_int, [_vp, _vp]),
+    ("b200_stream_create", C.c_int, [_i32, _pp]),
+    ("b200_stream_destroy", C.c_int, [_vp]),
     ("b200_planner_set_cost_factor", C.c_int, [_vp, _dbl]),
     ("b200_planner_detect_collision", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i32)]),
     ("b200_planner_find_path", C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _i64]),

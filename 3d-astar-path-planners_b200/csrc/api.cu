@@ -184,6 +184,19 @@ int b200_odom_to_camera_pose(const double body_pos[3], const double body_q_wxyz[
 }
 const char* b200_version(void) { return "b200-planner 0.1 (sm_100a)"; }
 
+// streams for hosts that do not link the CUDA runtime themselves (the reference's ROS node does not)
+int b200_stream_create(int32_t device, void** out) {
+  REQUIRE(out, "NULL argument");
+  CK(cudaSetDevice(device));
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *out = (void*)st;
+  return B200_OK;
+}
+int b200_stream_destroy(void* stream) {
+  if (stream) CK(cudaStreamDestroy((cudaStream_t)stream));
+  return B200_OK;
+}
 int b200_host_alloc(void** ptr, int64_t bytes) {
   REQUIRE(ptr && bytes >= 0, "b200_host_alloc: bad args");
   CK(cudaMallocHost(ptr, (size_t)bytes));

@@ -25,7 +25,10 @@ using HeuristicFunction = std::function<unsigned int(Vec3d, Vec3d)>;
 class AlgorithmBase {
  public:
   explicit AlgorithmBase(const std::string& name) : algorithm_name_(name) {}
-  virtual ~AlgorithmBase() { if (h_) b200_planner_destroy(h_); }
+  virtual ~AlgorithmBase() {
+    if (h_) b200_planner_destroy(h_);
+    if (own_stream_) b200_stream_destroy(own_stream_);
+  }
   enum { REACH_HORIZON = 1, REACH_END = 2, NO_PATH = 3, NEAR_END = 4 };
 
   void setGridMap(GridMap::Ptr& grid_map) {
@@ -55,6 +58,13 @@ class AlgorithmBase {
     if (h_) { b200_planner_destroy(h_); h_ = nullptr; }
     b200_check(b200_planner_create(algorithm_name_.c_str(), &prm_, &h_), "init");
     if (grid_map_) b200_check(b200_planner_set_map(h_, grid_map_->handle()), "init/set_map");
+    if (own_stream_) b200_check(b200_planner_set_stream(h_, own_stream_), "init/set_stream");
+  }
+  // new: give this planner a CUDA stream of its own (after init()), so that planners bound to the same GridMap and driven
+  // from different threads overlap their batches on the device (b200_planner_set_stream); the map must be up to date first
+  void useOwnStream(int device = 0) {
+    if (!own_stream_) b200_check(b200_stream_create(device, &own_stream_), "useOwnStream");
+    b200_check(b200_planner_set_stream(h_, own_stream_), "useOwnStream");
   }
   // AlgorithmBase.cpp:17-32 — per-query state lives on the device and is reset by every findPath
   void reset() { path_.clear(); }
@@ -141,6 +151,7 @@ class AlgorithmBase {
   const std::string algorithm_name_;
   b200_planner_params_t prm_{};
   b200_planner_t* h_ = nullptr;
+  void* own_stream_ = nullptr;
   std::vector<Vec3d> path_;
   b200_path_result_t last_{};
 };

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 
 #include "b200_planners.hpp"
 
@@ -53,6 +54,57 @@ int main(int argc, char** argv) {
                   gm->getOccupancy(Vec3d(1.0, 0.0, 1.0)), gm->getOccupancy(Vec3d(100.0, 0.0, 1.0)), (long long)st[0], (long long)st[1],
                   (long long)st[2], (long long)st[3], gm->hasDepthObservation() ? 1 : 0);
       return 0;
+    }
+    else if (name == "pool") {
+      // three LazyThetaStar planners on ONE map, each on a stream of its own and driven by its own thread, two batches
+      // each: every batch must equal the batch a single planner computes on the map's stream
+      GridMap::Ptr gm(new GridMap);
+      gm->initMap(nh);
+      std::vector<float> cloud;
+      for (int j = 40; j < 88; ++j)
+        for (int k = 0; k < 32; ++k) { cloud.push_back(0.05f); cloud.push_back(-6.4f + (j + 0.5f) * 0.1f); cloud.push_back(-0.01f + (k + 0.5f) * 0.1f); cloud.push_back(0.f); }
+      gm->odomCallback(Vec3d(0, 0, 1));
+      gm->cloudCallback(cloud.data(), (int64_t)cloud.size() / 4, 16);
+      std::vector<Vec3d> src, dst;
+      for (int i = 0; i < 400; ++i) {
+        src.push_back(Vec3d(-5.0 + 0.01 * i, -4.0 + 0.02 * i, 0.5 + 0.004 * i));
+        dst.push_back(Vec3d(5.0 - 0.015 * i, 4.0 - 0.018 * i, 2.5 - 0.004 * i));
+      }
+      auto make = [&]() {
+        std::unique_ptr<Planners::LazyThetaStar> p(new Planners::LazyThetaStar());
+        p->setParam(nh);
+        p->setGridMap(gm);
+        p->init();
+        return p;
+      };
+      auto base = make();
+      std::vector<b200_path_result_t> want;
+      std::vector<double> want_path;
+      base->findPaths(src, dst, want, want_path, 400 * 256);
+      b200_map_sync(gm->handle());
+      const int lanes = 3;
+      std::vector<std::unique_ptr<Planners::LazyThetaStar>> pl;
+      for (int l = 0; l < lanes; ++l) { pl.push_back(make()); pl.back()->useOwnStream(0); }
+      std::vector<int> bad(lanes, 0);
+      std::vector<std::thread> th;
+      for (int l = 0; l < lanes; ++l)
+        th.emplace_back([&, l]() {
+          for (int rep = 0; rep < 2; ++rep) {
+            std::vector<b200_path_result_t> got;
+            std::vector<double> got_path;
+            pl[l]->findPaths(src, dst, got, got_path, 400 * 256);
+            for (size_t i = 0; i < got.size(); ++i)
+              if (got[i].solved != want[i].solved || got[i].n_path != want[i].n_path || got[i].g_final != want[i].g_final ||
+                  got[i].path_length != want[i].path_length || got[i].explored_nodes != want[i].explored_nodes)
+                ++bad[l];
+          }
+        });
+      for (auto& t : th) t.join();
+      int solved = 0, mism = 0;
+      for (const auto& r : want) solved += r.solved;
+      for (int b : bad) mism += b;
+      std::printf("{\"mode\": \"pool\", \"lanes\": %d, \"queries\": %zu, \"solved\": %d, \"mismatches\": %d}\n", lanes, want.size(), solved, mism);
+      return mism ? 4 : 0;
     }
     else algorithm.reset(new Planners::AStar());
     algorithm->setCostFactor(2.0f);

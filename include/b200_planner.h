@@ -303,6 +303,10 @@ int b200_planner_set_map(b200_planner_t* planner, b200_map_t* map);
  * beside the first queries of the next instead of leaving the SMs idle.  The caller orders the stream after the map's
  * last write (b200_map_sync, or an event on the map's stream). */
 int b200_planner_set_stream(b200_planner_t* planner, void* cuda_stream);
+/* NEW: a non-blocking CUDA stream on `device` for callers that do not link the CUDA runtime (the reference's node does not);
+ * pass it to b200_planner_set_stream / b200_map_set_stream, destroy it after the handles that use it. */
+int b200_stream_create(int32_t device, void** cuda_stream_out);
+int b200_stream_destroy(void* cuda_stream);
 /* AlgorithmBase::setCostFactor (AlgorithmBase.hpp:39) */
 int b200_planner_set_cost_factor(b200_planner_t* planner, double cost_weight);
 /* AlgorithmBase::detectCollision (AlgorithmBase.cpp:38-44): *collides = bool(getInflateOccupancy(pos)). */

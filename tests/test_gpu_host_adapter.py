@@ -87,3 +87,15 @@ def test_cpp_adapter_depth_path(b200, po):
     assert want["wall_occupancy"] == 1 and want["wall_inflated"] == 1 and want["free_occupancy"] == 0
     for k, v in want.items():
         assert d[k] == v, (k, d[k], v)
+
+
+def test_cpp_adapter_planners_on_their_own_streams(b200):
+    """AlgorithmBase::useOwnStream of the C++ adapter: three LazyThetaStar planners on one GridMap, three std::threads, two batches
+    each — every batch identical to the single-planner batch (b200_stream_create / b200_planner_set_stream through the adapter)."""
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(EXE)])
+    out = subprocess.run([EXE, "pool"], capture_output=True, text=True, timeout=120)
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert "error" not in d, d
+    assert d["mode"] == "pool" and d["lanes"] == 3 and d["queries"] == 400
+    assert d["mismatches"] == 0 and d["solved"] > 300 and out.returncode == 0
