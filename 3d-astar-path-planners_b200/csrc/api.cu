@@ -1384,7 +1384,8 @@ int b200_planner_find_paths(b200_planner_t* pl, const double* starts, const doub
   // tier 0 holds 32 768 nodes per slot when that fits in a quarter of the free memory (a rerun in tier 1 costs a
   // second launch that waits for the first: 2 of 131 072 Lazy Theta* queries needed > 16 384 nodes and their
   // rerun took 75 of 290 ms), else 16 384, else fewer slots
-  int cap0 = std::min(pl->prm.allocate_num, 32768);
+  static const int cap0_env = getenv("B200_TIER0_CAP") ? atoi(getenv("B200_TIER0_CAP")) : 0;  // tuning knob
+  int cap0 = std::min(pl->prm.allocate_num, cap0_env >= 1024 ? cap0_env : 32768);
   if (!(pl->tier[0].base && pl->tier[0].cap == cap0 && pl->tier[0].slots >= slots0)) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));

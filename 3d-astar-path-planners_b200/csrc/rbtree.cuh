@@ -268,19 +268,27 @@ struct RbSet {
     if (x != RB_NIL) {
       // Per level the key of the node and BOTH child nodes are requested together (all three addresses come from the node
       // in hand), so a level costs one memory round trip instead of two dependent ones; the child not taken is a wasted
-      // load on a lane that is waiting anyway.
-      TreeNode n = t.load(x);
+      // load on a lane that is waiting anyway.  The loop body is kept to what a level needs: the colour bit is masked in 32
+      // bits before the key address is formed (one LOP + one IMAD.WIDE; the compiler's own 64-bit form took six), the
+      // comparison is (fv < fx) || (fv == fx && v < xv) on predicates, and only left / right / vc of the chosen child move.
+      uint32_t nleft, nright, nvc;
+      {
+        const TreeNode n = t.load(x);
+        nleft = n.left; nright = n.right; nvc = n.vc;
+      }
       for (;;) {
         y = x;
-        const uint32_t xv = n.vc & ~RB_RED;
+        uint32_t xv;
+        asm("and.b32 %0, %1, 0x7fffffff;" : "=r"(xv) : "r"(nvc));  // opaque on purpose: keeps the mask out of the 64-bit address arithmetic
         const double fx = fk.get(xv);
-        TreeNode nl = n, nr = n;
-        if (n.left != RB_NIL) nl = t.load(n.left);
-        if (n.right != RB_NIL) nr = t.load(n.right);
-        comp = (fv != fx) ? fv < fx : v < xv;
-        x = comp ? n.left : n.right;
+        // (a missing child loads the header instead: unconditional loads, and what they return is never used — the loop
+        // ends on x == RB_NIL before)
+        const TreeNode cl = t.load(nleft != RB_NIL ? nleft : RB_HEADER), cr = t.load(nright != RB_NIL ? nright : RB_HEADER);
+        const uint32_t ll = cl.left, lr = cl.right, lv = cl.vc, rl = cr.left, rr = cr.right, rv = cr.vc;
+        comp = (fv < fx) || (fv == fx && v < xv);
+        x = comp ? nleft : nright;
         if (x == RB_NIL) break;
-        n = comp ? nl : nr;
+        nleft = comp ? ll : rl; nright = comp ? lr : rr; nvc = comp ? lv : rv;
       }
     }
     uint32_t j = y;
