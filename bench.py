@@ -49,7 +49,8 @@ class ClockSampler:
     def __init__(self, index, uuid=None):
         self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
         self.sm, self.reasons, self.max_mhz, self.nvml, self.stop_flag = [], set(), None, None, False
-        self.interval = 0.002  # seconds between NVML polls; raised for host-facing regions (see main)
+        # seconds between NVML polls; raised for host-facing regions (see main).  B200_BENCH_POLL_MS overrides (diagnostic).
+        self.interval = float(os.environ.get("B200_BENCH_POLL_MS", "2")) * 1e-3
 
     def _nvml_handle(self):
         import pynvml
