@@ -627,15 +627,15 @@ class PlannerPool:
     plans one query at a time on the caller's thread.  Results are bit-identical to the single-handle run."""
 
     def __init__(self, grid_map, algorithm="astar", lanes=2, **planner_kw):
-        import torch  # streams only; the work is the C-ABI's
-        self._torch = torch
         self.lanes = int(lanes)
-        self.streams = [torch.cuda.Stream(device=int(grid_map.params.device)) for _ in range(self.lanes)]
-        self.planners = []
-        for st in self.streams:
+        self.streams, self.planners = [], []  # streams: raw cudaStream_t values (b200_stream_create: no CUDA runtime binding needed)
+        for _ in range(self.lanes):
+            st = C.c_void_p()
+            _ck(lib().b200_stream_create(int(grid_map.params.device), C.byref(st)))
+            self.streams.append(st.value)
             pl = Planner(algorithm, **planner_kw)
             pl.setGridMap(grid_map)
-            pl.set_stream(st.cuda_stream)
+            pl.set_stream(st.value)
             self.planners.append(pl)
         grid_map.sync()  # the lanes' streams start after whatever built the map
 
@@ -643,6 +643,12 @@ class PlannerPool:
         for pl in self.planners:
             pl.close()
         self.planners = []
+        if lib is not None:
+            for st in self.streams:
+                lib().b200_stream_destroy(C.c_void_p(st))
+        self.streams = []
+
+    __del__ = close
 
     def find_paths_many(self, batches, **kw):
         """batches: list of (starts, goals[, results]) — host arrays, or CUDA tensors with a preallocated results tensor.

@@ -441,13 +441,14 @@ def run_pipelined(b200, torch, gm, algo, sem, ds, dg, nq, dres_single, rounds=3,
     outs = [torch.empty(nq * 128, dtype=torch.uint8, device=ds.device) for _ in range(lanes * rounds)]
     pool.find_paths_many([(ds, dg, outs[i]) for i in range(lanes)])  # warm-up: workspace allocation of every lane
     torch.cuda.synchronize()
+    lane_streams = [torch.cuda.ExternalStream(st, device=ds.device) for st in pool.streams]  # the pool's own cudaStream_t's
     start = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in pool.streams]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in lane_streams]
     start.record()
-    for st in pool.streams:
+    for st in lane_streams:
         st.wait_event(start)
     pool.find_paths_many([(ds, dg, outs[i]) for i in range(lanes * rounds)])
-    for e, st in zip(ends, pool.streams):
+    for e, st in zip(ends, lane_streams):
         e.record(st)
     torch.cuda.synchronize()
     ms = max(start.elapsed_time(e) for e in ends)
