@@ -113,3 +113,41 @@ def test_slab_halo_exchange_three_ranks_gloo(tmp_path):
                 if len(upper):
                     above[x, y] = upper.min() - z_last
         assert np.array_equal(got["below"], below) and np.array_equal(got["above"], above)
+
+
+def test_planner_pool_schedules_batches_round_robin_and_in_order():
+    """Host logic of b200.PlannerPool.find_paths_many without a GPU: batch i runs on lane i % lanes, the batches of a lane in
+    submission order, results come back in batch order, and a failing lane's exception reaches the caller."""
+    import threading
+    import astar_planners_b200 as b200
+
+    class FakePlanner:
+        def __init__(self, lane, log, fail_on=None):
+            self.lane, self.log, self.fail_on = lane, log, fail_on
+
+        def findPaths(self, starts, goals, results=None, **kw):
+            if self.fail_on is not None and starts == self.fail_on:
+                raise RuntimeError("lane failure")
+            self.log.append((self.lane, starts, threading.get_ident()))
+            return ("res", starts, goals, results)
+
+        def close(self):
+            pass
+
+    log = []
+    pool = object.__new__(b200.PlannerPool)  # the constructor needs a device; the scheduling does not
+    pool.lanes, pool.streams = 3, []
+    pool.planners = [FakePlanner(l, log) for l in range(3)]
+    batches = [(i, -i) if i % 2 else (i, -i, f"out{i}") for i in range(8)]
+    out = pool.find_paths_many(batches)
+    assert [o[1] for o in out] == list(range(8)) and [o[2] for o in out] == [-i for i in range(8)]
+    assert [o[3] for o in out] == [None if i % 2 else f"out{i}" for i in range(8)]
+    for lane in range(3):
+        mine = [b for (l, b, _) in log if l == lane]
+        assert mine == [i for i in range(8) if i % 3 == lane]            # right lane, submission order
+        assert len({t for (l, _, t) in log if l == lane}) == 1            # one host thread per lane
+    assert pool.find_paths_many([]) == []
+    pool.planners = [FakePlanner(l, log, fail_on=4) for l in range(3)]
+    with pytest.raises(RuntimeError):
+        pool.find_paths_many(batches)
+    pool.planners = []
